@@ -1,0 +1,126 @@
+/*
+ * sbc.h -- C ABI of the B200 annealed-Langevin MIMO channel-estimation library (libsbc_b200.so).
+ *
+ * The reference (utcsilab/score-based-channels) is pure Python over torch and has no FFI of its
+ * own; each entry point below replaces the span of reference code cited next to it and is what a
+ * maintainer would bind with ctypes.  Plain pointers and sizes only -- no
+ * torch types.  All functions return 0 on success or a negative SBC_E_* code; the message of the
+ * last failure on the calling thread is available from sbc_last_error().  Nothing here falls back
+ * to a CPU implementation: without a CUDA device every compute entry point fails with SBC_E_CUDA.
+ *
+ * Threading / streams: every compute call only enqueues work on the caller's stream (a
+ * cudaStream_t passed as void*, NULL = legacy default stream); no hidden synchronisation, no
+ * allocation (workspaces are created in sbc_model_create).  A handle may be used from several
+ * streams as long as calls that share the handle's global-arena workspace (large Nt x Nr only, see
+ * sbc_info.arena_in_smem) are not concurrent.
+ *
+ * RNG contract (noise when ext_noise == NULL): Philox4x32-10, key = (seed lo, seed hi), counter =
+ * (element >> 1, level * steps_each + inner_step, sample_id lo, sample_id hi); the four 32-bit
+ * outputs give two Box-Muller pairs (u = ((r >> 8) + 0.5) * 2^-24), element 2k uses outputs 0,1 and
+ * element 2k+1 outputs 2,3; (re, im) = (r cos, r sin) / sqrt(2), i.e. CN(0,1) like
+ * torch.randn_like(complex) at reference test_score.py:161.  Results therefore depend only on
+ * (seed, sample_id), never on batch composition, launch geometry or GPU count.
+ */
+#ifndef SBC_H_
+#define SBC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBC_VERSION 100   /* 0.1.0 */
+
+enum {
+    SBC_OK = 0,
+    SBC_E_ARG = -1,      /* invalid argument (shape constraint, null pointer, ...) */
+    SBC_E_CUDA = -2,     /* CUDA runtime failure (message has the CUDA error string) */
+    SBC_E_NOMEM = -3,
+    SBC_E_UNSUPPORTED = -4
+};
+
+/* Packed model: the layer program + parameter blob produced by the host-side packer
+ * (score_based_channels_b200/program.py) from a reference state_dict.  Replaces
+ * `NCSNv2Deepest(config)` + `load_state_dict` + `.cuda()` (reference test_score.py:59-63). */
+typedef struct sbc_model_desc {
+    int32_t ngf;            /* config.model.ngf */
+    int32_t Nt, Nr;         /* network input is [B, channels, Nt, Nr] (reference test_score.py:149) */
+    int32_t channels;       /* 2 (re, im) */
+    const int32_t* op_table;/* host, [n_ops][24] int32 (csrc/sbc_program.h: SbcOp) */
+    int32_t n_ops;
+    const float* blob;      /* host, packed parameters */
+    int64_t blob_floats;
+    int32_t arena_floats;   /* per-sample activation arena size */
+    int32_t in_off, out_off, post_off;
+    int32_t max_w_len;      /* largest per-op parameter segment (floats) */
+    const float* sigmas;    /* host, [n_sigmas] fp32 noise schedule (reference ncsnv2/models/__init__.py:4-8) */
+    int32_t n_sigmas;
+    int64_t conv_flops;     /* dense conv FLOP / forward / sample (reported by sbc_query) */
+} sbc_model_desc;
+
+typedef struct sbc_info {
+    int32_t version;
+    int32_t device;
+    int32_t num_sms;
+    int32_t threads_per_cta;
+    int32_t arena_in_smem;      /* 1: activations never leave shared memory */
+    int32_t weights_staged;     /* 1: per-op parameters streamed with cp.async.bulk */
+    int64_t smem_bytes_per_cta;
+    int64_t arena_bytes;
+    int64_t conv_flops_per_forward;
+    int64_t kernel_launches;    /* launches issued through this handle so far */
+} sbc_info;
+
+/* One annealed-Langevin run over levels [level_begin, level_end) x steps_each for B independent
+ * channel realisations.  Replaces the loop body reference test_score.py:135-171 (duplicated at
+ * tune_hparams_score.py:112-148).  Per-sample noise_var / alpha_step / beta let one launch mix SNR
+ * points and hyper-parameter cells. */
+typedef struct sbc_ald_args {
+    int32_t B, Nt, Nr, Np;
+    int32_t level_begin, level_end, steps_each;
+    const void* P;            /* [B,Np,Nt] complex64: `forward` = val_P        (test_score.py:128) */
+    const void* Y;            /* [B,Np,Nr] complex64: `y` = val_Y              (test_score.py:122-127) */
+    void* X;                  /* [B,Nt,Nr] complex64 in/out: `current`         (test_score.py:126,164) */
+    const void* H_oracle;     /* [B,Nt,Nr] complex64 ground truth or NULL      (test_score.py:131) */
+    const float* noise_var;   /* [B] local_noise = 10^(-snr/10)*Nt             (test_score.py:75) */
+    const float* alpha_step;  /* [B]                                           (test_score.py:46-48) */
+    const float* beta;        /* [B] beta_noise                                (test_score.py:46-48) */
+    double sigma_end;         /* config.model.sigma_end                        (test_score.py:144) */
+    float* nmse_log;          /* [steps,B] per-step NMSE or NULL               (test_score.py:168-170) */
+    uint64_t seed;
+    const uint64_t* sample_ids; /* [B] global sample ids (NULL: 0..B-1) */
+    const void* ext_noise;    /* [steps,B,Nt,Nr] complex64 unit-power noise replacing the RNG, or NULL */
+} sbc_ald_args;
+
+int sbc_version(void);
+const char* sbc_last_error(void);
+
+int sbc_model_create(const sbc_model_desc* desc, int device, void** handle_out);
+int sbc_model_free(void* handle);
+int sbc_query(void* handle, sbc_info* out);
+
+/* NCSNv2Deepest.forward(x, y) (reference ncsnv2/models/ncsnv2.py:269-300).  Device pointers.
+ * x: fp32 [B,channels,Nt,Nr] with element strides x_strides (any layout, e.g. the permuted
+ * view_as_real view of test_score.py:149); labels: int64 [B]; out: fp32 contiguous. */
+int sbc_forward(void* handle, const float* x, const int64_t x_strides[4], const int64_t* labels, float* out,
+                int32_t B, void* stream);
+
+/* Device-pointer ALD run (all arrays in sbc_ald_args are device memory). */
+int sbc_ald_run(void* handle, const sbc_ald_args* args, void* stream);
+
+/* Host-buffer variants: same semantics, all arrays are host memory; copies in, runs, copies out and
+ * synchronises the stream before returning (the end-to-end path for non-torch callers). */
+int sbc_forward_host(void* handle, const float* x, const int64_t* labels, float* out, int32_t B);
+int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
+
+/* Debug aid: run the layer program of sample x (device fp32 [channels,Nt,Nr], contiguous) up to but
+ * excluding op `stop_op` (n_ops = all) and copy the whole arena to arena_out (device,
+ * arena_floats). */
+int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBC_H_ */

@@ -1,0 +1,66 @@
+"""ctypes binding of the C ABI in ``include/sbc.h`` (``libsbc_b200.so``, built by
+``__graft_entry__.build()``).  There is deliberately no fallback: if the CUDA library is missing
+or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbc_b200.so")
+
+EXPORTS = ("sbc_version", "sbc_last_error", "sbc_model_create", "sbc_model_free", "sbc_query", "sbc_forward",
+           "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host", "sbc_debug_arena")
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("ngf", C.c_int32), ("Nt", C.c_int32), ("Nr", C.c_int32), ("channels", C.c_int32),
+                ("op_table", C.c_void_p), ("n_ops", C.c_int32), ("blob", C.c_void_p), ("blob_floats", C.c_int64),
+                ("arena_floats", C.c_int32), ("in_off", C.c_int32), ("out_off", C.c_int32), ("post_off", C.c_int32),
+                ("max_w_len", C.c_int32), ("sigmas", C.c_void_p), ("n_sigmas", C.c_int32), ("conv_flops", C.c_int64)]
+
+
+class Info(C.Structure):
+    _fields_ = [("version", C.c_int32), ("device", C.c_int32), ("num_sms", C.c_int32), ("threads_per_cta", C.c_int32),
+                ("arena_in_smem", C.c_int32), ("weights_staged", C.c_int32), ("smem_bytes_per_cta", C.c_int64),
+                ("arena_bytes", C.c_int64), ("conv_flops_per_forward", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+class AldArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("Nt", C.c_int32), ("Nr", C.c_int32), ("Np", C.c_int32),
+                ("level_begin", C.c_int32), ("level_end", C.c_int32), ("steps_each", C.c_int32),
+                ("P", C.c_void_p), ("Y", C.c_void_p), ("X", C.c_void_p), ("H_oracle", C.c_void_p),
+                ("noise_var", C.c_void_p), ("alpha_step", C.c_void_p), ("beta", C.c_void_p),
+                ("sigma_end", C.c_double), ("nmse_log", C.c_void_p), ("seed", C.c_uint64),
+                ("sample_ids", C.c_void_p), ("ext_noise", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.sbc_version.restype = C.c_int
+        L.sbc_last_error.restype = C.c_char_p
+        L.sbc_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
+        L.sbc_model_free.argtypes = [C.c_void_p]
+        L.sbc_query.argtypes = [C.c_void_p, C.POINTER(Info)]
+        L.sbc_forward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p]
+        L.sbc_ald_run.argtypes = [C.c_void_p, C.POINTER(AldArgs), C.c_void_p]
+        L.sbc_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.sbc_ald_run_host.argtypes = [C.c_void_p, C.POINTER(AldArgs)]
+        L.sbc_debug_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().sbc_last_error().decode()))

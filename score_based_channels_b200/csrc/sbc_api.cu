@@ -1,0 +1,304 @@
+// sbc_api.cu -- C ABI (include/sbc.h) over the fused ALD kernel.  Pure CUDA runtime; no torch types.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/sbc.h"
+#include "sbc_kernel.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int sbc_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define SBC_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return sbc_fail(SBC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct SbcModel {
+    int device = 0;
+    int num_sms = 0;
+    int smem_optin = 0;
+    sbc_model_desc d{};
+    SbcOp* d_ops = nullptr;
+    float* d_blob = nullptr;
+    float* d_sigmas = nullptr;
+    float* d_gws = nullptr;
+    int first_w = -1;
+    bool arena_in_smem = false;
+    bool stage = false;
+    size_t smem_bytes = 0;
+    long long launches = 0;
+};
+
+extern "C" int sbc_version(void) { return SBC_VERSION; }
+extern "C" const char* sbc_last_error(void) { return g_err; }
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** handle_out) {
+    if (!desc || !handle_out) return sbc_fail(SBC_E_ARG, "sbc_model_create: null argument");
+    if (!desc->op_table || desc->n_ops <= 0 || !desc->blob || desc->blob_floats <= 0 || !desc->sigmas ||
+        desc->n_sigmas <= 0)
+        return sbc_fail(SBC_E_ARG, "sbc_model_create: empty program / blob / sigmas");
+    if (desc->Nt % 8 || desc->Nr % 8 || desc->Nt <= 0 || desc->Nr <= 0)
+        return sbc_fail(SBC_E_ARG, "sbc_model_create: Nt (%d) and Nr (%d) must be positive multiples of 8", desc->Nt,
+                        desc->Nr);
+    if (desc->channels != 2) return sbc_fail(SBC_E_ARG, "sbc_model_create: channels must be 2 (re, im)");
+    if (desc->arena_floats % 4 || desc->max_w_len % 4)
+        return sbc_fail(SBC_E_ARG, "sbc_model_create: arena_floats and max_w_len must be multiples of 4");
+    int ndev = 0;
+    SBC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return sbc_fail(SBC_E_ARG, "sbc_model_create: no CUDA device %d", device);
+    SBC_CUDA(cudaSetDevice(device));
+    SbcModel* m = new SbcModel();
+    m->device = device;
+    m->d = *desc;
+    SBC_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
+    SBC_CUDA(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+
+    // validate + annotate the op table (pad0 := index of the next op that has parameters)
+    std::vector<SbcOp> ops(desc->n_ops);
+    memcpy(ops.data(), desc->op_table, sizeof(SbcOp) * (size_t)desc->n_ops);
+    int next = -1;
+    for (int i = desc->n_ops - 1; i >= 0; i--) {
+        SbcOp& o = ops[i];
+        o.pad0 = next;
+        if (o.w_len > 0) next = i;
+        if (o.kind < 0 || o.kind > SBC_OP_UPACC) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
+        if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
+            o.w_len > desc->max_w_len) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
+        if (o.kind == SBC_OP_CONV) {
+            const bool ok = (o.px == 1 || o.px == 2 || o.px == 4) && (o.cb == 1 || o.cb == 2 || o.cb == 4 || o.cb == 8) &&
+                            o.ks >= 1 && o.ks <= 32 && (o.ks & (o.ks - 1)) == 0 && o.cin % o.ks == 0 &&
+                            o.cout % o.cb == 0 && o.ow % o.px == 0 && (o.ksize == 1 || o.ksize == 3);
+            if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported conv tiling", i); }
+        }
+    }
+    m->first_w = next;
+
+    // where do activations live, and are parameters staged through shared memory?
+    const size_t arena_bytes = (size_t)desc->arena_floats * 4, stage_bytes = 2 * (size_t)desc->max_w_len * 4;
+    const size_t misc = 64;
+    m->stage = env_int("SBC_STAGE_WEIGHTS", 1) != 0;
+    m->arena_in_smem = !env_int("SBC_FORCE_GLOBAL_ARENA", 0) &&
+                       arena_bytes + (m->stage ? stage_bytes : 0) + misc <= (size_t)m->smem_optin;
+    if (!m->arena_in_smem && stage_bytes + misc > (size_t)m->smem_optin) m->stage = false;
+    m->smem_bytes = (m->arena_in_smem ? arena_bytes : 0) + (m->stage ? stage_bytes : 0) + misc;
+
+    SBC_CUDA(cudaMalloc(&m->d_ops, sizeof(SbcOp) * (size_t)desc->n_ops));
+    SBC_CUDA(cudaMemcpy(m->d_ops, ops.data(), sizeof(SbcOp) * (size_t)desc->n_ops, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMalloc(&m->d_blob, sizeof(float) * (size_t)desc->blob_floats));
+    SBC_CUDA(cudaMemcpy(m->d_blob, desc->blob, sizeof(float) * (size_t)desc->blob_floats, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMalloc(&m->d_sigmas, sizeof(float) * (size_t)desc->n_sigmas));
+    SBC_CUDA(cudaMemcpy(m->d_sigmas, desc->sigmas, sizeof(float) * (size_t)desc->n_sigmas, cudaMemcpyHostToDevice));
+    if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
+    m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr;   // host pointers are not retained
+
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_optin));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_optin));
+    *handle_out = m;
+    return SBC_OK;
+}
+
+extern "C" int sbc_model_free(void* handle) {
+    if (!handle) return SBC_OK;
+    SbcModel* m = (SbcModel*)handle;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_ops); cudaFree(m->d_blob); cudaFree(m->d_sigmas); cudaFree(m->d_gws);
+    delete m;
+    return SBC_OK;
+}
+
+extern "C" int sbc_query(void* handle, sbc_info* out) {
+    if (!handle || !out) return sbc_fail(SBC_E_ARG, "sbc_query: null argument");
+    SbcModel* m = (SbcModel*)handle;
+    out->version = SBC_VERSION;
+    out->device = m->device;
+    out->num_sms = m->num_sms;
+    out->threads_per_cta = SBC_NTHREADS;
+    out->arena_in_smem = m->arena_in_smem;
+    out->weights_staged = m->stage;
+    out->smem_bytes_per_cta = (int64_t)m->smem_bytes;
+    out->arena_bytes = (int64_t)m->d.arena_floats * 4;
+    out->conv_flops_per_forward = m->d.conv_flops;
+    out->kernel_launches = m->launches;
+    return SBC_OK;
+}
+
+static void fill_common(const SbcModel* m, SbcLaunch& L) {
+    memset(&L, 0, sizeof L);
+    L.ops = m->d_ops; L.n_ops = m->d.n_ops; L.first_w = m->first_w; L.blob = m->d_blob;
+    L.arena_floats = m->d.arena_floats; L.in_off = m->d.in_off; L.out_off = m->d.out_off; L.post_off = m->d.post_off;
+    L.Nt = m->d.Nt; L.Nr = m->d.Nr; L.channels = m->d.channels; L.max_w_len = m->d.max_w_len;
+    L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
+    L.gws = m->d_gws; L.stage_weights = m->stage ? 1 : 0; L.debug_stop = -1;
+}
+
+static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
+    SBC_CUDA(cudaSetDevice(m->device));
+    const int grid = L.B < m->num_sms ? L.B : m->num_sms;
+    size_t smem = m->smem_bytes;
+    if (L.debug_stop >= 0 && L.stage_weights) {   // debug runs read parameters straight from global memory
+        L.stage_weights = 0;
+        smem -= 2 * (size_t)m->d.max_w_len * 4;
+    }
+    if (m->arena_in_smem)
+        sbc_ald_kernel<true><<<grid, SBC_NTHREADS, smem, st>>>(L);
+    else
+        sbc_ald_kernel<false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+    SBC_CUDA(cudaGetLastError());
+    m->launches++;
+    return SBC_OK;
+}
+
+extern "C" int sbc_forward(void* handle, const float* x, const int64_t x_strides[4], const int64_t* labels,
+                           float* out, int32_t B, void* stream) {
+    if (!handle || !x || !x_strides || !labels || !out) return sbc_fail(SBC_E_ARG, "sbc_forward: null argument");
+    if (B < 0) return sbc_fail(SBC_E_ARG, "sbc_forward: negative batch");
+    if (B == 0) return SBC_OK;
+    SbcModel* m = (SbcModel*)handle;
+    SbcLaunch L;
+    fill_common(m, L);
+    L.mode = 0; L.B = B; L.fx = x; L.labels = (const long long*)labels; L.fout = out;
+    for (int i = 0; i < 4; i++) L.fxs[i] = x_strides[i];
+    return launch(m, L, (cudaStream_t)stream);
+}
+
+static int check_ald(const SbcModel* m, const sbc_ald_args* a) {
+    if (!a) return sbc_fail(SBC_E_ARG, "sbc_ald_run: null args");
+    if (a->B < 0) return sbc_fail(SBC_E_ARG, "sbc_ald_run: negative batch");
+    if (a->Nt != m->d.Nt || a->Nr != m->d.Nr)
+        return sbc_fail(SBC_E_ARG, "sbc_ald_run: model packed for %dx%d, got Nt=%d Nr=%d", m->d.Nt, m->d.Nr, a->Nt, a->Nr);
+    if (a->Np <= 0 || a->Np > a->Nt) return sbc_fail(SBC_E_ARG, "sbc_ald_run: need 0 < Np <= Nt (Np=%d)", a->Np);
+    if (a->level_begin < 0 || a->level_end > m->d.n_sigmas || a->level_begin > a->level_end)
+        return sbc_fail(SBC_E_ARG, "sbc_ald_run: level range [%d,%d) outside [0,%d]", a->level_begin, a->level_end,
+                        m->d.n_sigmas);
+    if (a->steps_each <= 0) return sbc_fail(SBC_E_ARG, "sbc_ald_run: steps_each must be positive");
+    if (a->B > 0 && (!a->P || !a->Y || !a->X || !a->noise_var || !a->alpha_step || !a->beta))
+        return sbc_fail(SBC_E_ARG, "sbc_ald_run: null array");
+    if (!(a->sigma_end > 0.)) return sbc_fail(SBC_E_ARG, "sbc_ald_run: sigma_end must be positive");
+    return SBC_OK;
+}
+
+static void fill_ald(SbcLaunch& L, const sbc_ald_args* a) {
+    L.mode = 1; L.B = a->B; L.Np = a->Np;
+    L.level_begin = a->level_begin; L.level_end = a->level_end; L.steps_each = a->steps_each;
+    L.P = (const float*)a->P; L.Y = (const float*)a->Y; L.X = (float*)a->X; L.Hor = (const float*)a->H_oracle;
+    L.noise_var = a->noise_var; L.alpha_step = a->alpha_step; L.beta = a->beta; L.sigma_end = a->sigma_end;
+    L.nmse_log = a->nmse_log; L.seed = a->seed; L.sample_ids = (const unsigned long long*)a->sample_ids;
+    L.ext_noise = (const float*)a->ext_noise;
+}
+
+extern "C" int sbc_ald_run(void* handle, const sbc_ald_args* a, void* stream) {
+    if (!handle) return sbc_fail(SBC_E_ARG, "sbc_ald_run: null handle");
+    SbcModel* m = (SbcModel*)handle;
+    int rc = check_ald(m, a);
+    if (rc) return rc;
+    if (a->B == 0 || a->level_begin == a->level_end) return SBC_OK;
+    SbcLaunch L;
+    fill_common(m, L);
+    fill_ald(L, a);
+    return launch(m, L, (cudaStream_t)stream);
+}
+
+// ---- host-buffer variants ------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+};
+
+extern "C" int sbc_forward_host(void* handle, const float* x, const int64_t* labels, float* out, int32_t B) {
+    if (!handle || !x || !labels || !out) return sbc_fail(SBC_E_ARG, "sbc_forward_host: null argument");
+    if (B <= 0) return B == 0 ? SBC_OK : sbc_fail(SBC_E_ARG, "sbc_forward_host: negative batch");
+    SbcModel* m = (SbcModel*)handle;
+    SBC_CUDA(cudaSetDevice(m->device));
+    const size_t n = (size_t)B * m->d.channels * m->d.Nt * m->d.Nr;
+    DevBuf dx, dl, dout;
+    if (dx.alloc(n * 4) || dl.alloc((size_t)B * 8) || dout.alloc(n * 4)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+    SBC_CUDA(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dl.p, labels, (size_t)B * 8, cudaMemcpyHostToDevice));
+    const int64_t st[4] = {(int64_t)m->d.channels * m->d.Nt * m->d.Nr, (int64_t)m->d.Nt * m->d.Nr, m->d.Nr, 1};
+    int rc = sbc_forward(handle, (const float*)dx.p, st, (const int64_t*)dl.p, (float*)dout.p, B, nullptr);
+    if (rc) return rc;
+    SBC_CUDA(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return SBC_OK;
+}
+
+extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
+    if (!handle) return sbc_fail(SBC_E_ARG, "sbc_ald_run_host: null handle");
+    SbcModel* m = (SbcModel*)handle;
+    int rc = check_ald(m, a);
+    if (rc) return rc;
+    if (a->B == 0 || a->level_begin == a->level_end) return SBC_OK;
+    SBC_CUDA(cudaSetDevice(m->device));
+    const size_t B = a->B, ne = (size_t)a->Nt * a->Nr, steps = (size_t)(a->level_end - a->level_begin) * a->steps_each;
+    const size_t nP = B * a->Np * a->Nt * 8, nY = B * a->Np * a->Nr * 8, nX = B * ne * 8;
+    DevBuf dP, dY, dX, dH, dnv, dal, dbe, dlog, dids, dn;
+    if (dP.alloc(nP) || dY.alloc(nY) || dX.alloc(nX) || dnv.alloc(B * 4) || dal.alloc(B * 4) || dbe.alloc(B * 4))
+        return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+    SBC_CUDA(cudaMemcpy(dP.p, a->P, nP, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dY.p, a->Y, nY, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dX.p, a->X, nX, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dnv.p, a->noise_var, B * 4, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dal.p, a->alpha_step, B * 4, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(dbe.p, a->beta, B * 4, cudaMemcpyHostToDevice));
+    sbc_ald_args d = *a;
+    d.P = dP.p; d.Y = dY.p; d.X = dX.p; d.noise_var = (const float*)dnv.p; d.alpha_step = (const float*)dal.p;
+    d.beta = (const float*)dbe.p;
+    if (a->H_oracle) {
+        if (dH.alloc(nX)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        SBC_CUDA(cudaMemcpy(dH.p, a->H_oracle, nX, cudaMemcpyHostToDevice));
+        d.H_oracle = dH.p;
+    }
+    if (a->nmse_log) {
+        if (dlog.alloc(steps * B * 4)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        d.nmse_log = (float*)dlog.p;
+    }
+    if (a->sample_ids) {
+        if (dids.alloc(B * 8)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        SBC_CUDA(cudaMemcpy(dids.p, a->sample_ids, B * 8, cudaMemcpyHostToDevice));
+        d.sample_ids = (const uint64_t*)dids.p;
+    }
+    if (a->ext_noise) {
+        if (dn.alloc(steps * nX)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        SBC_CUDA(cudaMemcpy(dn.p, a->ext_noise, steps * nX, cudaMemcpyHostToDevice));
+        d.ext_noise = dn.p;
+    }
+    rc = sbc_ald_run(handle, &d, nullptr);
+    if (rc) return rc;
+    SBC_CUDA(cudaMemcpy(a->X, dX.p, nX, cudaMemcpyDeviceToHost));
+    if (a->nmse_log) SBC_CUDA(cudaMemcpy(a->nmse_log, dlog.p, steps * B * 4, cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaDeviceSynchronize());
+    return SBC_OK;
+}
+
+extern "C" int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream) {
+    if (!handle || !x || !arena_out) return sbc_fail(SBC_E_ARG, "sbc_debug_arena: null argument");
+    SbcModel* m = (SbcModel*)handle;
+    if (stop_op < 0 || stop_op > m->d.n_ops) return sbc_fail(SBC_E_ARG, "sbc_debug_arena: stop_op out of range");
+    static const long long zero_label = 0;
+    (void)zero_label;
+    SbcLaunch L;
+    fill_common(m, L);
+    L.mode = 0; L.B = 1; L.fx = x; L.labels = nullptr; L.fout = nullptr;
+    L.fxs[0] = (long long)m->d.channels * m->d.Nt * m->d.Nr; L.fxs[1] = (long long)m->d.Nt * m->d.Nr;
+    L.fxs[2] = m->d.Nr; L.fxs[3] = 1;
+    L.debug_stop = stop_op; L.debug_out = arena_out;
+    return launch(m, L, (cudaStream_t)stream);
+}

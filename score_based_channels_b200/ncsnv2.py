@@ -1,0 +1,112 @@
+"""Drop-in ``NCSNv2Deepest`` (reference ``ncsnv2/models/ncsnv2.py:198-300``).
+
+Same constructor argument (the DotMap-style ``config``), same ``state_dict`` key names and shapes
+(so ``load_state_dict(contents['model_state'])`` of a reference checkpoint works unchanged), same
+``sigmas`` buffer and the same ``forward(x, y)`` contract -- but ``forward`` is one launch of the
+fused sm_100a kernel through the C ABI instead of ~650 ATen kernels.  Inference only (the
+reference hot path runs under ``torch.no_grad()``, ``test_score.py:150``); CUDA only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, params
+from .engine import PackedModel
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's nested parameter names."""
+
+
+def _cfg_get(node, key, default=None):
+    try:
+        v = node[key] if isinstance(node, dict) else getattr(node, key)
+    except (KeyError, AttributeError):
+        return default
+    if v is None or (hasattr(v, "__len__") and not isinstance(v, (str, bytes)) and len(v) == 0
+                     and not isinstance(v, (list, tuple))):
+        return default          # empty (falsy) DotMap child == "unset"
+    return v
+
+
+class NCSNv2Deepest(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        model, data = config.model, config.data
+        self.ngf = int(model.ngf)
+        self.num_classes = int(model.num_classes)
+        self.channels = int(_cfg_get(data, "channels", 2))
+        norm = _cfg_get(model, "normalization", "InstanceNorm++")
+        act = str(_cfg_get(model, "nonlinearity", "elu")).lower()
+        if norm != "InstanceNorm++" or act != "elu":
+            raise NotImplementedError("fused kernel implements InstanceNorm++ / ELU (the shipped configuration, "
+                                      "train_score.py:39-40); got %r / %r" % (norm, act))
+        # reference ncsnv2.py:201-202,270-271: both unset -> h = 2x - 1 is applied
+        if _cfg_get(data, "logit_transform", False) or _cfg_get(data, "rescaled", False):
+            raise NotImplementedError("logit_transform / rescaled inputs are not used by score_based_channels")
+        if str(_cfg_get(model, "sigma_dist", "geometric")) != "geometric":
+            raise NotImplementedError("only the geometric sigma schedule is used on this path")
+        sig = params.get_sigmas_np(float(model.sigma_begin), float(model.sigma_end), self.num_classes)
+        self.register_buffer("sigmas", torch.from_numpy(sig))
+        # parameters under the reference's names
+        rng = np.random.default_rng(0)
+        init = params.random_state(self.ngf, self.channels, self.num_classes, float(model.sigma_begin),
+                                   float(model.sigma_end), seed=int(rng.integers(1 << 30)))
+        for name, shape in params.param_shapes(self.ngf, self.channels, self.num_classes).items():
+            if name == "sigmas":
+                continue
+            node = self
+            parts = name.split(".")
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            node.register_parameter(parts[-1], nn.Parameter(torch.from_numpy(init[name]), requires_grad=False))
+        self._packed: Optional[PackedModel] = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------
+    def _key(self, Nt, Nr, device):
+        return (Nt, Nr, device.index if device.index is not None else torch.cuda.current_device(),
+                tuple(p._version for p in self.parameters()), self.sigmas._version,
+                tuple(p.data_ptr() for p in self.parameters()))
+
+    def packed(self, Nt: int, Nr: int, device: torch.device) -> PackedModel:
+        """(Re)pack the current parameters for an Nt x Nr input on `device` (cached)."""
+        key = self._key(Nt, Nr, device)
+        if self._packed is None or self._packed_key != key:
+            if self._packed is not None:
+                self._packed.close()
+            state = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
+            self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels)
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """score = f(2x-1)/sigmas[y]; x fp32 [B,channels,Nt,Nr] (any strides), y int64 [B]."""
+        if not x.is_cuda:
+            raise RuntimeError("NCSNv2Deepest (B200) runs on CUDA tensors only; there is no CPU path")
+        if x.dim() != 4 or x.shape[1] != self.channels:
+            raise ValueError("expected x of shape [B,%d,Nt,Nr], got %s" % (self.channels, tuple(x.shape)))
+        if x.dtype != torch.float32:
+            x = x.float()
+        B, _, Nt, Nr = x.shape
+        y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        if y.numel() != B:
+            raise ValueError("labels must have one entry per sample")
+        pm = self.packed(Nt, Nr, x.device)
+        out = torch.empty((B, self.channels, Nt, Nr), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
+        strides = (C.c_int64 * 4)(*x.stride())
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sbc_forward(pm.handle, x.data_ptr(), strides, y.data_ptr(), out.data_ptr(), B,
+                                              C.c_void_p(stream)), "sbc_forward")
+        return out

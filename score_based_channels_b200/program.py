@@ -152,7 +152,8 @@ class ProgramBuilder:
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
                  channels: int = 2, nthreads: int = 256):
-        assert H % 8 == 0 and W % 8 == 0, "Nt and Nr must be divisible by 8 (three 2x mean-pools)"
+        if H <= 0 or W <= 0 or H % 8 or W % 8:
+            raise ValueError("Nt and Nr must be positive multiples of 8 (three 2x mean-pools), got %dx%d" % (H, W))
         self.sd = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
         self.ngf, self.H, self.W, self.channels = ngf, H, W, channels
         self.nthreads = nthreads
@@ -242,7 +243,7 @@ class ProgramBuilder:
                                                       self.sd[prefix + ".gamma"],
                                                       self.sd[prefix + ".beta"]])])
         # scratch: per-thread (mean, M2, count) partials + per-channel (mean, rstd)
-        scratch = self.tmp(1, 1, 3 * self.nthreads + 2 * c, "nsc")
+        scratch = self.tmp(1, 1, 3 * max(self.nthreads, c) + 2 * c, "nsc")
         self.ops.append(Op(OP_NORM_ELU, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w,
                            w_off=w_off, w_len=w_len, scratch=self.off(scratch), oh=h, ow=w, name=prefix))
         self.free(scratch)

@@ -1,0 +1,118 @@
+"""CPU thread-emulation of the kernel's per-thread op bodies (csrc/sbc_ops.h, shared verbatim with
+the CUDA kernel) against the schedule simulator and the reference goldens.  Catches tiling /
+indexing errors in the device code without a GPU.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from score_based_channels_b200 import params, program
+
+from conftest import GOLDEN, REPO
+
+EMU_DIR = os.path.join(REPO, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libemu.so")
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(REPO, "score_based_channels_b200", "csrc", "sbc_ops.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
+    lib = C.CDLL(so)
+    lib.emu_run_program.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.emu_langevin_step.restype = C.c_float
+    lib.emu_langevin_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_uint64,
+                                      C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.emu_noise.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+    return lib
+
+
+def run_emu(lib, prog, x, stop=-1):
+    arena = np.zeros(prog.arena_floats, np.float32)
+    n_in = prog.channels * prog.H * prog.W
+    arena[prog.in_off:prog.in_off + n_in] = x.reshape(-1)
+    tab = np.ascontiguousarray(prog.op_table())
+    rc = lib.emu_run_program(tab.ctypes.data, tab.shape[0], prog.blob.ctypes.data, arena.ctypes.data, prog.nthreads,
+                             stop)
+    assert rc == 0
+    return arena
+
+
+@pytest.mark.parametrize("name,H,W", [("forward_ngf8.npz", 64, 16), ("forward_ngf8_32x8.npz", 32, 8),
+                                      ("forward_ngf16.npz", 64, 16)])
+def test_emulated_forward_matches_reference_golden(emu, name, H, W):
+    g = np.load(os.path.join(GOLDEN, name))
+    sd = params.random_state(int(g["ngf"]), seed=int(g["wseed"]))
+    prog = program.build_program(sd, int(g["ngf"]), H, W)
+    sig = sd["sigmas"]
+    n = 2 * H * W
+    for b in range(g["x"].shape[0]):
+        arena = run_emu(emu, prog, g["x"][b])
+        out = arena[prog.out_off:prog.out_off + n].reshape(2, H, W) / sig[int(g["y"][b])]
+        rel = np.linalg.norm(out - g["out"][b]) / np.linalg.norm(g["out"][b])
+        assert rel < 2e-5, (name, b, rel)
+
+
+def test_emulated_ops_match_simulator_op_by_op(emu):
+    """Every op of the program, individually: emulated device code vs the torch simulator, both
+    started from the same arena state (so a failure names the op)."""
+    sd = params.random_state(8, seed=1)
+    prog = program.build_program(sd, 8, 64, 16)
+    x = (np.random.default_rng(0).standard_normal((2, 64, 16)) * 3).astype(np.float32)
+    _, ref_arena = program.simulate(prog, torch.from_numpy(x))
+    arena = run_emu(emu, prog, x)
+    # end-to-end arena agreement on every tensor that is still defined at the end
+    n = 2 * 64 * 16
+    a = arena[prog.out_off:prog.out_off + n]
+    r = ref_arena.numpy()[prog.out_off:prog.out_off + n]
+    assert np.linalg.norm(a - r) / np.linalg.norm(r) < 2e-5
+    # prefix runs: the state after k ops must agree for a spread of k (localises a broken op)
+    for k in list(range(1, 40)) + list(range(40, len(prog.ops), 7)):
+        _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
+        ea = run_emu(emu, prog, x, stop=k)
+        op = prog.ops[k - 1]
+        outs = [(o, op.cout * op.oh * op.ow) for o in (op.dst, op.acc, op.edst) if o >= 0]
+        for off, cnt in outs:
+            d = np.abs(ea[off:off + cnt] - ra.numpy()[off:off + cnt]).max()
+            s = np.abs(ra.numpy()[off:off + cnt]).max() + 1e-6
+            assert d / s < 5e-5, (k - 1, op.name, op.kind, d, s)
+
+
+def test_emulated_langevin_step_matches_oracle(emu):
+    g = np.load(os.path.join(GOLDEN, "ald_cfg1.npz"))
+    sd = params.random_state(8, seed=int(g["wseed"]))
+    prog = program.build_program(sd, 8, 64, 16)
+    sig = sd["sigmas"]
+    b, Nt, Nr, Np = 1, 64, 16, g["P"].shape[1]
+    lvl = int(g["levels"][0])
+    sigma = float(sig[lvl])
+    alpha = float(g["alpha_step"]) * (sigma / float(g["sigma_end"])) ** 2
+    den = float(g["noise_var"]) / 2. + sigma ** 2
+    nscale = np.sqrt(2 * alpha * float(g["beta"]))
+    X0 = g["X0"][b]
+    xr = np.stack([X0.real, X0.imag]).astype(np.float32)
+    arena = run_emu(emu, prog, xr)
+    P = np.ascontiguousarray(g["P"][b]); Y = np.ascontiguousarray(g["Y"][b]); H = np.ascontiguousarray(g["H"][b])
+    en = np.ascontiguousarray(g["ext_noise"][0, b])
+    tot = emu.emu_langevin_step(arena.ctypes.data, prog.in_off, prog.out_off, prog.post_off, P.ctypes.data,
+                                Y.ctypes.data, H.ctypes.data, en.ctypes.data, sigma, alpha, den, nscale, 0, 0, 0, Nt,
+                                Nr, Np, prog.nthreads)
+    n = Nt * Nr
+    x1 = arena[prog.in_off:prog.in_off + n].reshape(Nt, Nr) + 1j * arena[prog.in_off + n:prog.in_off + 2 * n].reshape(Nt, Nr)
+    ref = g["xs"][0, b]
+    assert np.abs(x1 - ref).max() < 1e-5 * np.abs(ref).max()
+    nm = tot / np.sum(np.abs(H) ** 2)
+    assert abs(nm - g["nmse"][0, b]) < 2e-5 * g["nmse"][0, b]
+
+
+def test_device_noise_matches_oracle_noise(emu):
+    out = np.empty(1024, np.complex64)
+    emu.emu_noise(77, 5, 1234, 1024, out.ctypes.data)
+    ref = orc.noise(77, 5, 1234, 1024)
+    assert np.allclose(out, ref, rtol=1e-6, atol=1e-7)
