@@ -120,6 +120,11 @@ int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
  * arena_floats). */
 int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
 
+/* Profiling aid: subsequent launches of this handle make CTA 0 record clock64() at every op
+ * boundary of its first sample / first step into dev_stamps (device int64 [n_ops + 2]: op starts,
+ * end of network, end of the Langevin update).  NULL switches it off. */
+int sbc_set_profile_buffer(void* handle, int64_t* dev_stamps);
+
 #ifdef __cplusplus
 }
 #endif

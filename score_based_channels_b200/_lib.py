@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbc_b200.so")
 
 EXPORTS = ("sbc_version", "sbc_last_error", "sbc_model_create", "sbc_model_free", "sbc_query", "sbc_forward",
-           "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host", "sbc_debug_arena")
+           "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host", "sbc_debug_arena", "sbc_set_profile_buffer")
 
 
 class ModelDesc(C.Structure):
@@ -57,6 +57,7 @@ def lib():
         L.sbc_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.sbc_ald_run_host.argtypes = [C.c_void_p, C.POINTER(AldArgs)]
         L.sbc_debug_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.sbc_set_profile_buffer.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -40,6 +40,7 @@ struct SbcModel {
     bool stage = false;
     size_t smem_bytes = 0;
     long long launches = 0;
+    long long* d_prof = nullptr;   // optional per-op clock stamps (sbc_set_profile_buffer)
 };
 
 extern "C" int sbc_version(void) { return SBC_VERSION; }
@@ -92,12 +93,15 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     m->first_w = next;
 
     // where do activations live, and are parameters staged through shared memory?
+    cudaFuncAttributes fa{};
+    SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true>));
+    const int dyn_max = m->smem_optin - (int)fa.sharedSizeBytes;   // opt-in limit covers static + dynamic
     const size_t arena_bytes = (size_t)desc->arena_floats * 4, stage_bytes = 2 * (size_t)desc->max_w_len * 4;
     const size_t misc = 64;
     m->stage = env_int("SBC_STAGE_WEIGHTS", 1) != 0;
     m->arena_in_smem = !env_int("SBC_FORCE_GLOBAL_ARENA", 0) &&
-                       arena_bytes + (m->stage ? stage_bytes : 0) + misc <= (size_t)m->smem_optin;
-    if (!m->arena_in_smem && stage_bytes + misc > (size_t)m->smem_optin) m->stage = false;
+                       arena_bytes + (m->stage ? stage_bytes : 0) + misc <= (size_t)dyn_max;
+    if (!m->arena_in_smem && stage_bytes + misc > (size_t)dyn_max) m->stage = false;
     m->smem_bytes = (m->arena_in_smem ? arena_bytes : 0) + (m->stage ? stage_bytes : 0) + misc;
 
     SBC_CUDA(cudaMalloc(&m->d_ops, sizeof(SbcOp) * (size_t)desc->n_ops));
@@ -109,8 +113,8 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
     m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr;   // host pointers are not retained
 
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_optin));
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_optin));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     *handle_out = m;
     return SBC_OK;
 }
@@ -147,6 +151,7 @@ static void fill_common(const SbcModel* m, SbcLaunch& L) {
     L.Nt = m->d.Nt; L.Nr = m->d.Nr; L.channels = m->d.channels; L.max_w_len = m->d.max_w_len;
     L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
     L.gws = m->d_gws; L.stage_weights = m->stage ? 1 : 0; L.debug_stop = -1;
+    L.prof = m->d_prof;
 }
 
 static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
@@ -285,6 +290,12 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
     SBC_CUDA(cudaMemcpy(a->X, dX.p, nX, cudaMemcpyDeviceToHost));
     if (a->nmse_log) SBC_CUDA(cudaMemcpy(a->nmse_log, dlog.p, steps * B * 4, cudaMemcpyDeviceToHost));
     SBC_CUDA(cudaDeviceSynchronize());
+    return SBC_OK;
+}
+
+extern "C" int sbc_set_profile_buffer(void* handle, int64_t* dev_stamps) {
+    if (!handle) return sbc_fail(SBC_E_ARG, "sbc_set_profile_buffer: null handle");
+    ((SbcModel*)handle)->d_prof = (long long*)dev_stamps;
     return SBC_OK;
 }
 

@@ -51,6 +51,7 @@ struct SbcLaunch {
     int stage_weights;       // 1: cp.async.bulk double buffering, 0: read parameters from global/L2
     int debug_stop;          // >=0: stop sample 0 / step 0 before op `debug_stop`, dump the arena
     float* debug_out;
+    long long* prof;         // optional [n_ops+2] clock64() stamps of CTA 0, first sample, first step
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -220,8 +221,10 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             }
 
             // ---------------- the network: walk the layer program ----------------
+            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && b == 0 && gs == 0 && tid == 0;
             for (int i = 0; i < L.n_ops; i++) {
                 if (L.debug_stop >= 0 && i == L.debug_stop) break;
+                if (do_prof) L.prof[i] = clock64();
                 const SbcOp op = L.ops[i];
                 const float* wseg = L.blob + op.w_off;
                 if (op.w_len > 0 && stage) {
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 return;
             }
 
+            if (do_prof) L.prof[L.n_ops] = clock64();
             const float* net = arena + L.out_off;
             if (L.mode == 0) {
                 // score = net / sigmas[y]   (ncsnv2.py:295-298)
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 }
             }
             __syncthreads();
+            if (do_prof) L.prof[L.n_ops + 1] = clock64();
         }
 
         if (L.mode == 1) {   // write the final estimate back (interleaved complex64)

@@ -83,6 +83,7 @@ class NCSNv2Deepest(nn.Module):
         if self._packed is None or self._packed_key != key:
             if self._packed is not None:
                 self._packed.close()
+                self._packed, self._packed_key = None, None
             state = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
             self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels)
             self._packed_key = key

@@ -38,7 +38,7 @@ def qpsk_pilots(B: int, Nt: int, Np: int, seed: int = 1234) -> np.ndarray:
     test_score.py:108-110)."""
     rng = np.random.default_rng(seed)
     p = (2 * rng.integers(0, 2, (B, Nt, Np)) - 1 + 1j * (2 * rng.integers(0, 2, (B, Nt, Np)) - 1)) / np.sqrt(2)
-    return np.conj(np.transpose(p, (0, 2, 1))).astype(np.complex64)
+    return np.ascontiguousarray(np.conj(np.transpose(p, (0, 2, 1))), dtype=np.complex64)
 
 
 def cn01(shape, rng) -> np.ndarray:

@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Per-op cycle profile of the fused kernel (clock64 stamps of CTA 0) + a plain timed forward.
+Usage on the GPU box:  python tools/profile_ops.py [B] > gpurun_out/ops_profile.txt"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from score_based_channels_b200 import _lib, params, program, sampler, synth  # noqa: E402
+from score_based_channels_b200.models import make_model  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+dev = torch.device("cuda:0")
+sd = params.random_state(8, seed=1)
+m = make_model(sd, ngf=8).to(dev)
+pm = m.packed(64, 16, dev)
+prog = pm.prog
+x = torch.randn(B, 2, 64, 16, device=dev)
+y = torch.zeros(B, dtype=torch.long, device=dev)
+for _ in range(3):
+    m(x, y)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    m(x, y)
+e1.record()
+torch.cuda.synchronize()
+print("forward B=%d: %.3f ms per launch" % (B, e0.elapsed_time(e1) / 10))
+
+stamps = torch.zeros(len(prog.ops) + 2, dtype=torch.int64, device=dev)
+_lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, stamps.data_ptr()), "prof")
+P = torch.from_numpy(synth.qpsk_pilots(B, 64, 38)).to(dev)
+H = torch.from_numpy(synth.cdl_like_channels(B)).to(dev)
+Y = torch.matmul(P, H)
+X0 = torch.randn_like(H)
+sampler.ald_run(m, P, Y, X0, H, noise_var=1.0, alpha_step=3e-11, beta=0.01, level_begin=0, level_end=1, steps_each=2)
+torch.cuda.synchronize()
+_lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, None), "prof")
+st = stamps.cpu().numpy()
+d = np.diff(st)
+tot = st[-1] - st[0]
+print("CTA0 first step: %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
+kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc"}
+by_kind = {}
+rows = []
+for i, op in enumerate(prog.ops):
+    c = int(d[i])
+    key = kinds[op.kind]
+    if op.kind == 1:
+        key = "conv %dx%d c%d->%d k%d d%d%s px%d cb%d ks%d" % (op.h, op.w, op.cin, op.cout, op.ksize, op.dil,
+                                                          " pool" if op.flags else "", op.px, op.cb, op.ks)
+    else:
+        key = "%s %dx%d c%d" % (key, op.h, op.w, op.cin)
+    by_kind.setdefault(key, [0, 0])
+    by_kind[key][0] += c
+    by_kind[key][1] += 1
+    rows.append((i, op.name, key, c))
+print("\n== by op class (cycles, count, cycles/op, share of network)")
+net = st[-2] - st[0]
+for k, (c, n) in sorted(by_kind.items(), key=lambda kv: -kv[1][0]):
+    print("%-48s %9d %4d %8.0f %6.2f%%" % (k, c, n, c / n, 100.0 * c / net))
+print("\n== every op")
+for r in rows:
+    print("%3d %-40s %-46s %8d" % r)
