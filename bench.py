@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--levels", type=int, default=NUM_LEVELS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("SBC_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +180,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     sd = params.random_state(8, seed=1)
-    model = make_model(sd, ngf=8).to(dev)
+    model = make_model(sd, ngf=8, precision=args.precision).to(dev)
     B = args.batch
     P, Y, X0, H, nv = make_batch(B, rank)
     host = [torch.from_numpy(a).pin_memory() for a in (P, Y, X0, H, nv)]
@@ -254,7 +255,7 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": how + ", sustained dense bf16",
-                "kernel": "sbc_ald_kernel<true> (fp32 FFMA path: no tensor-core tiles yet)"}
+                "kernel": "sbc_ald_kernel<true>, conv arithmetic = %s" % args.precision}
 
     if rank == 0:
         cpu = None
@@ -262,8 +263,10 @@ def main():
             cpu = cpu_arm(args, levels)
         line = {"metric": METRIC, "value": value, "unit": "estimates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "clocks": clocks, "gpu_launches": int(launches),
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (3xTF32 split, fp32-equivalent), f32 accumulate",
+                          "tf32": "tf32 operands, f32 accumulate"}[args.precision],
+                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
                 "roofline": roofline, "cpu_baseline": cpu}

@@ -80,7 +80,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         SbcOp& o = ops[i];
         o.pad0 = next;
         if (o.w_len > 0) next = i;
-        if (o.kind < 0 || o.kind > SBC_OP_UPACC) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
+        if (o.kind < 0 || o.kind > SBC_OP_LAST) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
         if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
             o.w_len > desc->max_w_len) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
         if (o.kind == SBC_OP_CONV) {
@@ -88,6 +88,12 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
                             o.ks >= 1 && o.ks <= 32 && (o.ks & (o.ks - 1)) == 0 && o.cin % o.ks == 0 &&
                             o.cout % o.cb == 0 && o.ow % o.px == 0 && (o.ksize == 1 || o.ksize == 3);
             if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported conv tiling", i); }
+        }
+        if (o.kind == SBC_OP_CONV_MMA) {
+            const bool ok = o.ks >= 1 && o.ks <= SBC_NTHREADS / 32 && (o.ks & (o.ks - 1)) == 0 &&
+                            (o.ksize == 1 || o.ksize == 3) && o.tapmask != 0 && (o.ks == 1 || o.scratch >= 0) &&
+                            o.w_off % 4 == 0;
+            if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported tensor-core conv", i); }
         }
     }
     m->first_w = next;

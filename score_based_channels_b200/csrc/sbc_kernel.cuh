@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sbc_mma.h"
 #include "sbc_ops.h"
 
 #define SBC_NTHREADS 256
@@ -125,6 +126,162 @@ __device__ __forceinline__ void sbc_conv_dispatch(const SbcOp& op, float* arena,
 }
 
 // ---------------------------------------------------------------------------------------------
+// tensor-core conv (SBC_OP_CONV_MMA): warp-level implicit GEMM on mma.sync m16n8k8 TF32.
+//   X3 = true : 3xTF32 split  (a = a_hi + a_lo, b = b_hi + b_lo;  D += a_lo b_hi + a_hi b_lo + a_hi b_hi)
+//               -> fp32-equivalent accuracy (the parity mode);  X3 = false: plain TF32 operands.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sbc_mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+          "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+#define SBC_MMA_SLOTS 8
+
+// Accumulate K steps [s0, s1) for up to 8 slots (slot j = tile mt0 + (j / nq) * mt_stride, pooling
+// position j % nq) sharing one cout tile nt.
+template <bool X3>
+__device__ __forceinline__ void sbc_mma_pass(const SbcOp& op, const SbcMmaGeom& G, const float* arena,
+                                             const float4* __restrict__ wfrag, int mt0, int mt_stride, int nslots,
+                                             int nt, int s0, int s1, int lane, float (&acc)[SBC_MMA_SLOTS][4]) {
+    const int g = lane >> 2;
+    int iy0[SBC_MMA_SLOTS], ix0[SBC_MMA_SLOTS], iy1[SBC_MMA_SLOTS], ix1[SBC_MMA_SLOTS];
+    unsigned ok0 = 0, ok1 = 0;
+#pragma unroll
+    for (int j = 0; j < SBC_MMA_SLOTS; j++) {
+        iy0[j] = ix0[j] = iy1[j] = ix1[j] = 0;
+        if (j < nslots) {
+            const int mt = mt0 + (j / G.nq) * mt_stride, quad = j % G.nq;
+            bool a, b;
+            sbc_mma_row(op, G, mt, quad, g, iy0[j], ix0[j], a);
+            sbc_mma_row(op, G, mt, quad, g + 8, iy1[j], ix1[j], b);
+            ok0 |= (unsigned)a << j;
+            ok1 |= (unsigned)b << j;
+        }
+    }
+    const int k = op.ksize, r = k >> 1, KK = k * k;
+    int s = 0;
+    for (int tap = 0; tap < KK; tap++) {
+        if (!((op.tapmask >> tap) & 1)) continue;
+        const int ty = tap / k;
+        const int dy = (ty - r) * op.dil, dx = (tap - ty * k - r) * op.dil;
+        for (int kc = 0; kc < G.KC; kc++, s++) {
+            if (s < s0 || s >= s1) continue;
+            const float4 b = __ldg(&wfrag[(size_t)(s * G.NT + nt) * 32 + lane]);
+#pragma unroll
+            for (int j = 0; j < SBC_MMA_SLOTS; j++) {
+                if (j < nslots) {
+                    float a[4];
+                    sbc_mma_a_frag(op, arena, iy0[j], ix0[j], (ok0 >> j) & 1, iy1[j], ix1[j], (ok1 >> j) & 1, dy, dx,
+                                   kc, lane, a);
+                    float ah[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ah[i] = sbc_tf32(a[i]);
+                    if (X3) {
+                        float al[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) al[i] = sbc_tf32(a[i] - ah[i]);
+                        sbc_mma_tf32(acc[j], al, b.x, b.y);   // small terms first
+                        sbc_mma_tf32(acc[j], ah, b.z, b.w);
+                    }
+                    sbc_mma_tf32(acc[j], ah, b.x, b.y);
+                }
+            }
+        }
+    }
+}
+
+template <bool X3>
+__device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, const float* blob, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = SBC_NTHREADS / 32;
+    SbcMmaGeom G;
+    sbc_mma_geom(op, G);
+    const float4* wfrag = reinterpret_cast<const float4*>(blob + op.w_off);
+    float acc[SBC_MMA_SLOTS][4];
+
+    if (op.ks > 1) {
+        // fewer (tile, cout-tile) units than warps: `ks` warps split the K steps of one unit and the
+        // partial accumulators are combined through shared memory
+        const int ks = op.ks, units = G.MT * G.NT;
+        const int u = warp / ks, kp = warp - u * ks;
+        const int mt = u / G.NT, nt = u - mt * G.NT;
+        float4* part = reinterpret_cast<float4*>(arena + op.scratch);
+        if (u < units) {
+#pragma unroll
+            for (int j = 0; j < SBC_MMA_SLOTS; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            sbc_mma_pass<X3>(op, G, arena, wfrag, mt, 0, G.nq, nt, (G.S * kp) / ks, (G.S * (kp + 1)) / ks, lane, acc);
+            float4 c = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+            if (G.nq == 4) {
+#pragma unroll
+                for (int j = 1; j < 4; j++) { c.x += acc[j][0]; c.y += acc[j][1]; c.z += acc[j][2]; c.w += acc[j][3]; }
+            }
+            part[warp * 32 + lane] = c;
+        }
+        __syncthreads();
+        if (u < units && kp == 0) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < ks; i++) {
+                const float4 p = part[(warp + i) * 32 + lane];
+                c[0] += p.x; c[1] += p.y; c[2] += p.z; c[3] += p.w;
+            }
+            sbc_mma_epilogue(op, arena, blob, mt, nt, lane, c);
+        }
+        return;
+    }
+
+    // enough units: each warp owns a fixed cout tile (so one B fragment feeds all its pixel tiles)
+    int ntg = 1;
+    while (ntg * 2 <= G.NT && ntg * 2 <= NW) ntg *= 2;
+    const int mt_first = warp / ntg, mt_stride = NW / ntg;
+    const int tpp = SBC_MMA_SLOTS / G.nq;                    // tiles per pass
+    for (int nt = warp % ntg; nt < G.NT; nt += ntg) {
+        for (int mt0 = mt_first; mt0 < G.MT; mt0 += tpp * mt_stride) {
+            int ntile = (G.MT - mt0 + mt_stride - 1) / mt_stride;
+            if (ntile > tpp) ntile = tpp;
+#pragma unroll
+            for (int j = 0; j < SBC_MMA_SLOTS; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            sbc_mma_pass<X3>(op, G, arena, wfrag, mt0, mt_stride, ntile * G.nq, nt, 0, G.S, lane, acc);
+            if (G.nq == 1) {
+#pragma unroll
+                for (int j = 0; j < SBC_MMA_SLOTS; j++)
+                    if (j < ntile) sbc_mma_epilogue(op, arena, blob, mt0 + j * mt_stride, nt, lane, acc[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SBC_MMA_SLOTS / 4; j++)
+                    if (j < ntile) {
+                        float c[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) c[i] = acc[4 * j][i] + acc[4 * j + 1][i] + acc[4 * j + 2][i] + acc[4 * j + 3][i];
+                        sbc_mma_epilogue(op, arena, blob, mt0 + j * mt_stride, nt, lane, c);
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm++ statistics: S lanes per channel, two passes, shuffle reductions (no barrier)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sbc_norm_stats(const SbcOp& op, float* arena, int tid) {
+    const int S = sbc_norm_S(op, SBC_NTHREADS), C = op.cin;
+    const float inv = 1.f / (float)(op.h * op.w);
+    for (int base = 0; base < C * S; base += SBC_NTHREADS) {   // uniform trip count (shuffles are warp-wide)
+        const int t = base + tid;
+        const bool valid = t < C * S;
+        const int c = valid ? t / S : 0, s = t - (t / S) * S;
+        float sum = valid ? sbc_norm_partial_sum(op, arena, c, s, S) : 0.f;
+        for (int off = 1; off < S; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum * inv;
+        float m2 = valid ? sbc_norm_partial_m2(op, arena, c, s, S, mean) : 0.f;
+        for (int off = 1; off < S; off <<= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+        if (valid && s == 0) sbc_norm_store_stats(op, arena, c, mean, m2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <bool SMEM_ARENA>
@@ -156,8 +313,8 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
     }
     __syncthreads();
 
-    const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
-    float* ax = arena + L.in_off;             // planar x: re plane, im plane
+    const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr, xps = SBC_PS(Nt, Nr);
+    float* ax = arena + L.in_off;             // planar x: re plane, im plane (padded plane stride xps)
     uint32_t wcount = 0;                      // parameter segments consumed so far (same in every thread)
 
     if (stage && tid == 0 && (int)blockIdx.x < L.B && L.first_w >= 0) {
@@ -176,7 +333,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             for (int e = tid; e < ne; e += SBC_NTHREADS) {
                 const float2 v = reinterpret_cast<const float2*>(X)[e];
                 ax[e] = v.x;
-                ax[ne + e] = v.y;
+                ax[xps + e] = v.y;
             }
             if (L.Hor) {   // ||H||_F^2 once per sample (test_score.py:169)
                 const float* Hc = L.Hor + (size_t)b * ne * 2;
@@ -199,7 +356,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             for (int i = tid; i < L.channels * ne; i += SBC_NTHREADS) {
                 const int c = i / ne, e = i - c * ne;
                 const int t = e / Nr, r = e - t * Nr;
-                ax[i] = fx[c * L.fxs[1] + t * L.fxs[2] + r * L.fxs[3]];
+                ax[c * xps + e] = fx[c * L.fxs[1] + t * L.fxs[2] + r * L.fxs[3]];
             }
         }
         __syncthreads();
@@ -246,12 +403,14 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     case SBC_OP_CONV:
                         sbc_conv_dispatch(op, arena, wseg, tid);
                         break;
+                    case SBC_OP_CONV_MMA:
+                        if (op.flags & SBC_F_X3) sbc_conv_mma<true>(op, arena, L.blob, tid);
+                        else sbc_conv_mma<false>(op, arena, L.blob, tid);
+                        break;
                     case SBC_OP_NORM_ELU:
-                        sbc_norm_phaseA(op, arena, tid, SBC_NTHREADS);
+                        sbc_norm_stats(op, arena, tid);
                         __syncthreads();
-                        sbc_norm_phaseB(op, arena, tid, SBC_NTHREADS);
-                        __syncthreads();
-                        sbc_norm_phaseC(op, arena, wseg, tid, SBC_NTHREADS);
+                        sbc_norm_apply(op, arena, wseg, tid, SBC_NTHREADS);
                         break;
                     case SBC_OP_ELU:
                         sbc_elu_op(op, arena, tid, SBC_NTHREADS);
@@ -285,7 +444,10 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 if (lab >= L.n_sigmas) lab = L.n_sigmas - 1;
                 const float sg = L.sigmas[lab];
                 float* o = L.fout + (size_t)b * L.channels * ne;
-                for (int i = tid; i < L.channels * ne; i += SBC_NTHREADS) o[i] = net[i] / sg;
+                for (int i = tid; i < L.channels * ne; i += SBC_NTHREADS) {
+                    const int c = i / ne;
+                    o[i] = net[c * xps + (i - c * ne)] / sg;
+                }
             } else {
                 // ---------------- data-consistency gradient, Langevin update, NMSE ----------------
                 const float* Pm = L.P + (size_t)b * L.Np * Nt * 2;
@@ -317,7 +479,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         if (L.mode == 1) {   // write the final estimate back (interleaved complex64)
             float* X = L.X + (size_t)b * ne * 2;
             for (int e = tid; e < ne; e += SBC_NTHREADS)
-                reinterpret_cast<float2*>(X)[e] = make_float2(ax[e], ax[ne + e]);
+                reinterpret_cast<float2*>(X)[e] = make_float2(ax[e], ax[xps + e]);
         }
         __syncthreads();
     }

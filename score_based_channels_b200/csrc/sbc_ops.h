@@ -22,8 +22,15 @@ struct alignas(16) SbcF4 {
     float x, y, z, w;
 };
 
-// nn.ELU(alpha=1)  (reference ncsnv2/models/layers.py:13)
-SBC_HD float sbc_elu(float v) { return v > 0.f ? v : expm1f(v); }
+// nn.ELU(alpha=1)  (reference ncsnv2/models/layers.py:13).  Device: exp via MUFU.EX2 (absolute
+// error ~1e-7, far inside the parity tolerance); host emulation: expm1f.
+SBC_HD float sbc_elu(float v) {
+#if defined(__CUDA_ARCH__)
+    return v > 0.f ? v : __expf(v) - 1.f;
+#else
+    return v > 0.f ? v : expm1f(v);
+#endif
+}
 
 // ----------------------------------------------------------------------------------------------
 // Convolution (reference layers.py:28-60; ConvMeanPool layers.py:309-313)
@@ -45,6 +52,7 @@ SBC_HD void sbc_conv_partial(const SbcOp& op, const float* arena, const float* w
     const int c0 = kpart * cper, c1 = c0 + cper;
     const int KK = K * K;
     const float* src = arena + op.src;
+    const int ps = SBC_PS(h, w);
     const bool pool = (op.flags & SBC_F_POOL) != 0;
 #pragma unroll
     for (int i = 0; i < PX * CB; i++) acc[i] = 0.f;
@@ -52,7 +60,7 @@ SBC_HD void sbc_conv_partial(const SbcOp& op, const float* arena, const float* w
     if (K == 3 && dil == 1 && !pool) {
         // hot path: contiguous (PX+2)-wide window per tap row
         for (int ci = c0; ci < c1; ci++) {
-            const float* pl = src + ci * h * w;
+            const float* pl = src + ci * ps;
             const float* wp = wseg + (size_t)((cbi * cin + ci) * 9) * CB;
 #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
@@ -97,7 +105,7 @@ SBC_HD void sbc_conv_partial(const SbcOp& op, const float* arena, const float* w
     // already carry the 1/4)
     const int r = K / 2;
     for (int ci = c0; ci < c1; ci++) {
-        const float* pl = src + ci * h * w;
+        const float* pl = src + ci * ps;
         const float* wp = wseg + (size_t)((cbi * cin + ci) * KK) * CB;
         for (int ky = 0; ky < K; ky++) {
             const int oy = (ky - r) * dil;
@@ -156,7 +164,7 @@ SBC_HD void sbc_conv_epilogue(const SbcOp& op, float* arena, const float* wseg, 
     const int sp = item - cbi * nsp;
     const int Y = sp / spr;
     const int X0 = (sp - Y * spr) * PX;
-    const int plane = oh * ow;
+    const int plane = SBC_PS(oh, ow);
 #pragma unroll
     for (int c = 0; c < CB; c++) {
         const int co = cbi * CB + c;
@@ -186,47 +194,39 @@ SBC_HD void sbc_conv_epilogue(const SbcOp& op, float* arena, const float* wseg, 
 SBC_HD int sbc_conv_items(const SbcOp& op) { return op.oh * (op.ow / op.px) * (op.cout / op.cb); }
 
 // ----------------------------------------------------------------------------------------------
-// InstanceNorm2dPlus + ELU (reference normalization.py:163-176), three phases.
-//   scratch: part[3 * C*S] (count, mean, M2 per (channel, segment)), then chan[2*C] (mean, rstd)
-//   thread (c, s) owns elements s, s+S, s+2S, ... of channel c  (S = max(1, nthr / C))
+// InstanceNorm2dPlus + ELU (reference normalization.py:163-176).
+//   S = power of two <= 32 lanes cooperate on one channel; lane (c, s) owns elements s, s+S, ... of
+//   channel c.  Statistics are two-pass (mean, then centred second moment); the S partial sums are
+//   combined with warp shuffles on the device (sbc_kernel.cuh) and by a plain loop in the CPU
+//   emulation.  scratch: chan[2*C] = (mean, rstd) per channel.
 // ----------------------------------------------------------------------------------------------
-SBC_HD int sbc_norm_S(const SbcOp& op, int nthr) { int S = nthr / op.cin; return S < 1 ? 1 : S; }
-
-SBC_HD void sbc_norm_phaseA(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int C = op.cin, HW = op.h * op.w, S = sbc_norm_S(op, nthr);
-    float* part = arena + op.scratch;
-    for (int t = tid; t < C * S; t += nthr) {
-        const int c = t / S, s = t - c * S;
-        const float* x = arena + op.src + c * HW;
-        float sum = 0.f;
-        int n = 0;
-        for (int i = s; i < HW; i += S) { sum += x[i]; n++; }
-        const float mean = n > 0 ? sum / (float)n : 0.f;
-        float m2 = 0.f;
-        for (int i = s; i < HW; i += S) { const float d = x[i] - mean; m2 = fmaf(d, d, m2); }
-        part[3 * t] = (float)n; part[3 * t + 1] = mean; part[3 * t + 2] = m2;
-    }
+SBC_HD int sbc_norm_S(const SbcOp& op, int nthr) {
+    int S = 32;
+    while (S > 1 && op.cin * S > nthr) S >>= 1;
+    return S;
 }
-SBC_HD void sbc_norm_phaseB(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int C = op.cin, HW = op.h * op.w, S = sbc_norm_S(op, nthr);
-    const float* part = arena + op.scratch;
-    float* chan = arena + op.scratch + 3 * C * S;
-    for (int c = tid; c < C; c += nthr) {
-        float tot = 0.f;
-        for (int s = 0; s < S; s++) tot = fmaf(part[3 * (c * S + s)], part[3 * (c * S + s) + 1], tot);
-        const float mean = tot / (float)HW;
-        float m2 = 0.f;   // Chan et al. combination of per-segment (count, mean, M2)
-        for (int s = 0; s < S; s++) {
-            const float n = part[3 * (c * S + s)], d = part[3 * (c * S + s) + 1] - mean;
-            m2 += part[3 * (c * S + s) + 2] + n * d * d;
-        }
-        chan[c] = mean;
-        chan[C + c] = 1.f / sqrtf(m2 / (float)HW + 1e-5f);   // nn.InstanceNorm2d: biased variance
-    }
+SBC_HD float sbc_norm_partial_sum(const SbcOp& op, const float* arena, int c, int s, int S) {
+    const int HW = op.h * op.w;
+    const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
+    float sum = 0.f;
+    for (int i = s; i < HW; i += S) sum += x[i];
+    return sum;
 }
-SBC_HD void sbc_norm_phaseC(const SbcOp& op, float* arena, const float* wseg, int tid, int nthr) {
-    const int C = op.cin, HW = op.h * op.w, S = sbc_norm_S(op, nthr);
-    const float* chan = arena + op.scratch + 3 * C * S;
+SBC_HD float sbc_norm_partial_m2(const SbcOp& op, const float* arena, int c, int s, int S, float mean) {
+    const int HW = op.h * op.w;
+    const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
+    float m2 = 0.f;
+    for (int i = s; i < HW; i += S) { const float d = x[i] - mean; m2 = fmaf(d, d, m2); }
+    return m2;
+}
+SBC_HD void sbc_norm_store_stats(const SbcOp& op, float* arena, int c, float mean, float m2) {
+    float* chan = arena + op.scratch;
+    chan[c] = mean;
+    chan[op.cin + c] = 1.f / sqrtf(m2 / (float)(op.h * op.w) + 1e-5f);   // nn.InstanceNorm2d: biased variance
+}
+SBC_HD void sbc_norm_apply(const SbcOp& op, float* arena, const float* wseg, int tid, int nthr) {
+    const int C = op.cin, HW = op.h * op.w, S = sbc_norm_S(op, nthr), ps = SBC_PS(op.h, op.w);
+    const float* chan = arena + op.scratch;
     // cross-channel statistics of the per-channel means: torch.mean / torch.var (unbiased) over C
     float m = 0.f;
     for (int c = 0; c < C; c++) m += chan[c];
@@ -241,8 +241,8 @@ SBC_HD void sbc_norm_phaseC(const SbcOp& op, float* arena, const float* wseg, in
         const float mu = chan[c];
         const float a = gamma[c] * chan[C + c];
         const float b = fmaf(gamma[c], (mu - m) * rv * alpha[c], beta[c]);
-        const float* x = arena + op.src + c * HW;
-        float* o = arena + op.dst + c * HW;
+        const float* x = arena + op.src + c * ps;
+        float* o = arena + op.dst + c * ps;
         for (int i = s; i < HW; i += S) o[i] = sbc_elu(fmaf(x[i] - mu, a, b));
     }
 }
@@ -251,12 +251,18 @@ SBC_HD void sbc_norm_phaseC(const SbcOp& op, float* arena, const float* wseg, in
 // element-wise ops
 // ----------------------------------------------------------------------------------------------
 SBC_HD void sbc_elu_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int n = op.cin * op.h * op.w;
-    for (int i = tid; i < n; i += nthr) arena[op.dst + i] = sbc_elu(arena[op.src + i]);
+    const int HW = op.h * op.w, n = op.cin * HW, ps = SBC_PS(op.h, op.w);
+    for (int i = tid; i < n; i += nthr) {
+        const int c = i / HW, j = c * ps + (i - c * HW);
+        arena[op.dst + j] = sbc_elu(arena[op.src + j]);
+    }
 }
 SBC_HD void sbc_affine_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int n = op.cin * op.h * op.w;
-    for (int i = tid; i < n; i += nthr) arena[op.dst + i] = 2.f * arena[op.src + i] - 1.f;
+    const int HW = op.h * op.w, n = op.cin * HW, ps = SBC_PS(op.h, op.w);
+    for (int i = tid; i < n; i += nthr) {
+        const int c = i / HW, j = c * ps + (i - c * HW);
+        arena[op.dst + j] = 2.f * arena[op.src + j] - 1.f;
+    }
 }
 
 // MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70): strip of up to 4 pixels/thread
@@ -269,7 +275,7 @@ SBC_HD void sbc_maxpool5_op(const SbcOp& op, float* arena, int tid, int nthr) {
         const int c = it / (H * spr);
         const int rem = it - c * (H * spr);
         const int y = rem / spr, x0 = (rem - y * spr) * PX;
-        const float* pl = arena + op.src + c * H * W;
+        const float* pl = arena + op.src + c * SBC_PS(H, W);
         float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int dy = -2; dy <= 2; dy++) {
             const int yy = y + dy;
@@ -289,7 +295,7 @@ SBC_HD void sbc_maxpool5_op(const SbcOp& op, float* arena, int tid, int nthr) {
                 }
             }
         }
-        float* o = arena + op.dst + c * H * W + y * W + x0;
+        float* o = arena + op.dst + c * SBC_PS(H, W) + y * W + x0;
 #pragma unroll
         for (int p = 0; p < 4; p++)
             if (p < PX) o[p] = best[p];
@@ -310,12 +316,13 @@ SBC_HD void sbc_upacc_op(const SbcOp& op, float* arena, int tid, int nthr) {
         const int y0 = (int)fy, x0 = (int)fx;
         const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
         const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        const float* p = arena + op.src + c * H * W;
+        const float* p = arena + op.src + c * SBC_PS(H, W);
         const float val = hy * (hx * p[y0 * W + x0] + lx * p[y0 * W + x1]) +
                           ly * (hx * p[y1 * W + x0] + lx * p[y1 * W + x1]);
-        const float v = arena[op.acc + i] + val;
-        arena[op.acc + i] = v;
-        if (op.edst >= 0) arena[op.edst + i] = sbc_elu(v);
+        const int j = c * SBC_PS(OH, OW) + rem;
+        const float v = arena[op.acc + j] + val;
+        arena[op.acc + j] = v;
+        if (op.edst >= 0) arena[op.edst + j] = sbc_elu(v);
     }
 }
 
@@ -348,7 +355,7 @@ SBC_HD void sbc_noise_cn01(uint64_t seed, uint64_t sid, uint32_t step, int e, fl
 
 // ----------------------------------------------------------------------------------------------
 // Annealed-Langevin step around the network (reference test_score.py:157-170).
-// x lives planar in the arena at in_off: xr[t*Nr+r], xi = xr + Nt*Nr.  P [Np][Nt], Y [Np][Nr],
+// x lives planar in the arena at in_off: xr[t*Nr+r], xi = xr + SBC_PS(Nt,Nr).  P [Np][Nt], Y [Np][Nr],
 // Hor [Nt][Nr] are interleaved complex64 in global memory.
 // ----------------------------------------------------------------------------------------------
 struct SbcStepScalars {
@@ -362,7 +369,7 @@ struct SbcStepScalars {
 SBC_HD void sbc_dc_residual(const float* arena_x, float* res, const float* P, const float* Y, int Nt, int Nr, int Np,
                             int tid, int nthr) {
     const float* xr = arena_x;
-    const float* xi = arena_x + Nt * Nr;
+    const float* xi = arena_x + SBC_PS(Nt, Nr);
     for (int o = tid; o < Np * Nr; o += nthr) {
         const int p = o / Nr, r = o - p * Nr;
         float sr = 0.f, si = 0.f;
@@ -381,8 +388,9 @@ SBC_HD float sbc_langevin_update(float* arena_x, const float* net_out, const flo
                                  const float* Hor, const float* ext_noise, const SbcStepScalars& sc, uint64_t seed,
                                  uint64_t sid, uint32_t gstep, int Nt, int Nr, int Np, int tid, int nthr) {
     float* xr = arena_x;
-    float* xi = arena_x + Nt * Nr;
+    float* xi = arena_x + SBC_PS(Nt, Nr);
     const int ne = Nt * Nr;
+    const float* net_im = net_out + SBC_PS(Nt, Nr);
     float part = 0.f;
     for (int e = tid; e < ne; e += nthr) {
         const int t = e / Nr, r = e - t * Nr;
@@ -396,7 +404,7 @@ SBC_HD float sbc_langevin_update(float* arena_x, const float* net_out, const flo
         float nr_, ni_;
         if (ext_noise) { nr_ = ext_noise[2 * e]; ni_ = ext_noise[2 * e + 1]; }
         else sbc_noise_cn01(seed, sid, gstep, e, nr_, ni_);
-        const float sr = net_out[e] / sc.sigma, si = net_out[ne + e] / sc.sigma;   // ncsnv2.py:295-298
+        const float sr = net_out[e] / sc.sigma, si = net_im[e] / sc.sigma;   // ncsnv2.py:295-298
         const float vr = xr[e] + sc.alpha * (sr - gr / sc.den) + sc.nscale * nr_;
         const float vi = xi[e] + sc.alpha * (si - gi / sc.den) + sc.nscale * ni_;
         xr[e] = vr; xi[e] = vi;

@@ -13,8 +13,9 @@ class PackedModel:
     """Owns one ``sbc_model_create`` handle for a (state_dict, ngf, Nt, Nr) on one CUDA device."""
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, Nt: int, Nr: int, device: int = 0,
-                 channels: int = 2):
-        self.prog = program.build_program(state, ngf, Nt, Nr, channels)
+                 channels: int = 2, precision: str = "tf32x3"):
+        self.precision = precision
+        self.prog = program.build_program(state, ngf, Nt, Nr, channels, precision=precision)
         self.sigmas = np.ascontiguousarray(state["sigmas"], dtype=np.float32)
         self.ngf, self.Nt, self.Nr, self.channels, self.device = ngf, Nt, Nr, channels, device
         self._tab = np.ascontiguousarray(self.prog.op_table())

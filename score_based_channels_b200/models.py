@@ -29,10 +29,10 @@ def make_config(ngf: int = 8, num_classes: int = 2311, sigma_begin: float = 27.7
     return cfg
 
 
-def make_model(state: Dict[str, np.ndarray], ngf: int = 8, **cfg_kw) -> NCSNv2Deepest:
+def make_model(state: Dict[str, np.ndarray], ngf: int = 8, precision=None, **cfg_kw) -> NCSNv2Deepest:
     """NCSNv2Deepest carrying `state` (reference-keyed numpy arrays; sigmas define the schedule)."""
     sig = np.asarray(state["sigmas"], dtype=np.float64)
     cfg = make_config(ngf=ngf, num_classes=sig.size, **cfg_kw)
-    m = NCSNv2Deepest(cfg)
+    m = NCSNv2Deepest(cfg, precision=precision)
     m.load_state_dict({k: torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in state.items()})
     return m.eval()

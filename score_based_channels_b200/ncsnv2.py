@@ -9,6 +9,7 @@ reference hot path runs under ``torch.no_grad()``, ``test_score.py:150``); CUDA 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -35,9 +36,18 @@ def _cfg_get(node, key, default=None):
 
 
 class NCSNv2Deepest(nn.Module):
-    def __init__(self, config):
+    """``precision`` selects the arithmetic of the 113 convolutions (everything else is fp32):
+
+    * ``"tf32x3"`` (default): tensor cores, 3xTF32 error-compensated products -- fp32-equivalent
+      results (the reference disables TF32, ``test_score.py:24-26``);
+    * ``"tf32"``: tensor cores, plain TF32 operands, fp32 accumulate (fastest);
+    * ``"fp32"``: FFMA on CUDA cores.
+    The environment variable ``SBC_PRECISION`` overrides the default."""
+
+    def __init__(self, config, precision: Optional[str] = None):
         super().__init__()
         self.config = config
+        self.precision = precision or os.environ.get("SBC_PRECISION", "tf32x3")
         model, data = config.model, config.data
         self.ngf = int(model.ngf)
         self.num_classes = int(model.num_classes)
@@ -73,7 +83,7 @@ class NCSNv2Deepest(nn.Module):
 
     # ------------------------------------------------------------------
     def _key(self, Nt, Nr, device):
-        return (Nt, Nr, device.index if device.index is not None else torch.cuda.current_device(),
+        return (Nt, Nr, device.index if device.index is not None else torch.cuda.current_device(), self.precision,
                 tuple(p._version for p in self.parameters()), self.sigmas._version,
                 tuple(p.data_ptr() for p in self.parameters()))
 
@@ -85,7 +95,7 @@ class NCSNv2Deepest(nn.Module):
                 self._packed.close()
                 self._packed, self._packed_key = None, None
             state = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
-            self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels)
+            self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels, self.precision)
             self._packed_key = key
         return self._packed
 

@@ -40,14 +40,26 @@ OP_NORM_ELU = 2   # dst = ELU(InstanceNorm++(src))
 OP_ELU = 3        # dst = ELU(src)
 OP_MAXPOOL5 = 4   # dst = maxpool 5x5 stride 1 pad 2
 OP_UPACC = 5      # acc += bilinear(src -> (oh,ow), align_corners=True)
-N_OP_KINDS = 6
+OP_CONV_MMA = 6   # same contract as OP_CONV, contraction on tensor cores (mma.sync m16n8k8 TF32)
+N_OP_KINDS = 7
+
+PLANE_PAD = 8     # every activation plane is stored with stride h*w + 8 floats: with the stride
+                  # = 8 (mod 16) the (channel t, pixel g) gather of an MMA A-fragment hits 32 banks
+
+
+def PS(h: int, w: int) -> int:
+    return h * w + PLANE_PAD
+
+
+PRECISIONS = ("fp32", "tf32x3", "tf32")
 
 # ---- flags ----------------------------------------------------------------
 F_POOL = 1        # conv followed by 2x2 mean-pool (ConvMeanPool)
+F_X3 = 2          # OP_CONV_MMA: 3xTF32 error-compensated product (fp32-equivalent accuracy)
 
 OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout",
              "h", "w", "ksize", "dil", "w_off", "w_len", "b_rel", "px",
-             "cb", "ks", "scratch", "oh", "ow", "pad0", "pad1", "pad2")
+             "cb", "ks", "scratch", "oh", "ow", "pad0", "tapmask", "pad2")
 OP_WORDS = len(OP_FIELDS)            # 24 int32 = 96 bytes per op
 assert OP_WORDS == 24
 
@@ -75,6 +87,7 @@ class Op:
     scratch: int = -1   # arena offset of the per-op scratch (K-split partials / norm stats)
     oh: int = 0         # OUTPUT spatial size
     ow: int = 0
+    tapmask: int = 0    # OP_CONV_MMA: bit i set = tap i (row-major in the k x k window) can touch the image
     name: str = ""
 
     def words(self) -> List[int]:
@@ -96,6 +109,7 @@ class Program:
     nthreads: int
     max_w_len: int
     conv_flops: int                  # dense conv FLOPs / forward / sample (reference convention)
+    precision: str = "fp32"
     post_off: int = 0                # arena offset of the post-network scratch (2*H*W + 4*nthreads floats)
 
     def op_table(self) -> np.ndarray:
@@ -151,7 +165,10 @@ class ProgramBuilder:
     """Builds the op list for one (ngf, H, W) instance of NCSNv2Deepest."""
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
-                 channels: int = 2, nthreads: int = 256):
+                 channels: int = 2, nthreads: int = 256, precision: str = "fp32"):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
+        self.precision = precision
         if H <= 0 or W <= 0 or H % 8 or W % 8:
             raise ValueError("Nt and Nr must be positive multiples of 8 (three 2x mean-pools), got %dx%d" % (H, W))
         self.sd = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
@@ -167,7 +184,7 @@ class ProgramBuilder:
 
     # -- tensors ----------------------------------------------------------
     def new(self, name: str, c: int, h: int, w: int) -> str:
-        self.ar.alloc(name, c * h * w, len(self.ops))
+        self.ar.alloc(name, c * PS(h, w), len(self.ops))
         self.shape[name] = (c, h, w)
         return name
 
@@ -216,6 +233,9 @@ class ProgramBuilder:
                 assert self.shape[t] == (cout, oh, ow), (prefix, t, self.shape[t], (cout, oh, ow))
         # dense FLOP count, reference convention (conv evaluated at input resolution)
         self.flops += 2 * h * w * cin * k * k * cout
+        if self.precision != "fp32":
+            self._conv_mma(prefix, wt, bias, src, dst, acc, edst, dil, pool, (cin, h, w), (cout, oh, ow))
+            return
         # ---- tiling choice (see csrc/sbc_ops.h: conv_partial) ----
         cb = 8 if cout % 8 == 0 else (4 if cout % 4 == 0 else (2 if cout % 2 == 0 else 1))
         px = 4 if ow % 4 == 0 else (2 if ow % 2 == 0 else 1)
@@ -233,7 +253,52 @@ class ProgramBuilder:
         self.ops.append(Op(OP_CONV, F_POOL if pool else 0, self.off(src), self.off(dst), self.off(acc),
                            self.off(edst), cin, cout, h, w, k, dil, w_off, w_len,
                            rels[1] if bias is not None else -1, px, cb, ks,
-                           -1, oh, ow, prefix))
+                           -1, oh, ow, name=prefix))
+
+    def _conv_mma(self, prefix, wt, bias, src, dst, acc, edst, dil, pool, ishape, oshape) -> None:
+        """Tensor-core conv: implicit GEMM  D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]
+        per (tap, cin chunk) with mma.sync.m16n8k8 TF32 (csrc/sbc_mma.cuh).  The weights are packed in
+        B-fragment order, pre-split into TF32 hi/lo parts: frag[step][ntile][lane] = (hi0, hi1, lo0, lo1)
+        where lane = 4*g + t holds B[k = t (+4)][n = g], step = live_tap_index * KC + cin_chunk."""
+        cin, h, w = ishape
+        cout, oh, ow = oshape
+        k = wt.shape[2]
+        r = k // 2
+        live = []
+        for tap in range(k * k):
+            dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
+            if abs(dy) < h and abs(dx) < w:          # otherwise the tap only ever reads zero padding
+                live.append(tap)
+        tapmask = sum(1 << t for t in live)
+        KC, NT = (cin + 7) // 8, (cout + 7) // 8
+        wpad = np.zeros((NT * 8, KC * 8, k * k), np.float32)
+        wpad[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
+        g, t = np.arange(32) >> 2, np.arange(32) & 3
+        frag = np.zeros((len(live), KC, NT, 32, 4), np.float32)
+        for i, tap in enumerate(live):
+            for kc in range(KC):
+                for nt in range(NT):
+                    w0 = wpad[nt * 8 + g, kc * 8 + t, tap]
+                    w1 = wpad[nt * 8 + g, kc * 8 + t + 4, tap]
+                    h0, h1 = tf32_rna(w0), tf32_rna(w1)
+                    frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = h0, h1
+                    frag[i, kc, nt, :, 2], frag[i, kc, nt, :, 3] = tf32_rna(w0 - h0), tf32_rna(w1 - h1)
+        arrs = [frag] + ([bias] if bias is not None else [])
+        w_off, w_len, rels = self._push(arrs)
+        MT = (oh * ow + 15) // 16
+        units, S = MT * NT, len(live) * KC
+        nwarps = self.nthreads // 32
+        ks = 1
+        while units * ks * 2 <= nwarps and ks * 2 <= S:
+            ks *= 2
+        scratch = self.tmp(1, 1, nwarps * 32 * 4, "ksp") if ks > 1 else None
+        flags = (F_POOL if pool else 0) | (F_X3 if self.precision == "tf32x3" else 0)
+        # parameters of MMA convs are read straight from global/L2 in fragment order (w_len = 0: not staged)
+        self.ops.append(Op(OP_CONV_MMA, flags, self.off(src), self.off(dst), self.off(acc), self.off(edst),
+                           cin, cout, h, w, k, dil, w_off, 0, rels[1] if bias is not None else -1, 0, 0, ks,
+                           self.off(scratch), oh, ow, tapmask=tapmask, name=prefix))
+        if scratch is not None:
+            self.free(scratch)
 
     def norm_elu(self, prefix: str, src: str, dst: str) -> None:
         """dst = ELU(InstanceNorm2dPlus(src))  (``normalization.py:163-176`` + ``layers.py:13``)."""
@@ -242,8 +307,8 @@ class ProgramBuilder:
         w_off, w_len, _ = self._push([np.concatenate([self.sd[prefix + ".alpha"],
                                                       self.sd[prefix + ".gamma"],
                                                       self.sd[prefix + ".beta"]])])
-        # scratch: per-thread (mean, M2, count) partials + per-channel (mean, rstd)
-        scratch = self.tmp(1, 1, 3 * max(self.nthreads, c) + 2 * c, "nsc")
+        # scratch: per-channel (mean, rstd)
+        scratch = self.tmp(1, 1, 2 * c, "nsc")
         self.ops.append(Op(OP_NORM_ELU, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w,
                            w_off=w_off, w_len=w_len, scratch=self.off(scratch), oh=h, ow=w, name=prefix))
         self.free(scratch)
@@ -405,7 +470,7 @@ class ProgramBuilder:
         self.conv("end_conv", t, dst=out)
         self.free(t)
         # scratch for the sampler phases that follow the network (residual P*x-y, reductions)
-        post = self.new("post", 1, 1, 2 * H * W + 4 * self.nthreads)
+        post = self.new("post", 1, 1, 2 * H * W + 4 * self.nthreads)   # one plane of 2*H*W + 4*nthr (+pad)
         blob = np.concatenate(self.blob) if self.blob else np.zeros(0, np.float32)
         assert blob.size == self.blob_len
         max_w_len = max(op.w_len for op in self.ops)
@@ -416,7 +481,7 @@ class ProgramBuilder:
                 v = getattr(op, f)
                 setattr(op, f, -1 if (v is None or v == -1) else self.ar.offs[v])
         return Program(self.ops, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out], H, W, ngf,
-                       self.channels, self.nthreads, max_w_len, self.flops,
+                       self.channels, self.nthreads, max_w_len, self.flops, precision=self.precision,
                        post_off=self.ar.offs[post])
 
     def _stage(self, p: str, skip: str, cout: int, dil: Optional[int]) -> str:
@@ -445,16 +510,59 @@ class ProgramBuilder:
         return self.residual(p + ".1", out, cout, False, dil)
 
 
+def tf32_rna(x: np.ndarray) -> np.ndarray:
+    """fp32 -> TF32 (10-bit mantissa), round to nearest with ties away from zero: cvt.rna.tf32.f32."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channels: int = 2,
-                  nthreads: int = 256) -> Program:
-    return ProgramBuilder(state, ngf, H, W, channels, nthreads).build()
+                  nthreads: int = 256, precision: str = "fp32") -> Program:
+    return ProgramBuilder(state, ngf, H, W, channels, nthreads, precision).build()
 
 
 # ---------------------------------------------------------------------------
 # torch (CPU) interpreter of a Program -- host-side check of the schedule only
 # ---------------------------------------------------------------------------
+def tensor_view(arena, off: int, c: int, h: int, w: int):
+    """[c,h,w] view of a planar tensor stored at float offset ``off`` with padded plane stride
+    (works for numpy arrays and torch tensors)."""
+    ps = PS(h, w)
+    if isinstance(arena, np.ndarray):
+        return np.lib.stride_tricks.as_strided(arena[off:], (c, h, w), (4 * ps, 4 * w, 4))
+    return arena.as_strided((c, h, w), (ps, w, 1), off)
+
+
+def conv_weights(prog: Program, op: Op):
+    """Decode (weight [cout,cin,k,k], bias or None) of a conv op back from the packed blob."""
+    import torch
+    blob = torch.from_numpy(prog.blob)
+    k = op.ksize
+    if op.kind == OP_CONV:
+        cb = op.cb
+        nw = op.cout * op.cin * k * k
+        wp = blob[op.w_off:op.w_off + nw].view(op.cout // cb, op.cin, k * k, cb)
+        wt = wp.permute(0, 3, 1, 2).reshape(op.cout, op.cin, k, k)
+    else:
+        live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
+        KC, NT = (op.cin + 7) // 8, (op.cout + 7) // 8
+        n = len(live) * KC * NT * 32 * 4
+        frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, 4)
+        full = torch.zeros(NT * 8, KC * 8, k * k)
+        g, t = torch.arange(32) >> 2, torch.arange(32) & 3
+        for i, tap in enumerate(live):
+            for kc in range(KC):
+                for nt in range(NT):
+                    full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + frag[i, kc, nt, :, 2]
+                    full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + frag[i, kc, nt, :, 3]
+        wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
+    bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
+    return wt, bias
+
+
 def simulate(prog: Program, x, upto: Optional[int] = None):
-    """Run the program on one sample ``x`` ([channels,H,W] float32 torch tensor) with torch CPU ops.
+    """Run the program on one sample ``x`` ([channels,H,W] float32 torch tensor) with torch CPU ops
+    (fp32 arithmetic whatever the program's precision mode).
 
     Returns (raw network output [channels,H,W] (before the /sigma of ncsnv2.py:295-298), arena)."""
     import torch
@@ -462,12 +570,11 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
 
     arena = torch.zeros(prog.arena_floats, dtype=torch.float32)
     blob = torch.from_numpy(prog.blob)
-    n_in = prog.channels * prog.H * prog.W
-    arena[prog.in_off:prog.in_off + n_in] = x.reshape(-1).float()
 
     def view(off, c, h, w):
-        return arena[off:off + c * h * w].view(c, h, w)
+        return tensor_view(arena, off, c, h, w)
 
+    view(prog.in_off, prog.channels, prog.H, prog.W).copy_(x.float())
     for i, op in enumerate(prog.ops):
         if upto is not None and i >= upto:
             break
@@ -494,12 +601,9 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
             a += F.interpolate(s[None], size=(op.oh, op.ow), mode="bilinear", align_corners=True)[0]
             if op.edst >= 0:
                 view(op.edst, op.cin, op.oh, op.ow).copy_(F.elu(a))
-        elif op.kind == OP_CONV:
-            k, cb = op.ksize, op.cb
-            nw = op.cout * op.cin * k * k
-            wp = blob[op.w_off:op.w_off + nw].view(op.cout // cb, op.cin, k * k, cb)
-            wt = wp.permute(0, 3, 1, 2).reshape(op.cout, op.cin, k, k)
-            bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
+        elif op.kind in (OP_CONV, OP_CONV_MMA):
+            k = op.ksize
+            wt, bias = conv_weights(prog, op)
             s = view(op.src, op.cin, op.h, op.w)[None]
             if op.flags & F_POOL:
                 # packed weights already carry the 1/4; conv at full res then 2x2 SUM
@@ -520,5 +624,5 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
                 view(op.edst, op.cout, op.oh, op.ow).copy_(F.elu(v))
         else:
             raise ValueError(op.kind)
-    out = arena[prog.out_off:prog.out_off + n_in].view(prog.channels, prog.H, prog.W).clone()
+    out = view(prog.out_off, prog.channels, prog.H, prog.W).clone()
     return out, arena

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../score_based_channels_b200/csrc/sbc_mma.h"
 #include "../../score_based_channels_b200/csrc/sbc_ops.h"
 
 template <int PX, int CB>
@@ -32,6 +33,76 @@ static int conv_dispatch(const SbcOp& op, float* arena, const float* wseg) {
     return -1;
 }
 
+// warp-level emulation of the tensor-core conv: every lane's fragments are gathered with the shared
+// per-lane helpers (csrc/sbc_mma.h), the m16n8k8 product is done as plain matrices (operands rounded
+// to TF32 like the hardware path; 3-term split when SBC_F_X3), then the per-lane epilogue runs.
+static void conv_mma(const SbcOp& op, float* arena, const float* blob) {
+    SbcMmaGeom G;
+    sbc_mma_geom(op, G);
+    const bool x3 = (op.flags & SBC_F_X3) != 0;
+    const float* wfrag = blob + op.w_off;
+    const int k = op.ksize, r = k / 2;
+    for (int mt = 0; mt < G.MT; mt++)
+        for (int nt = 0; nt < G.NT; nt++) {
+            float D[16][8];
+            memset(D, 0, sizeof D);
+            for (int quad = 0; quad < G.nq; quad++) {
+                int s = 0;
+                for (int tap = 0; tap < k * k; tap++) {
+                    if (!((op.tapmask >> tap) & 1)) continue;
+                    const int dy = (tap / k - r) * op.dil, dx = (tap % k - r) * op.dil;
+                    for (int kc = 0; kc < G.KC; kc++, s++) {
+                        float Ah[16][8], Al[16][8], Bh[8][8], Bl[8][8];
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int g = lane >> 2, t = lane & 3;
+                            int iy0, ix0, iy1, ix1;
+                            bool ok0, ok1;
+                            sbc_mma_row(op, G, mt, quad, g, iy0, ix0, ok0);
+                            sbc_mma_row(op, G, mt, quad, g + 8, iy1, ix1, ok1);
+                            float a[4];
+                            sbc_mma_a_frag(op, arena, iy0, ix0, ok0, iy1, ix1, ok1, dy, dx, kc, lane, a);
+                            const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
+                            for (int i = 0; i < 4; i++) {
+                                Ah[rr[i]][cc[i]] = sbc_tf32(a[i]);
+                                Al[rr[i]][cc[i]] = sbc_tf32(a[i] - Ah[rr[i]][cc[i]]);
+                            }
+                            const float* b = wfrag + ((size_t)(s * G.NT + nt) * 32 + lane) * 4;
+                            Bh[t][g] = b[0]; Bh[t + 4][g] = b[1]; Bl[t][g] = b[2]; Bl[t + 4][g] = b[3];
+                        }
+                        for (int m = 0; m < 16; m++)
+                            for (int n = 0; n < 8; n++) {
+                                float d = D[m][n];
+                                if (x3) {
+                                    for (int kk = 0; kk < 8; kk++) d += Al[m][kk] * Bh[kk][n];
+                                    for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bl[kk][n];
+                                }
+                                for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bh[kk][n];
+                                D[m][n] = d;
+                            }
+                    }
+                }
+            }
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t = lane & 3;
+                const float c[4] = {D[g][2 * t], D[g][2 * t + 1], D[g + 8][2 * t], D[g + 8][2 * t + 1]};
+                sbc_mma_epilogue(op, arena, blob, mt, nt, lane, c);
+            }
+        }
+}
+
+static void norm_op(const SbcOp& op, float* arena, const float* wseg, int nthr) {
+    const int S = sbc_norm_S(op, nthr);
+    for (int c = 0; c < op.cin; c++) {
+        float sum = 0.f;
+        for (int s = 0; s < S; s++) sum += sbc_norm_partial_sum(op, arena, c, s, S);
+        const float mean = sum * (1.f / (float)(op.h * op.w));
+        float m2 = 0.f;
+        for (int s = 0; s < S; s++) m2 += sbc_norm_partial_m2(op, arena, c, s, S, mean);
+        sbc_norm_store_stats(op, arena, c, mean, m2);
+    }
+    for (int t = 0; t < nthr; t++) sbc_norm_apply(op, arena, wseg, t, nthr);
+}
+
 extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const float* blob, float* arena, int nthr,
                                int stop_op) {
     const SbcOp* ops = reinterpret_cast<const SbcOp*>(op_table);
@@ -43,10 +114,11 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const float* 
             case SBC_OP_CONV:
                 if (conv_dispatch(op, arena, wseg)) return -1;
                 break;
+            case SBC_OP_CONV_MMA:
+                conv_mma(op, arena, blob);
+                break;
             case SBC_OP_NORM_ELU:
-                for (int t = 0; t < nthr; t++) sbc_norm_phaseA(op, arena, t, nthr);
-                for (int t = 0; t < nthr; t++) sbc_norm_phaseB(op, arena, t, nthr);
-                for (int t = 0; t < nthr; t++) sbc_norm_phaseC(op, arena, wseg, t, nthr);
+                norm_op(op, arena, wseg, nthr);
                 break;
             case SBC_OP_ELU:
                 for (int t = 0; t < nthr; t++) sbc_elu_op(op, arena, t, nthr);

@@ -20,7 +20,8 @@ EMU_DIR = os.path.join(REPO, "tests", "emu")
 @pytest.fixture(scope="module")
 def emu():
     so = os.path.join(EMU_DIR, "libemu.so")
-    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(REPO, "score_based_channels_b200", "csrc", "sbc_ops.h")]
+    csrc = os.path.join(REPO, "score_based_channels_b200", "csrc")
+    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(csrc, f) for f in ("sbc_ops.h", "sbc_mma.h", "sbc_program.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
     lib = C.CDLL(so)
@@ -35,8 +36,7 @@ def emu():
 
 def run_emu(lib, prog, x, stop=-1):
     arena = np.zeros(prog.arena_floats, np.float32)
-    n_in = prog.channels * prog.H * prog.W
-    arena[prog.in_off:prog.in_off + n_in] = x.reshape(-1)
+    program.tensor_view(arena, prog.in_off, prog.channels, prog.H, prog.W)[...] = x
     tab = np.ascontiguousarray(prog.op_table())
     rc = lib.emu_run_program(tab.ctypes.data, tab.shape[0], prog.blob.ctypes.data, arena.ctypes.data, prog.nthreads,
                              stop)
@@ -44,44 +44,42 @@ def run_emu(lib, prog, x, stop=-1):
     return arena
 
 
+# tolerance on the per-sample relative L2 error of one forward, per precision mode
+FWD_TOL = {"fp32": 2e-5, "tf32x3": 2e-5, "tf32": 6e-3}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
 @pytest.mark.parametrize("name,H,W", [("forward_ngf8.npz", 64, 16), ("forward_ngf8_32x8.npz", 32, 8),
                                       ("forward_ngf16.npz", 64, 16)])
-def test_emulated_forward_matches_reference_golden(emu, name, H, W):
+def test_emulated_forward_matches_reference_golden(emu, name, H, W, prec):
     g = np.load(os.path.join(GOLDEN, name))
     sd = params.random_state(int(g["ngf"]), seed=int(g["wseed"]))
-    prog = program.build_program(sd, int(g["ngf"]), H, W)
+    prog = program.build_program(sd, int(g["ngf"]), H, W, precision=prec)
     sig = sd["sigmas"]
-    n = 2 * H * W
     for b in range(g["x"].shape[0]):
         arena = run_emu(emu, prog, g["x"][b])
-        out = arena[prog.out_off:prog.out_off + n].reshape(2, H, W) / sig[int(g["y"][b])]
+        out = program.tensor_view(arena, prog.out_off, 2, H, W) / sig[int(g["y"][b])]
         rel = np.linalg.norm(out - g["out"][b]) / np.linalg.norm(g["out"][b])
-        assert rel < 2e-5, (name, b, rel)
+        assert rel < FWD_TOL[prec], (name, b, rel)
 
 
-def test_emulated_ops_match_simulator_op_by_op(emu):
-    """Every op of the program, individually: emulated device code vs the torch simulator, both
-    started from the same arena state (so a failure names the op)."""
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_emulated_ops_match_simulator_op_by_op(emu, prec):
+    """Prefix runs: the arena after k ops, emulated device code vs the torch simulator (a failure
+    names the op)."""
     sd = params.random_state(8, seed=1)
-    prog = program.build_program(sd, 8, 64, 16)
+    prog = program.build_program(sd, 8, 64, 16, precision=prec)
     x = (np.random.default_rng(0).standard_normal((2, 64, 16)) * 3).astype(np.float32)
-    _, ref_arena = program.simulate(prog, torch.from_numpy(x))
-    arena = run_emu(emu, prog, x)
-    # end-to-end arena agreement on every tensor that is still defined at the end
-    n = 2 * 64 * 16
-    a = arena[prog.out_off:prog.out_off + n]
-    r = ref_arena.numpy()[prog.out_off:prog.out_off + n]
-    assert np.linalg.norm(a - r) / np.linalg.norm(r) < 2e-5
-    # prefix runs: the state after k ops must agree for a spread of k (localises a broken op)
-    for k in list(range(1, 40)) + list(range(40, len(prog.ops), 7)):
+    for k in list(range(1, 40)) + list(range(40, len(prog.ops), 7)) + [len(prog.ops)]:
         _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
         ea = run_emu(emu, prog, x, stop=k)
         op = prog.ops[k - 1]
-        outs = [(o, op.cout * op.oh * op.ow) for o in (op.dst, op.acc, op.edst) if o >= 0]
-        for off, cnt in outs:
-            d = np.abs(ea[off:off + cnt] - ra.numpy()[off:off + cnt]).max()
-            s = np.abs(ra.numpy()[off:off + cnt]).max() + 1e-6
-            assert d / s < 5e-5, (k - 1, op.name, op.kind, d, s)
+        for off in (op.dst, op.acc, op.edst):
+            if off >= 0:
+                e = program.tensor_view(ea, off, op.cout, op.oh, op.ow)
+                r = program.tensor_view(ra.numpy(), off, op.cout, op.oh, op.ow)
+                d, sc = np.abs(e - r).max(), np.abs(r).max() + 1e-6
+                assert d / sc < 5e-5, (k - 1, op.name, op.kind, d, sc)
 
 
 def test_emulated_langevin_step_matches_oracle(emu):
@@ -103,8 +101,8 @@ def test_emulated_langevin_step_matches_oracle(emu):
     tot = emu.emu_langevin_step(arena.ctypes.data, prog.in_off, prog.out_off, prog.post_off, P.ctypes.data,
                                 Y.ctypes.data, H.ctypes.data, en.ctypes.data, sigma, alpha, den, nscale, 0, 0, 0, Nt,
                                 Nr, Np, prog.nthreads)
-    n = Nt * Nr
-    x1 = arena[prog.in_off:prog.in_off + n].reshape(Nt, Nr) + 1j * arena[prog.in_off + n:prog.in_off + 2 * n].reshape(Nt, Nr)
+    xv = program.tensor_view(arena, prog.in_off, 2, Nt, Nr)
+    x1 = xv[0] + 1j * xv[1]
     ref = g["xs"][0, b]
     assert np.abs(x1 - ref).max() < 1e-5 * np.abs(ref).max()
     nm = tot / np.sum(np.abs(H) ** 2)

@@ -28,9 +28,14 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _model(ngf, wseed, dev):
+# precision mode -> (forward rel-L2 tol, ALD state tol relative to max|x|, NMSE-log rtol)
+TOL = {"fp32": (2e-5, 1e-5, 1e-4), "tf32x3": (2e-5, 1e-5, 1e-4), "tf32": (6e-3, 2e-3, 5e-3)}
+PRECS = list(TOL)
+
+
+def _model(ngf, wseed, dev, prec="tf32x3"):
     sd = params.random_state(ngf, seed=wseed)
-    return sd, make_model(sd, ngf=ngf).to(dev)
+    return sd, make_model(sd, ngf=ngf, precision=prec).to(dev)
 
 
 def _rel(a, b):
@@ -46,14 +51,15 @@ def test_native_library_is_the_one_running(dev):
     assert info.arena_in_smem == 1 and info.weights_staged == 1
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name,H,W", [("forward_ngf8.npz", 64, 16), ("forward_ngf8_32x8.npz", 32, 8),
                                       ("forward_ngf16.npz", 64, 16)])
-def test_forward_matches_reference_golden(dev, name, H, W):
+def test_forward_matches_reference_golden(dev, name, H, W, prec):
     g = np.load(os.path.join(GOLDEN, name))
-    sd, m = _model(int(g["ngf"]), int(g["wseed"]), dev)
+    sd, m = _model(int(g["ngf"]), int(g["wseed"]), dev, prec)
     out = m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)).cpu().numpy()
     for b in range(out.shape[0]):
-        assert _rel(out[b], g["out"][b]) < 2e-5, (name, b, _rel(out[b], g["out"][b]))
+        assert _rel(out[b], g["out"][b]) < TOL[prec][0], (name, prec, b, _rel(out[b], g["out"][b]))
 
 
 def test_forward_strided_input_like_reference_call_site(dev):
@@ -71,11 +77,13 @@ def test_forward_strided_input_like_reference_call_site(dev):
         assert _rel(out[b], ref[b]) < 2e-5
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", ["ald_cfg1.npz", "ald_mid.npz"])
-def test_ald_matches_reference_golden_with_replayed_noise(dev, name):
+def test_ald_matches_reference_golden_with_replayed_noise(dev, name, prec):
     """BASELINE config 1 (B=4, 2 levels x 3 steps) and a mid-trajectory case, reference noise replayed."""
     g = np.load(os.path.join(GOLDEN, name))
-    sd, m = _model(int(g["ngf"]), int(g["wseed"]), dev)
+    sd, m = _model(int(g["ngf"]), int(g["wseed"]), dev, prec)
+    _, xtol, ntol = TOL[prec]
     lv, se = g["levels"], int(g["steps_each"])
     t = lambda k: torch.from_numpy(g[k]).to(dev)
     kw = dict(noise_var=float(g["noise_var"]), alpha_step=float(g["alpha_step"]), beta=float(g["beta"]),
@@ -83,12 +91,12 @@ def test_ald_matches_reference_golden_with_replayed_noise(dev, name):
     X, nlog = sampler.ald_run(m, t("P"), t("Y"), t("X0"), t("H"), level_begin=int(lv[0]), level_end=int(lv[-1]) + 1,
                               ext_noise=t("ext_noise"), **kw)
     scale = np.abs(g["xs"][-1]).max()
-    assert np.abs(X.cpu().numpy() - g["xs"][-1]).max() < 1e-5 * scale
-    assert np.allclose(nlog.cpu().numpy(), g["nmse"], rtol=1e-4, atol=0)
+    assert np.abs(X.cpu().numpy() - g["xs"][-1]).max() < xtol * scale
+    assert np.allclose(nlog.cpu().numpy(), g["nmse"], rtol=ntol, atol=0)
     # intermediate state after the first level
     X1, _ = sampler.ald_run(m, t("P"), t("Y"), t("X0"), t("H"), level_begin=int(lv[0]), level_end=int(lv[0]) + 1,
                             ext_noise=t("ext_noise")[:se], **kw)
-    assert np.abs(X1.cpu().numpy() - g["xs"][se - 1]).max() < 1e-5 * scale
+    assert np.abs(X1.cpu().numpy() - g["xs"][se - 1]).max() < xtol * scale
 
 
 def _problem(B, Nt=64, Nr=16, Np=38, snr=0.0, seed=0):
@@ -212,7 +220,7 @@ sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from test_gpu_parity import _model, _problem, SIGMA_END
 from score_based_channels_b200 import sampler
 dev = torch.device('cuda:0')
-sd, m = _model(8, 1, dev)
+sd, m = _model(8, 1, dev, sys.argv[2])
 P, Y, X0, H, nv = _problem(3, seed=4)
 tt = lambda a: torch.from_numpy(a).to(dev)
 X, l = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), noise_var=nv, alpha_step=3e-11, beta=0.01,
@@ -222,14 +230,15 @@ np.savez(sys.argv[1], X=X.cpu().numpy(), l=l.cpu().numpy(), smem=info.arena_in_s
 """
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("env,expect", [({"SBC_STAGE_WEIGHTS": "0"}, (1, 0)), ({"SBC_FORCE_GLOBAL_ARENA": "1"}, (0, 1))])
-def test_alternate_execution_modes_are_bit_identical(dev, tmp_path, env, expect):
+def test_alternate_execution_modes_are_bit_identical(dev, tmp_path, env, expect, prec):
     """Parameters read straight from L2 instead of the cp.async.bulk ring, and the activation arena in
     global memory (the mode used when Nt x Nr does not fit in shared memory): same bits."""
     outs = []
     for e in ({}, env):
         f = str(tmp_path / ("o%d.npz" % len(outs)))
-        subprocess.check_call([sys.executable, "-c", _SUBPROCESS % (REPO, REPO), f], env={**os.environ, **e})
+        subprocess.check_call([sys.executable, "-c", _SUBPROCESS % (REPO, REPO), f, prec], env={**os.environ, **e})
         outs.append(np.load(f))
     assert (int(outs[1]["smem"]), int(outs[1]["staged"])) == expect
     assert np.array_equal(outs[0]["X"], outs[1]["X"]) and np.array_equal(outs[0]["l"], outs[1]["l"])
@@ -250,15 +259,16 @@ def test_large_antenna_config_runs_from_global_arena(dev):
     assert np.allclose(nlog.cpu().numpy(), nlo, rtol=1e-4)
 
 
-def test_debug_arena_matches_schedule_simulator_op_by_op(dev):
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_debug_arena_matches_schedule_simulator_op_by_op(dev, prec):
     """Localises a broken op on the GPU: arena after k ops vs the torch simulator of the same program."""
-    sd, m = _model(8, 1, dev)
+    sd, m = _model(8, 1, dev, prec)
     pm = m.packed(64, 16, dev)
     prog = pm.prog
     x = (np.random.default_rng(0).standard_normal((2, 64, 16)) * 3).astype(np.float32)
     xd = torch.from_numpy(x).to(dev)
     arena = torch.empty(prog.arena_floats, dtype=torch.float32, device=dev)
-    for k in [1, 2, 3, 5, 8, 13, 21, 30, 40, 60, 80, 100, 120, 140, len(prog.ops)]:
+    for k in list(range(1, 60, 2)) + list(range(60, len(prog.ops), 5)) + [len(prog.ops)]:
         _lib.check(_lib.lib().sbc_debug_arena(pm.handle, xd.data_ptr(), k, arena.data_ptr(), None), "debug")
         torch.cuda.synchronize()
         _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
@@ -266,7 +276,7 @@ def test_debug_arena_matches_schedule_simulator_op_by_op(dev):
         ga, ra = arena.cpu().numpy(), ra.numpy()
         for off in (op.dst, op.acc, op.edst):
             if off >= 0:
-                cnt = op.cout * op.oh * op.ow
-                d = np.abs(ga[off:off + cnt] - ra[off:off + cnt]).max()
-                s = np.abs(ra[off:off + cnt]).max() + 1e-6
+                e = program.tensor_view(ga, off, op.cout, op.oh, op.ow)
+                r = program.tensor_view(ra, off, op.cout, op.oh, op.ow)
+                d, s = np.abs(e - r).max(), np.abs(r).max() + 1e-6
                 assert d / s < 5e-5, (k - 1, op.name, d, s)

@@ -12,9 +12,10 @@ from score_based_channels_b200 import _lib, params, program, sampler, synth  # n
 from score_based_channels_b200.models import make_model  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+PREC = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
 dev = torch.device("cuda:0")
 sd = params.random_state(8, seed=1)
-m = make_model(sd, ngf=8).to(dev)
+m = make_model(sd, ngf=8, precision=PREC).to(dev)
 pm = m.packed(64, 16, dev)
 prog = pm.prog
 x = torch.randn(B, 2, 64, 16, device=dev)
@@ -28,7 +29,7 @@ for _ in range(10):
     m(x, y)
 e1.record()
 torch.cuda.synchronize()
-print("forward B=%d: %.3f ms per launch" % (B, e0.elapsed_time(e1) / 10))
+print("precision %s forward B=%d: %.3f ms per launch" % (PREC, B, e0.elapsed_time(e1) / 10))
 
 stamps = torch.zeros(len(prog.ops) + 2, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, stamps.data_ptr()), "prof")
@@ -43,15 +44,16 @@ st = stamps.cpu().numpy()
 d = np.diff(st)
 tot = st[-1] - st[0]
 print("CTA0 first step: %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
-kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc"}
+kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "conv_mma"}
 by_kind = {}
 rows = []
 for i, op in enumerate(prog.ops):
     c = int(d[i])
     key = kinds[op.kind]
-    if op.kind == 1:
-        key = "conv %dx%d c%d->%d k%d d%d%s px%d cb%d ks%d" % (op.h, op.w, op.cin, op.cout, op.ksize, op.dil,
-                                                          " pool" if op.flags else "", op.px, op.cb, op.ks)
+    if op.kind in (1, 6):
+        key = "conv%s %dx%d c%d->%d k%d d%d%s px%d cb%d ks%d" % ("_mma" if op.kind == 6 else "", op.h, op.w, op.cin,
+                                                               op.cout, op.ksize, op.dil,
+                                                               " pool" if op.flags & 1 else "", op.px, op.cb, op.ks)
     else:
         key = "%s %dx%d c%d" % (key, op.h, op.w, op.cin)
     by_kind.setdefault(key, [0, 0])
