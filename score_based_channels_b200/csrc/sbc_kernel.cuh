@@ -14,7 +14,7 @@
 #include "sbc_mma.h"
 #include "sbc_ops.h"
 
-#define SBC_NTHREADS 256
+#define SBC_NTHREADS 512
 
 struct SbcLaunch {
     // layer program
@@ -141,41 +141,75 @@ __device__ __forceinline__ void sbc_mma_tf32(float (&d)[4], const float (&a)[4],
 #define SBC_MMA_SLOTS 8
 
 // Accumulate K steps [s0, s1) for up to 8 slots (slot j = tile mt0 + (j / nq) * mt_stride, pooling
-// position j % nq) sharing one cout tile nt.
+// position j % nq) sharing one cout tile nt.  B fragments come from the staged parameter segment.
+// Per slot the gather keeps two base offsets and a 12-bit validity word (3 row bits + 3 column bits
+// for each of the two tile rows a lane feeds), so a K step costs a few integer ops per MMA.
 template <bool X3>
 __device__ __forceinline__ void sbc_mma_pass(const SbcOp& op, const SbcMmaGeom& G, const float* arena,
-                                             const float4* __restrict__ wfrag, int mt0, int mt_stride, int nslots,
-                                             int nt, int s0, int s1, int lane, float (&acc)[SBC_MMA_SLOTS][4]) {
-    const int g = lane >> 2;
-    int iy0[SBC_MMA_SLOTS], ix0[SBC_MMA_SLOTS], iy1[SBC_MMA_SLOTS], ix1[SBC_MMA_SLOTS];
-    unsigned ok0 = 0, ok1 = 0;
+                                             const float* wseg, int mt0, int mt_stride, int nslots, int nt, int s0,
+                                             int s1, int lane, float (&acc)[SBC_MMA_SLOTS][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int h = op.h, w = op.w, k = op.ksize, r = k >> 1, dil = op.dil, cin = op.cin;
+    const int ps = SBC_PS(h, w);
+    int off0[SBC_MMA_SLOTS], off1[SBC_MMA_SLOTS];
+    unsigned vm[SBC_MMA_SLOTS];
 #pragma unroll
     for (int j = 0; j < SBC_MMA_SLOTS; j++) {
-        iy0[j] = ix0[j] = iy1[j] = ix1[j] = 0;
+        off0[j] = off1[j] = 0;
+        vm[j] = 0;
         if (j < nslots) {
             const int mt = mt0 + (j / G.nq) * mt_stride, quad = j % G.nq;
+            int iy0, ix0, iy1, ix1;
             bool a, b;
-            sbc_mma_row(op, G, mt, quad, g, iy0[j], ix0[j], a);
-            sbc_mma_row(op, G, mt, quad, g + 8, iy1[j], ix1[j], b);
-            ok0 |= (unsigned)a << j;
-            ok1 |= (unsigned)b << j;
+            sbc_mma_row(op, G, mt, quad, g, iy0, ix0, a);
+            sbc_mma_row(op, G, mt, quad, g + 8, iy1, ix1, b);
+            off0[j] = iy0 * w + ix0;
+            off1[j] = iy1 * w + ix1;
+            unsigned m = 0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int d = (q - r) * dil;
+                m |= (unsigned)(a && iy0 + d >= 0 && iy0 + d < h) << q;
+                m |= (unsigned)(a && ix0 + d >= 0 && ix0 + d < w) << (3 + q);
+                m |= (unsigned)(b && iy1 + d >= 0 && iy1 + d < h) << (6 + q);
+                m |= (unsigned)(b && ix1 + d >= 0 && ix1 + d < w) << (9 + q);
+            }
+            vm[j] = m;
         }
     }
-    const int k = op.ksize, r = k >> 1, KK = k * k;
+    constexpr int E = X3 ? 4 : 2;
+    const float* src = arena + op.src;
     int s = 0;
-    for (int tap = 0; tap < KK; tap++) {
+    for (int tap = 0; tap < k * k; tap++) {
         if (!((op.tapmask >> tap) & 1)) continue;
-        const int ty = tap / k;
-        const int dy = (ty - r) * op.dil, dx = (tap - ty * k - r) * op.dil;
+        const int ky = tap / k, kx = tap - ky * k;
+        const int doff = (ky - r) * dil * w + (kx - r) * dil;
         for (int kc = 0; kc < G.KC; kc++, s++) {
             if (s < s0 || s >= s1) continue;
-            const float4 b = __ldg(&wfrag[(size_t)(s * G.NT + nt) * 32 + lane]);
+            const float* bp = wseg + ((size_t)(s * G.NT + nt) * 32 + lane) * E;
+            float bh0, bh1, bl0 = 0.f, bl1 = 0.f;
+            if (X3) {
+                const float4 b = *reinterpret_cast<const float4*>(bp);
+                bh0 = b.x; bh1 = b.y; bl0 = b.z; bl1 = b.w;
+            } else {
+                const float2 b = *reinterpret_cast<const float2*>(bp);
+                bh0 = b.x; bh1 = b.y;
+            }
+            const int c0 = kc * 8 + t;
+            const bool k0 = c0 < cin, k1 = c0 + 4 < cin;
+            const float* p0 = src + c0 * ps + doff;
+            const float* p1 = p0 + 4 * ps;
 #pragma unroll
             for (int j = 0; j < SBC_MMA_SLOTS; j++) {
                 if (j < nslots) {
+                    const unsigned m = vm[j];
+                    const bool v0 = ((m >> ky) & (m >> (3 + kx)) & 1u) != 0;
+                    const bool v1 = ((m >> (6 + ky)) & (m >> (9 + kx)) & 1u) != 0;
                     float a[4];
-                    sbc_mma_a_frag(op, arena, iy0[j], ix0[j], (ok0 >> j) & 1, iy1[j], ix1[j], (ok1 >> j) & 1, dy, dx,
-                                   kc, lane, a);
+                    a[0] = (v0 && k0) ? p0[off0[j]] : 0.f;
+                    a[1] = (v1 && k0) ? p0[off1[j]] : 0.f;
+                    a[2] = (v0 && k1) ? p1[off0[j]] : 0.f;
+                    a[3] = (v1 && k1) ? p1[off1[j]] : 0.f;
                     float ah[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) ah[i] = sbc_tf32(a[i]);
@@ -183,10 +217,10 @@ __device__ __forceinline__ void sbc_mma_pass(const SbcOp& op, const SbcMmaGeom& 
                         float al[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) al[i] = sbc_tf32(a[i] - ah[i]);
-                        sbc_mma_tf32(acc[j], al, b.x, b.y);   // small terms first
-                        sbc_mma_tf32(acc[j], ah, b.z, b.w);
+                        sbc_mma_tf32(acc[j], al, bh0, bh1);   // small terms first
+                        sbc_mma_tf32(acc[j], ah, bl0, bl1);
                     }
-                    sbc_mma_tf32(acc[j], ah, b.x, b.y);
+                    sbc_mma_tf32(acc[j], ah, bh0, bh1);
                 }
             }
         }
@@ -194,12 +228,11 @@ __device__ __forceinline__ void sbc_mma_pass(const SbcOp& op, const SbcMmaGeom& 
 }
 
 template <bool X3>
-__device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, const float* blob, int tid) {
+__device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, const float* wseg, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = SBC_NTHREADS / 32;
     SbcMmaGeom G;
     sbc_mma_geom(op, G);
-    const float4* wfrag = reinterpret_cast<const float4*>(blob + op.w_off);
     float acc[SBC_MMA_SLOTS][4];
 
     if (op.ks > 1) {
@@ -212,7 +245,7 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, cons
         if (u < units) {
 #pragma unroll
             for (int j = 0; j < SBC_MMA_SLOTS; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-            sbc_mma_pass<X3>(op, G, arena, wfrag, mt, 0, G.nq, nt, (G.S * kp) / ks, (G.S * (kp + 1)) / ks, lane, acc);
+            sbc_mma_pass<X3>(op, G, arena, wseg, mt, 0, G.nq, nt, (G.S * kp) / ks, (G.S * (kp + 1)) / ks, lane, acc);
             float4 c = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
             if (G.nq == 4) {
 #pragma unroll
@@ -227,7 +260,7 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, cons
                 const float4 p = part[(warp + i) * 32 + lane];
                 c[0] += p.x; c[1] += p.y; c[2] += p.z; c[3] += p.w;
             }
-            sbc_mma_epilogue(op, arena, blob, mt, nt, lane, c);
+            sbc_mma_epilogue(op, arena, wseg, mt, nt, lane, c);
         }
         return;
     }
@@ -243,11 +276,11 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, cons
             if (ntile > tpp) ntile = tpp;
 #pragma unroll
             for (int j = 0; j < SBC_MMA_SLOTS; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-            sbc_mma_pass<X3>(op, G, arena, wfrag, mt0, mt_stride, ntile * G.nq, nt, 0, G.S, lane, acc);
+            sbc_mma_pass<X3>(op, G, arena, wseg, mt0, mt_stride, ntile * G.nq, nt, 0, G.S, lane, acc);
             if (G.nq == 1) {
 #pragma unroll
                 for (int j = 0; j < SBC_MMA_SLOTS; j++)
-                    if (j < ntile) sbc_mma_epilogue(op, arena, blob, mt0 + j * mt_stride, nt, lane, acc[j]);
+                    if (j < ntile) sbc_mma_epilogue(op, arena, wseg, mt0 + j * mt_stride, nt, lane, acc[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < SBC_MMA_SLOTS / 4; j++)
@@ -255,7 +288,7 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, float* arena, cons
                         float c[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) c[i] = acc[4 * j][i] + acc[4 * j + 1][i] + acc[4 * j + 2][i] + acc[4 * j + 3][i];
-                        sbc_mma_epilogue(op, arena, blob, mt0 + j * mt_stride, nt, lane, c);
+                        sbc_mma_epilogue(op, arena, wseg, mt0 + j * mt_stride, nt, lane, c);
                     }
             }
         }
@@ -404,8 +437,8 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                         sbc_conv_dispatch(op, arena, wseg, tid);
                         break;
                     case SBC_OP_CONV_MMA:
-                        if (op.flags & SBC_F_X3) sbc_conv_mma<true>(op, arena, L.blob, tid);
-                        else sbc_conv_mma<false>(op, arena, L.blob, tid);
+                        if (op.flags & SBC_F_X3) sbc_conv_mma<true>(op, arena, wseg, tid);
+                        else sbc_conv_mma<false>(op, arena, wseg, tid);
                         break;
                     case SBC_OP_NORM_ELU:
                         sbc_norm_stats(op, arena, tid);

@@ -6,7 +6,7 @@
 //     D[16 output pixels, 8 couts] += A[16 pixels, 8 cins] * B[8 cins, 8 couts]
 // with the fragment layout of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32
 //     lane = 4*g + t :  A: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4)      (row = pixel, col = cin)
-//                       B: b0=(k=t,n=g) b1=(k=t+4,n=g)                        (packed by program.py)
+//                       B: b0=(k=t,n=g) b1=(k=t+4,n=g)      (packed by program.py: hi0,hi1[,lo0,lo1] per lane)
 //                       C: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)    (row = pixel, col = cout)
 // A tile is 16 consecutive output pixels in row-major order.  ConvMeanPool (SBC_F_POOL) runs four
 // accumulations per tile -- one per position of the 2x2 pooling window, input pixel
@@ -78,7 +78,7 @@ SBC_HD void sbc_mma_a_frag(const SbcOp& op, const float* arena, int iy0, int ix0
 }
 
 // Epilogue of one lane for tile (mt, nt):  v = c + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v)
-SBC_HD void sbc_mma_epilogue(const SbcOp& op, float* arena, const float* blob, int mt, int nt, int lane,
+SBC_HD void sbc_mma_epilogue(const SbcOp& op, float* arena, const float* wseg, int mt, int nt, int lane,
                              const float (&c)[4]) {
     const int g = lane >> 2, t = lane & 3;
     const int P = op.oh * op.ow, ps = SBC_PS(op.oh, op.ow);
@@ -88,7 +88,7 @@ SBC_HD void sbc_mma_epilogue(const SbcOp& op, float* arena, const float* blob, i
         const int co = nt * 8 + 2 * t + (j & 1);
         if (q < P && co < op.cout) {
             const int idx = co * ps + q;
-            float v = c[j] + ((op.b_rel >= 0) ? blob[op.w_off + op.b_rel + co] : 0.f);
+            float v = c[j] + ((op.b_rel >= 0) ? wseg[op.b_rel + co] : 0.f);
             if (op.dst >= 0) arena[op.dst + idx] = v;
             if (op.acc >= 0) {
                 v += arena[op.acc + idx];

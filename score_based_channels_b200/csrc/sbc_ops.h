@@ -209,6 +209,7 @@ SBC_HD float sbc_norm_partial_sum(const SbcOp& op, const float* arena, int c, in
     const int HW = op.h * op.w;
     const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
     float sum = 0.f;
+#pragma unroll 8
     for (int i = s; i < HW; i += S) sum += x[i];
     return sum;
 }
@@ -216,6 +217,7 @@ SBC_HD float sbc_norm_partial_m2(const SbcOp& op, const float* arena, int c, int
     const int HW = op.h * op.w;
     const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
     float m2 = 0.f;
+#pragma unroll 8
     for (int i = s; i < HW; i += S) { const float d = x[i] - mean; m2 = fmaf(d, d, m2); }
     return m2;
 }
@@ -243,6 +245,7 @@ SBC_HD void sbc_norm_apply(const SbcOp& op, float* arena, const float* wseg, int
         const float b = fmaf(gamma[c], (mu - m) * rv * alpha[c], beta[c]);
         const float* x = arena + op.src + c * ps;
         float* o = arena + op.dst + c * ps;
+#pragma unroll 8
         for (int i = s; i < HW; i += S) o[i] = sbc_elu(fmaf(x[i] - mu, a, b));
     }
 }
@@ -252,6 +255,7 @@ SBC_HD void sbc_norm_apply(const SbcOp& op, float* arena, const float* wseg, int
 // ----------------------------------------------------------------------------------------------
 SBC_HD void sbc_elu_op(const SbcOp& op, float* arena, int tid, int nthr) {
     const int HW = op.h * op.w, n = op.cin * HW, ps = SBC_PS(op.h, op.w);
+#pragma unroll 4
     for (int i = tid; i < n; i += nthr) {
         const int c = i / HW, j = c * ps + (i - c * HW);
         arena[op.dst + j] = sbc_elu(arena[op.src + j]);

@@ -165,7 +165,7 @@ class ProgramBuilder:
     """Builds the op list for one (ngf, H, W) instance of NCSNv2Deepest."""
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
-                 channels: int = 2, nthreads: int = 256, precision: str = "fp32"):
+                 channels: int = 2, nthreads: int = 512, precision: str = "fp32"):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % (PRECISIONS,))
         self.precision = precision
@@ -255,15 +255,22 @@ class ProgramBuilder:
                            rels[1] if bias is not None else -1, px, cb, ks,
                            -1, oh, ow, name=prefix))
 
+    # largest parameter segment (floats) that one slot of the shared-memory ring holds; MMA convs whose
+    # fragment array is bigger are split into cout chunks (each chunk is its own op)
+    SLOT_FLOATS = 9248
+
     def _conv_mma(self, prefix, wt, bias, src, dst, acc, edst, dil, pool, ishape, oshape) -> None:
         """Tensor-core conv: implicit GEMM  D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]
-        per (tap, cin chunk) with mma.sync.m16n8k8 TF32 (csrc/sbc_mma.cuh).  The weights are packed in
-        B-fragment order, pre-split into TF32 hi/lo parts: frag[step][ntile][lane] = (hi0, hi1, lo0, lo1)
-        where lane = 4*g + t holds B[k = t (+4)][n = g], step = live_tap_index * KC + cin_chunk."""
+        per (tap, cin chunk) with mma.sync.m16n8k8 TF32 (csrc/sbc_mma.h).  The weights are packed in
+        B-fragment order: frag[step][ntile][lane] = (hi0, hi1[, lo0, lo1]) where lane = 4*g + t holds
+        B[k = t (+4)][n = g], step = live_tap_index * KC + cin_chunk; hi = TF32(w), lo = TF32(w - hi)
+        (lo only in the 3xTF32 mode)."""
         cin, h, w = ishape
         cout, oh, ow = oshape
         k = wt.shape[2]
         r = k // 2
+        x3 = self.precision == "tf32x3"
+        E = 4 if x3 else 2                          # floats per lane per fragment
         live = []
         for tap in range(k * k):
             dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
@@ -271,34 +278,44 @@ class ProgramBuilder:
                 live.append(tap)
         tapmask = sum(1 << t for t in live)
         KC, NT = (cin + 7) // 8, (cout + 7) // 8
+        per_nt = len(live) * KC * 32 * E
+        nt_chunk = NT
+        while nt_chunk > 1 and per_nt * nt_chunk + 8 * nt_chunk > self.SLOT_FLOATS:
+            nt_chunk //= 2
         wpad = np.zeros((NT * 8, KC * 8, k * k), np.float32)
         wpad[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
         g, t = np.arange(32) >> 2, np.arange(32) & 3
-        frag = np.zeros((len(live), KC, NT, 32, 4), np.float32)
-        for i, tap in enumerate(live):
-            for kc in range(KC):
-                for nt in range(NT):
-                    w0 = wpad[nt * 8 + g, kc * 8 + t, tap]
-                    w1 = wpad[nt * 8 + g, kc * 8 + t + 4, tap]
-                    h0, h1 = tf32_rna(w0), tf32_rna(w1)
-                    frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = h0, h1
-                    frag[i, kc, nt, :, 2], frag[i, kc, nt, :, 3] = tf32_rna(w0 - h0), tf32_rna(w1 - h1)
-        arrs = [frag] + ([bias] if bias is not None else [])
-        w_off, w_len, rels = self._push(arrs)
-        MT = (oh * ow + 15) // 16
-        units, S = MT * NT, len(live) * KC
         nwarps = self.nthreads // 32
-        ks = 1
-        while units * ks * 2 <= nwarps and ks * 2 <= S:
-            ks *= 2
-        scratch = self.tmp(1, 1, nwarps * 32 * 4, "ksp") if ks > 1 else None
-        flags = (F_POOL if pool else 0) | (F_X3 if self.precision == "tf32x3" else 0)
-        # parameters of MMA convs are read straight from global/L2 in fragment order (w_len = 0: not staged)
-        self.ops.append(Op(OP_CONV_MMA, flags, self.off(src), self.off(dst), self.off(acc), self.off(edst),
-                           cin, cout, h, w, k, dil, w_off, 0, rels[1] if bias is not None else -1, 0, 0, ks,
-                           self.off(scratch), oh, ow, tapmask=tapmask, name=prefix))
-        if scratch is not None:
-            self.free(scratch)
+        ps_out = PS(oh, ow)
+        for nt0 in range(0, NT, nt_chunk):
+            ntc = min(nt_chunk, NT - nt0)
+            co0, co1 = nt0 * 8, min(cout, (nt0 + ntc) * 8)
+            frag = np.zeros((len(live), KC, ntc, 32, E), np.float32)
+            for i, tap in enumerate(live):
+                for kc in range(KC):
+                    for nt in range(ntc):
+                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t, tap]
+                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t + 4, tap]
+                        h0, h1 = tf32_rna(w0), tf32_rna(w1)
+                        frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = h0, h1
+                        if x3:
+                            frag[i, kc, nt, :, 2], frag[i, kc, nt, :, 3] = tf32_rna(w0 - h0), tf32_rna(w1 - h1)
+            arrs = [frag] + ([bias[co0:co1]] if bias is not None else [])
+            w_off, w_len, rels = self._push(arrs)
+            MT = (oh * ow + 15) // 16
+            units, S = MT * ntc, len(live) * KC
+            ks = 1
+            while units * ks * 2 <= nwarps and ks * 2 <= S:
+                ks *= 2
+            scratch = self.tmp(1, 1, nwarps * 32 * 4, "ksp") if ks > 1 else None
+            flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0)
+            shift = lambda name: None if name is None else (name, co0 * ps_out)
+            self.ops.append(Op(OP_CONV_MMA, flags, self.off(src), shift(dst), shift(acc), shift(edst),
+                               cin, co1 - co0, h, w, k, dil, w_off, w_len, rels[1] if bias is not None else -1,
+                               0, 0, ks, self.off(scratch), oh, ow, tapmask=tapmask,
+                               name=prefix + ("" if nt_chunk == NT else "[co%d:%d]" % (co0, co1))))
+            if scratch is not None:
+                self.free(scratch)
 
     def norm_elu(self, prefix: str, src: str, dst: str) -> None:
         """dst = ELU(InstanceNorm2dPlus(src))  (``normalization.py:163-176`` + ``layers.py:13``)."""
@@ -479,7 +496,10 @@ class ProgramBuilder:
         for op in self.ops:
             for f in ("src", "dst", "acc", "edst", "scratch"):
                 v = getattr(op, f)
-                setattr(op, f, -1 if (v is None or v == -1) else self.ar.offs[v])
+                if isinstance(v, tuple):
+                    setattr(op, f, self.ar.offs[v[0]] + v[1])
+                else:
+                    setattr(op, f, -1 if (v is None or v == -1) else self.ar.offs[v])
         return Program(self.ops, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out], H, W, ngf,
                        self.channels, self.nthreads, max_w_len, self.flops, precision=self.precision,
                        post_off=self.ar.offs[post])
@@ -517,7 +537,7 @@ def tf32_rna(x: np.ndarray) -> np.ndarray:
 
 
 def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channels: int = 2,
-                  nthreads: int = 256, precision: str = "fp32") -> Program:
+                  nthreads: int = 512, precision: str = "fp32") -> Program:
     return ProgramBuilder(state, ngf, H, W, channels, nthreads, precision).build()
 
 
@@ -546,15 +566,18 @@ def conv_weights(prog: Program, op: Op):
     else:
         live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
         KC, NT = (op.cin + 7) // 8, (op.cout + 7) // 8
-        n = len(live) * KC * NT * 32 * 4
-        frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, 4)
+        E = 4 if (op.flags & F_X3) else 2
+        n = len(live) * KC * NT * 32 * E
+        frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, E)
         full = torch.zeros(NT * 8, KC * 8, k * k)
         g, t = torch.arange(32) >> 2, torch.arange(32) & 3
         for i, tap in enumerate(live):
             for kc in range(KC):
                 for nt in range(NT):
-                    full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + frag[i, kc, nt, :, 2]
-                    full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + frag[i, kc, nt, :, 3]
+                    lo0 = frag[i, kc, nt, :, 2] if E == 4 else 0.0
+                    lo1 = frag[i, kc, nt, :, 3] if E == 4 else 0.0
+                    full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + lo0
+                    full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + lo1
         wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
     bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
     return wt, bias

@@ -36,11 +36,12 @@ static int conv_dispatch(const SbcOp& op, float* arena, const float* wseg) {
 // warp-level emulation of the tensor-core conv: every lane's fragments are gathered with the shared
 // per-lane helpers (csrc/sbc_mma.h), the m16n8k8 product is done as plain matrices (operands rounded
 // to TF32 like the hardware path; 3-term split when SBC_F_X3), then the per-lane epilogue runs.
-static void conv_mma(const SbcOp& op, float* arena, const float* blob) {
+static void conv_mma(const SbcOp& op, float* arena, const float* wseg) {
     SbcMmaGeom G;
     sbc_mma_geom(op, G);
     const bool x3 = (op.flags & SBC_F_X3) != 0;
-    const float* wfrag = blob + op.w_off;
+    const float* wfrag = wseg;
+    const int E = x3 ? 4 : 2;
     const int k = op.ksize, r = k / 2;
     for (int mt = 0; mt < G.MT; mt++)
         for (int nt = 0; nt < G.NT; nt++) {
@@ -66,8 +67,9 @@ static void conv_mma(const SbcOp& op, float* arena, const float* blob) {
                                 Ah[rr[i]][cc[i]] = sbc_tf32(a[i]);
                                 Al[rr[i]][cc[i]] = sbc_tf32(a[i] - Ah[rr[i]][cc[i]]);
                             }
-                            const float* b = wfrag + ((size_t)(s * G.NT + nt) * 32 + lane) * 4;
-                            Bh[t][g] = b[0]; Bh[t + 4][g] = b[1]; Bl[t][g] = b[2]; Bl[t + 4][g] = b[3];
+                            const float* b = wfrag + ((size_t)(s * G.NT + nt) * 32 + lane) * E;
+                            Bh[t][g] = b[0]; Bh[t + 4][g] = b[1];
+                            Bl[t][g] = x3 ? b[2] : 0.f; Bl[t + 4][g] = x3 ? b[3] : 0.f;
                         }
                         for (int m = 0; m < 16; m++)
                             for (int n = 0; n < 8; n++) {
@@ -85,7 +87,7 @@ static void conv_mma(const SbcOp& op, float* arena, const float* blob) {
             for (int lane = 0; lane < 32; lane++) {
                 const int g = lane >> 2, t = lane & 3;
                 const float c[4] = {D[g][2 * t], D[g][2 * t + 1], D[g + 8][2 * t], D[g + 8][2 * t + 1]};
-                sbc_mma_epilogue(op, arena, blob, mt, nt, lane, c);
+                sbc_mma_epilogue(op, arena, wseg, mt, nt, lane, c);
             }
         }
 }
@@ -115,7 +117,7 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const float* 
                 if (conv_dispatch(op, arena, wseg)) return -1;
                 break;
             case SBC_OP_CONV_MMA:
-                conv_mma(op, arena, blob);
+                conv_mma(op, arena, wseg);
                 break;
             case SBC_OP_NORM_ELU:
                 norm_op(op, arena, wseg, nthr);
