@@ -1,0 +1,154 @@
+"""Host-side logic (CPU only): DotMap shim, minimal HDF5 reader, Channels shim, parameter catalogue,
+C-ABI surface of the built library, and the multi-rank sharding / gather (gloo, world_size 2)."""
+import copy
+import ctypes as C
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, have_reference
+from score_based_channels_b200 import dist as sdist
+from score_based_channels_b200 import dotmap_shim, hdf5_min, params, program
+
+REF_MAT = "/root/reference/sample_data/CDL-C_Nt64_Nr16_ULA0.50_seed4321.mat"
+LOCAL_MAT = os.path.join(REPO, "fixtures_local", "CDL-C_Nt64_Nr16_ULA0.50_seed4321.mat")
+MAT = REF_MAT if os.path.exists(REF_MAT) else LOCAL_MAT
+REF_CKPT = "/root/reference/pretrained_models/score-deepest-cdl-c.pt"
+LOCAL_CKPT = os.path.join(REPO, "fixtures_local", "score-deepest-cdl-c.pt")
+CKPT = REF_CKPT if os.path.exists(REF_CKPT) else LOCAL_CKPT
+
+
+def test_dotmap_shim_semantics():
+    D = dotmap_shim.DotMap
+    c = D()
+    c.model.ngf = 8
+    assert c.model.ngf == 8 and c["model"]["ngf"] == 8
+    assert not c.data.logit_transform            # missing key -> empty, falsy child (ncsnv2.py:201-202,270)
+    assert "logit_transform" in c.data           # ... and it is stored, like the real class
+    c2 = copy.deepcopy(c)
+    c2.model.ngf = 16
+    assert c.model.ngf == 8
+    dotmap_shim.install()
+    c3 = pickle.loads(pickle.dumps(c))
+    assert c3.model.ngf == 8 and c3.toDict()["model"]["ngf"] == 8
+
+
+@pytest.mark.skipif(not os.path.exists(CKPT), reason="reference checkpoint not available")
+def test_reference_checkpoint_loads_into_drop_in_model():
+    from score_based_channels_b200 import entry_common as ec
+    from score_based_channels_b200.ncsnv2 import NCSNv2Deepest
+    contents = ec.load_checkpoint(CKPT)
+    cfg = contents["config"]
+    assert cfg.model.ngf == 8 and cfg.model.num_classes == 2311 and cfg.sampling.steps_each == 3
+    m = NCSNv2Deepest(cfg)
+    res = m.load_state_dict(contents["model_state"])
+    assert not res.missing_keys and not res.unexpected_keys
+    assert set(m.state_dict().keys()) == set(contents["model_state"].keys())
+    assert torch.equal(m.sigmas, contents["model_state"]["sigmas"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 2, 64, 16), torch.zeros(1, dtype=torch.long))      # no CPU fallback
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference not mounted")
+def test_param_catalogue_matches_reference_module():
+    import sys
+    sys.path.insert(0, "/root/reference")
+    dotmap_shim.install()
+    from ncsnv2.models.ncsnv2 import NCSNv2Deepest as Ref
+    from score_based_channels_b200.models import make_config
+    for ngf in (8, 16):
+        cfg = make_config(ngf=ngf)
+        cfg.device = "cpu"
+        ref = {k: tuple(v.shape) for k, v in Ref(cfg).state_dict().items()}
+        assert ref == dict(params.param_shapes(ngf))
+
+
+@pytest.mark.skipif(not os.path.exists(MAT), reason="sample data not available")
+def test_hdf5_reader_and_channels_shim(monkeypatch):
+    m = hdf5_min.loadmat_v73(MAT)
+    h = m["output_h"]
+    assert h.shape == (100, 10, 16, 64) and np.iscomplexobj(h)          # loaders.py:29-33 view of the file
+    assert abs(np.std(h[:, 0].astype(np.complex64)) - 0.363263) < 1e-5   # SURVEY.md section 8, deviation 10
+    from score_based_channels_b200 import loaders
+    from score_based_channels_b200.models import make_config
+    monkeypatch.setenv("SBC_DATA_DIR", os.path.dirname(MAT))
+    monkeypatch.setattr(loaders, "_SEARCH", ("./data", os.path.dirname(MAT)))
+    cfg = make_config()
+    cfg.data.channel, cfg.data.spacing_list, cfg.data.num_pilots, cfg.data.noise_std = "CDL-C", [0.5], 38, 0.01
+    np.random.seed(0)
+    ds = loaders.Channels(4321, cfg, norm="global")
+    assert len(ds) == 100 and ds.channels.shape == (100, 16, 64) and abs(ds.std - 0.363263) < 1e-5
+    assert ds.pilots.shape == (100, 64, 38) and np.allclose(np.abs(ds.pilots), 1.0)
+    it = ds[3]
+    assert it["H_herm"].shape == (2, 64, 16) and it["P"].shape == (64, 38) and it["P"].dtype == np.complex64
+    hh = it["H_herm"][0] + 1j * it["H_herm"][1]
+    assert np.allclose(hh, np.conj(ds.channels[3].T) / ds.std, atol=1e-6)
+    assert np.allclose(it["Y"], ds.channels[3] @ ds.pilots[3], atol=0.2)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """The library loads and exports exactly the entry points include/sbc.h declares (no compute calls)."""
+    from score_based_channels_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "sbc.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(sbc_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    L.sbc_version.restype = C.c_int
+    assert L.sbc_version() == 100
+    L.sbc_model_create.restype = C.c_int
+    h = C.c_void_p()
+    assert L.sbc_model_create(None, 0, C.byref(h)) == -1        # SBC_E_ARG, never a crash
+    L.sbc_last_error.restype = C.c_char_p
+    assert b"null" in L.sbc_last_error()
+
+
+def test_program_tiling_covers_other_geometries():
+    sd = params.random_state(8, seed=3)
+    for (H, W) in ((64, 16), (32, 8), (128, 32), (24, 40)):
+        for prec in program.PRECISIONS:
+            p = program.build_program(sd, 8, H, W, precision=prec)
+            assert p.conv_flops == 51740672 * (H * W) // 1024
+            assert all(op.w_len <= p.max_w_len and op.w_off % 4 == 0 for op in p.ops)
+    with pytest.raises(ValueError, match="multiples of 8"):
+        program.build_program(sd, 8, 60, 16)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = sdist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    total, steps = 37, 5                                  # ragged: 19 + 18
+
+    def fake_kernel(lo, hi):                              # stands in for the per-rank sampler launch
+        ids = torch.arange(lo, hi, dtype=torch.float32)
+        return torch.arange(steps, dtype=torch.float32)[:, None] * 1000 + ids[None, :]
+
+    full = sdist.run_sharded(fake_kernel, total)
+    expect = torch.arange(steps, dtype=torch.float32)[:, None] * 1000 + torch.arange(total, dtype=torch.float32)[None, :]
+    ok = torch.equal(full, expect)
+    lo, hi = sdist.shard_range(total, rank, world)
+    torch.save({"ok": ok, "lo": lo, "hi": hi}, os.path.join(tmp, "r%d.pt" % rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_sharding_and_nmse_gather_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(str(tmp_path), "r%d.pt" % i)) for i in range(2)]
+    assert r[0]["ok"] and r[1]["ok"]
+    assert (r[0]["lo"], r[0]["hi"], r[1]["lo"], r[1]["hi"]) == (0, 19, 19, 37)
+    # contiguous, disjoint, complete for awkward sizes too
+    for total in (0, 1, 7, 8, 100, 1700, 20400):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sdist.shard_range(total, k, world) for k in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
