@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--levels", type=int, default=NUM_LEVELS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("SBC_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("SBC_PRECISION", "tf32x3"), choices=["tf32x3", "tf32"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -264,7 +264,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "estimates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (3xTF32 split, fp32-equivalent), f32 accumulate",
+                "dtype": {"tf32x3": "tf32x3 (3xTF32 split, fp32-equivalent), f32 accumulate",
                           "tf32": "tf32 operands, f32 accumulate"}[args.precision],
                 "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),

@@ -50,6 +50,8 @@ typedef struct sbc_model_desc {
     int32_t channels;       /* 2 (re, im) */
     const int32_t* op_table;/* host, [n_ops][24] int32 (csrc/sbc_program.h: SbcOp) */
     int32_t n_ops;
+    const int32_t* geo_table;/* host, [n_geo][8] int32 (csrc/sbc_program.h: SbcGeo), entry 0 = Nt x Nr */
+    int32_t n_geo;
     const float* blob;      /* host, packed parameters */
     int64_t blob_floats;
     int32_t arena_floats;   /* per-sample activation arena size */
@@ -66,7 +68,7 @@ typedef struct sbc_info {
     int32_t num_sms;
     int32_t threads_per_cta;
     int32_t arena_in_smem;      /* 1: activations never leave shared memory */
-    int32_t weights_staged;     /* 1: per-op parameters streamed with cp.async.bulk */
+    int32_t weights_staged;     /* 1: per-op parameters streamed into shared memory with cp.async.bulk */
     int64_t smem_bytes_per_cta;
     int64_t arena_bytes;
     int64_t conv_flops_per_forward;

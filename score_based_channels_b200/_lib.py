@@ -15,7 +15,8 @@ EXPORTS = ("sbc_version", "sbc_last_error", "sbc_model_create", "sbc_model_free"
 
 class ModelDesc(C.Structure):
     _fields_ = [("ngf", C.c_int32), ("Nt", C.c_int32), ("Nr", C.c_int32), ("channels", C.c_int32),
-                ("op_table", C.c_void_p), ("n_ops", C.c_int32), ("blob", C.c_void_p), ("blob_floats", C.c_int64),
+                ("op_table", C.c_void_p), ("n_ops", C.c_int32), ("geo_table", C.c_void_p), ("n_geo", C.c_int32),
+                ("blob", C.c_void_p), ("blob_floats", C.c_int64),
                 ("arena_floats", C.c_int32), ("in_off", C.c_int32), ("out_off", C.c_int32), ("post_off", C.c_int32),
                 ("max_w_len", C.c_int32), ("sigmas", C.c_void_p), ("n_sigmas", C.c_int32), ("conv_flops", C.c_int64)]
 

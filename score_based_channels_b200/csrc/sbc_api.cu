@@ -41,6 +41,7 @@ struct SbcModel {
     size_t smem_bytes = 0;
     long long launches = 0;
     long long* d_prof = nullptr;   // optional per-op clock stamps (sbc_set_profile_buffer)
+    SbcGeo geo[SBC_MAX_GEO];
 };
 
 extern "C" int sbc_version(void) { return SBC_VERSION; }
@@ -69,6 +70,10 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SbcModel* m = new SbcModel();
     m->device = device;
     m->d = *desc;
+    if (!desc->geo_table || desc->n_geo <= 0 || desc->n_geo > SBC_MAX_GEO) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: bad geometry table"); }
+    memset(m->geo, 0, sizeof m->geo);
+    memcpy(m->geo, desc->geo_table, sizeof(SbcGeo) * (size_t)desc->n_geo);
+    if (m->geo[0].h != desc->Nt || m->geo[0].w != desc->Nr) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: geometry 0 must be Nt x Nr"); }
     SBC_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
     SBC_CUDA(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 
@@ -83,11 +88,11 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         if (o.kind < 0 || o.kind > SBC_OP_LAST) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
         if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
             o.w_len > desc->max_w_len) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
-        if (o.kind == SBC_OP_CONV) {
-            const bool ok = (o.px == 1 || o.px == 2 || o.px == 4) && (o.cb == 1 || o.cb == 2 || o.cb == 4 || o.cb == 8) &&
-                            o.ks >= 1 && o.ks <= 32 && (o.ks & (o.ks - 1)) == 0 && o.cin % o.ks == 0 &&
-                            o.cout % o.cb == 0 && o.ow % o.px == 0 && (o.ksize == 1 || o.ksize == 3);
-            if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported conv tiling", i); }
+        if (o.sgeo < 0 || o.sgeo >= SBC_MAX_GEO || o.dgeo < 0 || o.dgeo >= SBC_MAX_GEO) {
+            delete m; return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
+        }
+        if (o.w_len > 0 && (o.wbuf < 0 || o.wbuf % 4 || o.wbuf + o.w_len > desc->arena_floats)) {
+            delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter staging buffer", i);
         }
         if (o.kind == SBC_OP_CONV_MMA) {
             const bool ok = o.ks >= 1 && o.ks <= SBC_NTHREADS / 32 && (o.ks & (o.ks - 1)) == 0 &&
@@ -102,13 +107,12 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     cudaFuncAttributes fa{};
     SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true>));
     const int dyn_max = m->smem_optin - (int)fa.sharedSizeBytes;   // opt-in limit covers static + dynamic
-    const size_t arena_bytes = (size_t)desc->arena_floats * 4, stage_bytes = 2 * (size_t)desc->max_w_len * 4;
+    const size_t arena_bytes = (size_t)desc->arena_floats * 4;
     const size_t misc = 64;
-    m->stage = env_int("SBC_STAGE_WEIGHTS", 1) != 0;
-    m->arena_in_smem = !env_int("SBC_FORCE_GLOBAL_ARENA", 0) &&
-                       arena_bytes + (m->stage ? stage_bytes : 0) + misc <= (size_t)dyn_max;
-    if (!m->arena_in_smem && stage_bytes + misc > (size_t)dyn_max) m->stage = false;
-    m->smem_bytes = (m->arena_in_smem ? arena_bytes : 0) + (m->stage ? stage_bytes : 0) + misc;
+    m->arena_in_smem = !env_int("SBC_FORCE_GLOBAL_ARENA", 0) && arena_bytes + misc <= (size_t)dyn_max;
+    // parameter staging buffers live inside the arena: staging needs the arena in shared memory
+    m->stage = m->arena_in_smem && env_int("SBC_STAGE_WEIGHTS", 1) != 0;
+    m->smem_bytes = (m->arena_in_smem ? arena_bytes : 0) + misc;
 
     SBC_CUDA(cudaMalloc(&m->d_ops, sizeof(SbcOp) * (size_t)desc->n_ops));
     SBC_CUDA(cudaMemcpy(m->d_ops, ops.data(), sizeof(SbcOp) * (size_t)desc->n_ops, cudaMemcpyHostToDevice));
@@ -117,7 +121,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SBC_CUDA(cudaMalloc(&m->d_sigmas, sizeof(float) * (size_t)desc->n_sigmas));
     SBC_CUDA(cudaMemcpy(m->d_sigmas, desc->sigmas, sizeof(float) * (size_t)desc->n_sigmas, cudaMemcpyHostToDevice));
     if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
-    m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr;   // host pointers are not retained
+    m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr; m->d.geo_table = nullptr;   // host pointers are not retained
 
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
@@ -153,6 +157,7 @@ extern "C" int sbc_query(void* handle, sbc_info* out) {
 static void fill_common(const SbcModel* m, SbcLaunch& L) {
     memset(&L, 0, sizeof L);
     L.ops = m->d_ops; L.n_ops = m->d.n_ops; L.first_w = m->first_w; L.blob = m->d_blob;
+    memcpy(L.geo, m->geo, sizeof L.geo);
     L.arena_floats = m->d.arena_floats; L.in_off = m->d.in_off; L.out_off = m->d.out_off; L.post_off = m->d.post_off;
     L.Nt = m->d.Nt; L.Nr = m->d.Nr; L.channels = m->d.channels; L.max_w_len = m->d.max_w_len;
     L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
@@ -164,10 +169,7 @@ static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
     SBC_CUDA(cudaSetDevice(m->device));
     const int grid = L.B < m->num_sms ? L.B : m->num_sms;
     size_t smem = m->smem_bytes;
-    if (L.debug_stop >= 0 && L.stage_weights) {   // debug runs read parameters straight from global memory
-        L.stage_weights = 0;
-        smem -= 2 * (size_t)m->d.max_w_len * 4;
-    }
+    if (L.debug_stop >= 0) L.stage_weights = 0;   // debug runs read parameters straight from global memory
     if (m->arena_in_smem)
         sbc_ald_kernel<true><<<grid, SBC_NTHREADS, smem, st>>>(L);
     else

@@ -1,11 +1,11 @@
-// sbc_ops.h -- per-thread bodies of every op of the fused NCSNv2Deepest forward and of the
-// annealed-Langevin update.  All functions take (tid, nthr) explicitly and contain no barriers or
-// warp intrinsics, so the same source is compiled by nvcc for the kernel (sbc_kernel.cuh) and by
-// g++ for the CPU thread-emulation harness (tests/emu/emu.cpp) that checks indexing before any GPU
-// time is spent.  Ops that need a block-wide dependency are split into phases; the caller puts a
-// barrier between phases.
+// sbc_ops.h -- per-thread bodies of the non-convolution ops of the fused NCSNv2Deepest forward and of the
+// annealed-Langevin update.  All functions take (tid, nthr) explicitly and contain no barriers or warp
+// intrinsics, so the same source is compiled by nvcc for the kernel (sbc_kernel.cuh) and by g++ for the
+// CPU thread-emulation harness (tests/emu/emu.cpp) that checks indexing before any GPU time is spent.
 //
-// Layout: every activation is planar fp32 [C][H][W] at a float offset inside one per-sample arena.
+// Layout: see SbcGeo (sbc_program.h): channel-interleaved by 4 (one float4 = 4 channels of a pixel),
+// zero halo.  Every op that writes a tensor writes the interior only and re-zeroes the halo of its
+// fresh outputs (sbc_zero_halo), because arena regions are recycled between tensors.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -22,8 +22,8 @@ struct alignas(16) SbcF4 {
     float x, y, z, w;
 };
 
-// nn.ELU(alpha=1)  (reference ncsnv2/models/layers.py:13).  Device: exp via MUFU.EX2 (absolute
-// error ~1e-7, far inside the parity tolerance); host emulation: expm1f.
+// nn.ELU(alpha=1)  (reference ncsnv2/models/layers.py:13).  Device: exp via MUFU.EX2 (absolute error
+// ~1e-7, far inside the parity tolerance); host emulation: expm1f.
 SBC_HD float sbc_elu(float v) {
 #if defined(__CUDA_ARCH__)
     return v > 0.f ? v : __expf(v) - 1.f;
@@ -31,303 +31,189 @@ SBC_HD float sbc_elu(float v) {
     return v > 0.f ? v : expm1f(v);
 #endif
 }
+SBC_HD SbcF4 sbc_elu4(SbcF4 v) { return SbcF4{sbc_elu(v.x), sbc_elu(v.y), sbc_elu(v.z), sbc_elu(v.w)}; }
 
-// ----------------------------------------------------------------------------------------------
-// Convolution (reference layers.py:28-60; ConvMeanPool layers.py:309-313)
-//   item  = (cout block cbi, output row Y, strip of PX output pixels starting at X0)
-//   kpart = which 1/ks slice of the input channels this thread accumulates
-// Packed weights: [cout/CB][cin][k*k][CB] (program.py:conv), bias (if any) at wseg + b_rel.
-// ----------------------------------------------------------------------------------------------
-template <int PX, int CB>
-SBC_HD void sbc_conv_partial(const SbcOp& op, const float* arena, const float* wseg, int item, int kpart,
-                             float (&acc)[PX * CB]) {
-    const int h = op.h, w = op.w, oh = op.oh, ow = op.ow, cin = op.cin, K = op.ksize, dil = op.dil;
-    const int spr = ow / PX;          // strips per output row
-    const int nsp = oh * spr;         // spatial items
-    const int cbi = item / nsp;
-    const int sp = item - cbi * nsp;
-    const int Y = sp / spr;
-    const int X0 = (sp - Y * spr) * PX;
-    const int cper = cin / op.ks;
-    const int c0 = kpart * cper, c1 = c0 + cper;
-    const int KK = K * K;
-    const float* src = arena + op.src;
-    const int ps = SBC_PS(h, w);
-    const bool pool = (op.flags & SBC_F_POOL) != 0;
-#pragma unroll
-    for (int i = 0; i < PX * CB; i++) acc[i] = 0.f;
+SBC_HD SbcF4* sbc_px(float* base, const SbcGeo& G, int cg, int y, int x) {
+    return reinterpret_cast<SbcF4*>(base) + (cg * G.pps + G.org + y * G.wp + x);
+}
+SBC_HD const SbcF4* sbc_px(const float* base, const SbcGeo& G, int cg, int y, int x) {
+    return reinterpret_cast<const SbcF4*>(base) + (cg * G.pps + G.org + y * G.wp + x);
+}
 
-    if (K == 3 && dil == 1 && !pool) {
-        // hot path: contiguous (PX+2)-wide window per tap row
-        for (int ci = c0; ci < c1; ci++) {
-            const float* pl = src + ci * ps;
-            const float* wp = wseg + (size_t)((cbi * cin + ci) * 9) * CB;
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-                const int yy = Y + ky - 1;
-                if (yy < 0 || yy >= h) continue;
-                const float* row = pl + yy * w + X0;
-                float v[PX + 2];
-                v[0] = (X0 > 0) ? row[-1] : 0.f;
-                if (PX == 4) {
-                    const SbcF4 q = *reinterpret_cast<const SbcF4*>(row);
-                    v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < PX; j++) v[j + 1] = row[j];
-                }
-                v[PX + 1] = (X0 + PX < w) ? row[PX] : 0.f;
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    float wv[CB];
-                    const float* wt = wp + (ky * 3 + kx) * CB;
-                    if (CB % 4 == 0) {
-#pragma unroll
-                        for (int c4 = 0; c4 < CB / 4; c4++) {
-                            const SbcF4 q = *reinterpret_cast<const SbcF4*>(wt + 4 * c4);
-                            wv[4 * c4] = q.x; wv[4 * c4 + 1] = q.y; wv[4 * c4 + 2] = q.z; wv[4 * c4 + 3] = q.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CB; c++) wv[c] = wt[c];
-                    }
-#pragma unroll
-                    for (int p = 0; p < PX; p++)
-#pragma unroll
-                        for (int c = 0; c < CB; c++) acc[p * CB + c] = fmaf(v[p + kx], wv[c], acc[p * CB + c]);
-                }
-            }
+// zero the halo cells of a tensor with `c` channels (cg = ceil(c/4) channel groups)
+SBC_HD void sbc_zero_halo(float* t, const SbcGeo& G, int c, int tid, int nthr) {
+    const int ncg = (c + 3) >> 2;
+    const int rows = G.h + 2 * G.hy;
+    const int top = G.hy * G.wp;                  // cells in the top (and bottom) band
+    const int side = 2 * G.hx;                    // halo cells per interior row
+    const int per = 2 * top + G.h * side;
+    const SbcF4 z{0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < ncg * per; i += nthr) {
+        const int cg = i / per;
+        int r = i - cg * per;
+        int cell;
+        if (r < top) cell = r;
+        else if (r < 2 * top) cell = (rows - G.hy) * G.wp + (r - top);
+        else {
+            r -= 2 * top;
+            const int row = r / side, k = r - row * side;
+            cell = (G.hy + row) * G.wp + (k < G.hx ? k : G.w + k);
         }
-        return;
-    }
-
-    // generic path: 1x1, dilated, or pooled (conv over the 2x2 box-summed input at stride 2; weights
-    // already carry the 1/4)
-    const int r = K / 2;
-    for (int ci = c0; ci < c1; ci++) {
-        const float* pl = src + ci * ps;
-        const float* wp = wseg + (size_t)((cbi * cin + ci) * KK) * CB;
-        for (int ky = 0; ky < K; ky++) {
-            const int oy = (ky - r) * dil;
-            for (int kx = 0; kx < K; kx++) {
-                const int ox = (kx - r) * dil;
-                float v[PX];
-                bool any = false;
-                if (!pool) {
-                    const int yy = Y + oy;
-                    if (yy < 0 || yy >= h) continue;
-#pragma unroll
-                    for (int p = 0; p < PX; p++) {
-                        const int xx = X0 + p + ox;
-                        const bool in = (xx >= 0 && xx < w);
-                        v[p] = in ? pl[yy * w + xx] : 0.f;
-                        any |= in;
-                    }
-                } else {
-#pragma unroll
-                    for (int p = 0; p < PX; p++) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int dy = 0; dy < 2; dy++) {
-                            const int yy = 2 * Y + dy + oy;
-                            if (yy < 0 || yy >= h) continue;
-#pragma unroll
-                            for (int dx = 0; dx < 2; dx++) {
-                                const int xx = 2 * (X0 + p) + dx + ox;
-                                if (xx >= 0 && xx < w) { s += pl[yy * w + xx]; any = true; }
-                            }
-                        }
-                        v[p] = s;
-                    }
-                }
-                if (!any) continue;
-                const float* wt = wp + (ky * K + kx) * CB;
-#pragma unroll
-                for (int c = 0; c < CB; c++) {
-                    const float wc = wt[c];
-#pragma unroll
-                    for (int p = 0; p < PX; p++) acc[p * CB + c] = fmaf(v[p], wc, acc[p * CB + c]);
-                }
-            }
-        }
+        reinterpret_cast<SbcF4*>(t)[cg * G.pps + cell] = z;
     }
 }
 
-// Epilogue of one item (after the K-split partials have been summed):
-//   v = acc + bias;  dst <- v;  accbuf <- (v += accbuf);  edst <- ELU(v)
-template <int PX, int CB>
-SBC_HD void sbc_conv_epilogue(const SbcOp& op, float* arena, const float* wseg, int item,
-                              const float (&acc)[PX * CB]) {
-    const int oh = op.oh, ow = op.ow;
-    const int spr = ow / PX, nsp = oh * spr;
-    const int cbi = item / nsp;
-    const int sp = item - cbi * nsp;
-    const int Y = sp / spr;
-    const int X0 = (sp - Y * spr) * PX;
-    const int plane = SBC_PS(oh, ow);
-#pragma unroll
-    for (int c = 0; c < CB; c++) {
-        const int co = cbi * CB + c;
-        const float b = (op.b_rel >= 0) ? wseg[op.b_rel + co] : 0.f;
-        const int base = co * plane + Y * ow + X0;
-        float v[PX];
-#pragma unroll
-        for (int p = 0; p < PX; p++) v[p] = acc[p * CB + c] + b;
-        if (op.dst >= 0) {
-#pragma unroll
-            for (int p = 0; p < PX; p++) arena[op.dst + base + p] = v[p];
-        }
-        if (op.acc >= 0) {
-#pragma unroll
-            for (int p = 0; p < PX; p++) {
-                v[p] += arena[op.acc + base + p];
-                arena[op.acc + base + p] = v[p];
-            }
-        }
-        if (op.edst >= 0) {
-#pragma unroll
-            for (int p = 0; p < PX; p++) arena[op.edst + base + p] = sbc_elu(v[p]);
-        }
+// ----------------------------------------------------------------------------------------------
+// InstanceNorm2dPlus + ELU (reference normalization.py:163-176).  One float4 lane-item covers the 4
+// channels of a channel group; thread (cg, s) owns pixels s, s+T, s+2T, ... of channel group cg
+// (T = nthr / ncg threads per group).  Statistics are two-pass; the per-thread partials below are
+// combined across the T threads by shuffles + a shared-memory exchange on the device and by a plain
+// loop in the emulation.
+// ----------------------------------------------------------------------------------------------
+SBC_HD int sbc_norm_T(const SbcOp& op, int nthr) {
+    const int ncg = (op.cin + 3) >> 2;
+    int T = nthr / ncg;
+    int p = 32;                       // a power of two >= 32 so that warps never straddle channel groups
+    while (p * 2 <= T) p *= 2;
+    return p;
+}
+SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float* arena, int cg, int s, int T) {
+    SbcF4 a{0.f, 0.f, 0.f, 0.f};
+    const int HW = G.h * G.w;
+#pragma unroll 4
+    for (int i = s; i < HW; i += T) {
+        const int y = i / G.w, x = i - y * G.w;
+        const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
+    return a;
 }
-
-SBC_HD int sbc_conv_items(const SbcOp& op) { return op.oh * (op.ow / op.px) * (op.cout / op.cb); }
-
-// ----------------------------------------------------------------------------------------------
-// InstanceNorm2dPlus + ELU (reference normalization.py:163-176).
-//   S = power of two <= 32 lanes cooperate on one channel; lane (c, s) owns elements s, s+S, ... of
-//   channel c.  Statistics are two-pass (mean, then centred second moment); the S partial sums are
-//   combined with warp shuffles on the device (sbc_kernel.cuh) and by a plain loop in the CPU
-//   emulation.  scratch: chan[2*C] = (mean, rstd) per channel.
-// ----------------------------------------------------------------------------------------------
-SBC_HD int sbc_norm_S(const SbcOp& op, int nthr) {
-    int S = 32;
-    while (S > 1 && op.cin * S > nthr) S >>= 1;
-    return S;
+SBC_HD SbcF4 sbc_norm_partial_m2(const SbcOp& op, const SbcGeo& G, const float* arena, int cg, int s, int T,
+                                 SbcF4 mean) {
+    SbcF4 a{0.f, 0.f, 0.f, 0.f};
+    const int HW = G.h * G.w;
+#pragma unroll 4
+    for (int i = s; i < HW; i += T) {
+        const int y = i / G.w, x = i - y * G.w;
+        const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
+        const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+        a.x = fmaf(dx, dx, a.x); a.y = fmaf(dy, dy, a.y); a.z = fmaf(dz, dz, a.z); a.w = fmaf(dw, dw, a.w);
+    }
+    return a;
 }
-SBC_HD float sbc_norm_partial_sum(const SbcOp& op, const float* arena, int c, int s, int S) {
-    const int HW = op.h * op.w;
-    const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
-    float sum = 0.f;
-#pragma unroll 8
-    for (int i = s; i < HW; i += S) sum += x[i];
-    return sum;
-}
-SBC_HD float sbc_norm_partial_m2(const SbcOp& op, const float* arena, int c, int s, int S, float mean) {
-    const int HW = op.h * op.w;
-    const float* x = arena + op.src + c * SBC_PS(op.h, op.w);
-    float m2 = 0.f;
-#pragma unroll 8
-    for (int i = s; i < HW; i += S) { const float d = x[i] - mean; m2 = fmaf(d, d, m2); }
-    return m2;
-}
-SBC_HD void sbc_norm_store_stats(const SbcOp& op, float* arena, int c, float mean, float m2) {
-    float* chan = arena + op.scratch;
-    chan[c] = mean;
-    chan[op.cin + c] = 1.f / sqrtf(m2 / (float)(op.h * op.w) + 1e-5f);   // nn.InstanceNorm2d: biased variance
-}
-SBC_HD void sbc_norm_apply(const SbcOp& op, float* arena, const float* wseg, int tid, int nthr) {
-    const int C = op.cin, HW = op.h * op.w, S = sbc_norm_S(op, nthr), ps = SBC_PS(op.h, op.w);
-    const float* chan = arena + op.scratch;
+// `mu` [C] per-channel means (any addressable memory), mean4 / m2_4: this thread's channel-group statistics
+SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg, const float* mu, int cg,
+                           int s, int T, SbcF4 mean4, SbcF4 m2_4) {
+    const int C = op.cin, HW = G.h * G.w;
     // cross-channel statistics of the per-channel means: torch.mean / torch.var (unbiased) over C
     float m = 0.f;
-    for (int c = 0; c < C; c++) m += chan[c];
+    for (int c = 0; c < C; c++) m += mu[c];
     m /= (float)C;
     float v = 0.f;
-    for (int c = 0; c < C; c++) { const float d = chan[c] - m; v = fmaf(d, d, v); }
+    for (int c = 0; c < C; c++) { const float d = mu[c] - m; v = fmaf(d, d, v); }
     v /= (float)(C - 1);
     const float rv = 1.f / sqrtf(v + 1e-5f);
-    const float *alpha = wseg, *gamma = wseg + C, *beta = wseg + 2 * C;
-    for (int t = tid; t < C * S; t += nthr) {
-        const int c = t / S, s = t - c * S;
-        const float mu = chan[c];
-        const float a = gamma[c] * chan[C + c];
-        const float b = fmaf(gamma[c], (mu - m) * rv * alpha[c], beta[c]);
-        const float* x = arena + op.src + c * ps;
-        float* o = arena + op.dst + c * ps;
-#pragma unroll 8
-        for (int i = s; i < HW; i += S) o[i] = sbc_elu(fmaf(x[i] - mu, a, b));
+    const float *alpha = wseg + 4 * cg, *gamma = wseg + C + 4 * cg, *beta = wseg + 2 * C + 4 * cg;
+    const float inv = 1.f / (float)HW;
+    const float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w};
+    const float m2[4] = {m2_4.x, m2_4.y, m2_4.z, m2_4.w};
+    float a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool real = 4 * cg + j < C;
+        const float rstd = 1.f / sqrtf(m2[j] * inv + 1e-5f);       // nn.InstanceNorm2d: biased variance
+        a[j] = real ? gamma[j] * rstd : 0.f;
+        b[j] = real ? fmaf(gamma[j], (mean[j] - m) * rv * alpha[j], beta[j]) : 0.f;
+    }
+#pragma unroll 4
+    for (int i = s; i < HW; i += T) {
+        const int y = i / G.w, x = i - y * G.w;
+        const SbcF4 q = *sbc_px(arena + op.src, G, cg, y, x);
+        SbcF4 o;
+        o.x = sbc_elu(fmaf(q.x - mean[0], a[0], b[0]));
+        o.y = sbc_elu(fmaf(q.y - mean[1], a[1], b[1]));
+        o.z = sbc_elu(fmaf(q.z - mean[2], a[2], b[2]));
+        o.w = sbc_elu(fmaf(q.w - mean[3], a[3], b[3]));
+        *sbc_px(arena + op.dst, G, cg, y, x) = o;
     }
 }
 
 // ----------------------------------------------------------------------------------------------
-// element-wise ops
+// element-wise ops (one float4 = 4 channels of one pixel per item)
 // ----------------------------------------------------------------------------------------------
-SBC_HD void sbc_elu_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int HW = op.h * op.w, n = op.cin * HW, ps = SBC_PS(op.h, op.w);
+SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
+    const int HW = G.h * G.w, n = ((op.cin + 3) >> 2) * HW;
 #pragma unroll 4
     for (int i = tid; i < n; i += nthr) {
-        const int c = i / HW, j = c * ps + (i - c * HW);
-        arena[op.dst + j] = sbc_elu(arena[op.src + j]);
+        const int cg = i / HW, r = i - cg * HW, y = r / G.w, x = r - y * G.w;
+        *sbc_px(arena + op.dst, G, cg, y, x) = sbc_elu4(*sbc_px(arena + op.src, G, cg, y, x));
     }
+    sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
-SBC_HD void sbc_affine_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int HW = op.h * op.w, n = op.cin * HW, ps = SBC_PS(op.h, op.w);
+// dst = 2*src - 1 on channels < cin; channels cin .. cout-1 of dst are zero (ncsnv2.py:270-271)
+SBC_HD void sbc_affine_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
+    const int HW = G.h * G.w, n = ((op.cout + 3) >> 2) * HW;
     for (int i = tid; i < n; i += nthr) {
-        const int c = i / HW, j = c * ps + (i - c * HW);
-        arena[op.dst + j] = 2.f * arena[op.src + j] - 1.f;
+        const int cg = i / HW, r = i - cg * HW, y = r / G.w, x = r - y * G.w;
+        SbcF4 o{0.f, 0.f, 0.f, 0.f};
+        if (4 * cg < op.cin) {
+            const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
+            const int c = 4 * cg;
+            o.x = (c < op.cin) ? 2.f * v.x - 1.f : 0.f;
+            o.y = (c + 1 < op.cin) ? 2.f * v.y - 1.f : 0.f;
+            o.z = (c + 2 < op.cin) ? 2.f * v.z - 1.f : 0.f;
+            o.w = (c + 3 < op.cin) ? 2.f * v.w - 1.f : 0.f;
+        }
+        *sbc_px(arena + op.dst, G, cg, y, x) = o;
     }
+    sbc_zero_halo(arena + op.dst, G, op.cout, tid, nthr);
 }
 
-// MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70): strip of up to 4 pixels/thread
-SBC_HD void sbc_maxpool5_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int C = op.cin, H = op.h, W = op.w;
-    const int PX = (W % 4 == 0) ? 4 : ((W % 2 == 0) ? 2 : 1);
-    const int spr = W / PX;
-    const int n = C * H * spr;
-    for (int it = tid; it < n; it += nthr) {
-        const int c = it / (H * spr);
-        const int rem = it - c * (H * spr);
-        const int y = rem / spr, x0 = (rem - y * spr) * PX;
-        const float* pl = arena + op.src + c * SBC_PS(H, W);
-        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int dy = -2; dy <= 2; dy++) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;
-            const float* row = pl + yy * W;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int xx = x0 - 2 + j;
-                v[j] = (j < PX + 4 && xx >= 0 && xx < W) ? row[xx] : -INFINITY;
-            }
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                if (p < PX) {
-                    const float mrow = fmaxf(fmaxf(fmaxf(v[p], v[p + 1]), fmaxf(v[p + 2], v[p + 3])), v[p + 4]);
-                    best[p] = fmaxf(best[p], mrow);
-                }
+// MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70); 4 channels per item
+SBC_HD void sbc_maxpool5_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
+    const int H = G.h, W = G.w, HW = H * W, n = ((op.cin + 3) >> 2) * HW;
+    for (int i = tid; i < n; i += nthr) {
+        const int cg = i / HW, r = i - cg * HW, y = r / W, x = r - y * W;
+        SbcF4 m{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const int y0 = y - 2 < 0 ? 0 : y - 2, y1 = y + 2 >= H ? H - 1 : y + 2;
+        const int x0 = x - 2 < 0 ? 0 : x - 2, x1 = x + 2 >= W ? W - 1 : x + 2;
+        for (int yy = y0; yy <= y1; yy++) {
+            const SbcF4* row = sbc_px(arena + op.src, G, cg, yy, 0);
+            for (int xx = x0; xx <= x1; xx++) {
+                const SbcF4 v = row[xx];
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
-        float* o = arena + op.dst + c * SBC_PS(H, W) + y * W + x0;
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-            if (p < PX) o[p] = best[p];
+        *sbc_px(arena + op.dst, G, cg, y, x) = m;
     }
+    sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
 
 // acc += bilinear(src, size=(oh,ow), align_corners=True); optional edst = ELU(acc)  (layers.py:182-183)
-SBC_HD void sbc_upacc_op(const SbcOp& op, float* arena, int tid, int nthr) {
-    const int C = op.cin, H = op.h, W = op.w, OH = op.oh, OW = op.ow;
+SBC_HD void sbc_upacc_op(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena, int tid, int nthr) {
+    const int H = GS.h, W = GS.w, OH = GD.h, OW = GD.w;
     const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-    const int n = C * OH * OW;
+    const int n = ((op.cin + 3) >> 2) * OH * OW;
     for (int i = tid; i < n; i += nthr) {
-        const int c = i / (OH * OW);
-        const int rem = i - c * (OH * OW);
+        const int cg = i / (OH * OW), rem = i - cg * (OH * OW);
         const int y = rem / OW, x = rem - y * OW;
         const float fy = sy * (float)y, fx = sx * (float)x;
         const int y0 = (int)fy, x0 = (int)fx;
         const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
         const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        const float* p = arena + op.src + c * SBC_PS(H, W);
-        const float val = hy * (hx * p[y0 * W + x0] + lx * p[y0 * W + x1]) +
-                          ly * (hx * p[y1 * W + x0] + lx * p[y1 * W + x1]);
-        const int j = c * SBC_PS(OH, OW) + rem;
-        const float v = arena[op.acc + j] + val;
-        arena[op.acc + j] = v;
-        if (op.edst >= 0) arena[op.edst + j] = sbc_elu(v);
+        const SbcF4 p00 = *sbc_px(arena + op.src, GS, cg, y0, x0), p01 = *sbc_px(arena + op.src, GS, cg, y0, x1);
+        const SbcF4 p10 = *sbc_px(arena + op.src, GS, cg, y1, x0), p11 = *sbc_px(arena + op.src, GS, cg, y1, x1);
+        SbcF4* a = sbc_px(arena + op.acc, GD, cg, y, x);
+        SbcF4 v = *a;
+        v.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+        v.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+        v.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+        v.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+        *a = v;
+        if (op.edst >= 0) *sbc_px(arena + op.edst, GD, cg, y, x) = sbc_elu4(v);
     }
+    if (op.edst >= 0) sbc_zero_halo(arena + op.edst, GD, op.cin, tid, nthr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -359,8 +245,9 @@ SBC_HD void sbc_noise_cn01(uint64_t seed, uint64_t sid, uint32_t step, int e, fl
 
 // ----------------------------------------------------------------------------------------------
 // Annealed-Langevin step around the network (reference test_score.py:157-170).
-// x lives planar in the arena at in_off: xr[t*Nr+r], xi = xr + SBC_PS(Nt,Nr).  P [Np][Nt], Y [Np][Nr],
-// Hor [Nt][Nr] are interleaved complex64 in global memory.
+// x lives in the arena at in_off as a 2-channel tensor of geometry G (channel 0 = re, 1 = im of
+// x[t][r], pixel (y=t, x=r)).  P [Np][Nt], Y [Np][Nr], Hor [Nt][Nr] are interleaved complex64 in global
+// memory.
 // ----------------------------------------------------------------------------------------------
 struct SbcStepScalars {
     float sigma;      // sigmas[level]
@@ -369,36 +256,33 @@ struct SbcStepScalars {
     float nscale;     // sqrt(2 * alpha * beta)                    (test_score.py:160)
 };
 
-// phase 1: res = P @ x - y   (test_score.py:157-158, inner product), planar into arena[post ..]
-SBC_HD void sbc_dc_residual(const float* arena_x, float* res, const float* P, const float* Y, int Nt, int Nr, int Np,
-                            int tid, int nthr) {
-    const float* xr = arena_x;
-    const float* xi = arena_x + SBC_PS(Nt, Nr);
+// phase 1: res = P @ x - y   (test_score.py:157-158, inner product), planar [2][Np*Nr] into `res`
+SBC_HD void sbc_dc_residual(const float* ax, const SbcGeo& G, float* res, const float* P, const float* Y, int Nt,
+                            int Nr, int Np, int tid, int nthr) {
     for (int o = tid; o < Np * Nr; o += nthr) {
         const int p = o / Nr, r = o - p * Nr;
         float sr = 0.f, si = 0.f;
+#pragma unroll 4
         for (int t = 0; t < Nt; t++) {
             const float pr = P[2 * (p * Nt + t)], pi = P[2 * (p * Nt + t) + 1];
-            const float cr = xr[t * Nr + r], ci = xi[t * Nr + r];
-            sr += pr * cr - pi * ci;
-            si += pr * ci + pi * cr;
+            const SbcF4 c = *sbc_px(ax, G, 0, t, r);
+            sr += pr * c.x - pi * c.y;
+            si += pr * c.y + pi * c.x;
         }
         res[o] = sr - Y[2 * o];
         res[Np * Nr + o] = si - Y[2 * o + 1];
     }
 }
 // phase 2: g = P^H res;  x += alpha*(net/sigma - g/den) + nscale*eps;  per-thread |x-H|^2 partial
-SBC_HD float sbc_langevin_update(float* arena_x, const float* net_out, const float* res, const float* P,
+SBC_HD float sbc_langevin_update(float* ax, const float* net, const SbcGeo& G, const float* res, const float* P,
                                  const float* Hor, const float* ext_noise, const SbcStepScalars& sc, uint64_t seed,
                                  uint64_t sid, uint32_t gstep, int Nt, int Nr, int Np, int tid, int nthr) {
-    float* xr = arena_x;
-    float* xi = arena_x + SBC_PS(Nt, Nr);
     const int ne = Nt * Nr;
-    const float* net_im = net_out + SBC_PS(Nt, Nr);
     float part = 0.f;
     for (int e = tid; e < ne; e += nthr) {
         const int t = e / Nr, r = e - t * Nr;
         float gr = 0.f, gi = 0.f;
+#pragma unroll 2
         for (int p = 0; p < Np; p++) {   // conj(P[p,t]) * res[p,r]
             const float pr = P[2 * (p * Nt + t)], pi = -P[2 * (p * Nt + t) + 1];
             const float cr = res[p * Nr + r], ci = res[Np * Nr + p * Nr + r];
@@ -408,12 +292,15 @@ SBC_HD float sbc_langevin_update(float* arena_x, const float* net_out, const flo
         float nr_, ni_;
         if (ext_noise) { nr_ = ext_noise[2 * e]; ni_ = ext_noise[2 * e + 1]; }
         else sbc_noise_cn01(seed, sid, gstep, e, nr_, ni_);
-        const float sr = net_out[e] / sc.sigma, si = net_im[e] / sc.sigma;   // ncsnv2.py:295-298
-        const float vr = xr[e] + sc.alpha * (sr - gr / sc.den) + sc.nscale * nr_;
-        const float vi = xi[e] + sc.alpha * (si - gi / sc.den) + sc.nscale * ni_;
-        xr[e] = vr; xi[e] = vi;
+        SbcF4* xp = sbc_px(ax, G, 0, t, r);
+        const SbcF4 nv = *sbc_px(net, G, 0, t, r);
+        SbcF4 xv = *xp;
+        const float sr = nv.x / sc.sigma, si = nv.y / sc.sigma;   // ncsnv2.py:295-298
+        xv.x = xv.x + sc.alpha * (sr - gr / sc.den) + sc.nscale * nr_;
+        xv.y = xv.y + sc.alpha * (si - gi / sc.den) + sc.nscale * ni_;
+        *xp = xv;
         if (Hor) {
-            const float dr = vr - Hor[2 * e], di = vi - Hor[2 * e + 1];
+            const float dr = xv.x - Hor[2 * e], di = xv.y - Hor[2 * e + 1];
             part += dr * dr + di * di;
         }
     }

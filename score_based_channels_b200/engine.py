@@ -19,8 +19,10 @@ class PackedModel:
         self.sigmas = np.ascontiguousarray(state["sigmas"], dtype=np.float32)
         self.ngf, self.Nt, self.Nr, self.channels, self.device = ngf, Nt, Nr, channels, device
         self._tab = np.ascontiguousarray(self.prog.op_table())
+        self._geo = np.ascontiguousarray(self.prog.geo_table())
         p = self.prog
-        d = _lib.ModelDesc(ngf, Nt, Nr, channels, self._tab.ctypes.data, self._tab.shape[0], p.blob.ctypes.data,
+        d = _lib.ModelDesc(ngf, Nt, Nr, channels, self._tab.ctypes.data, self._tab.shape[0], self._geo.ctypes.data,
+                           len(p.geos), p.blob.ctypes.data,
                            p.blob.size, p.arena_floats, p.in_off, p.out_off, p.post_off, p.max_w_len,
                            self.sigmas.ctypes.data, self.sigmas.size, p.conv_flops)
         h = C.c_void_p()

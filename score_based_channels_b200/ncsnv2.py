@@ -40,8 +40,7 @@ class NCSNv2Deepest(nn.Module):
 
     * ``"tf32x3"`` (default): tensor cores, 3xTF32 error-compensated products -- fp32-equivalent
       results (the reference disables TF32, ``test_score.py:24-26``);
-    * ``"tf32"``: tensor cores, plain TF32 operands, fp32 accumulate (fastest);
-    * ``"fp32"``: FFMA on CUDA cores.
+    * ``"tf32"``: tensor cores, plain TF32 operands (round to nearest), fp32 accumulate (fastest).
     The environment variable ``SBC_PRECISION`` overrides the default."""
 
     def __init__(self, config, precision: Optional[str] = None):

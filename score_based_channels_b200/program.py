@@ -1,77 +1,97 @@
 """Host-side "layer program" for the fused NCSNv2Deepest forward.
 
-The CUDA kernel (``csrc/sbc_kernel.cuh``) keeps every activation of one sample
-in a single on-chip arena and walks a flat list of ops.  This module builds that
-list, plans the arena (which tensor lives at which float offset, with liveness
-based reuse) and packs the checkpoint tensors into the parameter blob the
-kernel streams per op.
+The CUDA kernel (``csrc/sbc_kernel.cuh``) keeps every activation of one sample in a single on-chip
+arena and walks a flat list of ops.  This module builds that list, plans the arena (which tensor lives
+at which float offset, with liveness based reuse) and packs the checkpoint tensors into the parameter
+blob the kernel streams per op.
 
-The schedule restates ``NCSNv2Deepest.forward`` (reference
-``ncsnv2/models/ncsnv2.py:269-300``) with its building blocks
-``ResidualBlock`` (``ncsnv2/models/layers.py:443-456``), ``ConvMeanPool``
-(``layers.py:309-313``), ``RefineBlock`` (``layers.py:234-249``), ``RCUBlock``
-(``layers.py:126-134``), ``CRPBlock`` (``layers.py:76-83``), ``MSFBlock``
-(``layers.py:178-184``) and ``InstanceNorm2dPlus``
-(``ncsnv2/models/normalization.py:163-176``).  Fusions applied (all exact
-re-associations of the reference arithmetic):
+The schedule restates ``NCSNv2Deepest.forward`` (reference ``ncsnv2/models/ncsnv2.py:269-300``) with
+its building blocks ``ResidualBlock`` (``ncsnv2/models/layers.py:443-456``), ``ConvMeanPool``
+(``layers.py:309-313``), ``RefineBlock`` (``layers.py:234-249``), ``RCUBlock`` (``layers.py:126-134``),
+``CRPBlock`` (``layers.py:76-83``), ``MSFBlock`` (``layers.py:178-184``) and ``InstanceNorm2dPlus``
+(``ncsnv2/models/normalization.py:163-176``).  Fusions applied (all exact re-associations of the
+reference arithmetic):
 
-* ``ELU`` is folded into the epilogue of whichever op produces its input
-  (``edst``), so no stand-alone activation pass remains except after skips;
+* ``ELU`` is folded into the epilogue of whichever op produces its input (``edst``);
 * residual / multi-scale sums are epilogue accumulations (``acc``);
-* ``ConvMeanPool`` = conv then 2x2 mean-pool is evaluated as a conv over the
-  2x2 box-summed input sampled at stride 2, times 1/4 (same linear map, 4x
-  fewer MACs) -- ``F_POOL``.
+* ``ConvMeanPool`` = conv then 2x2 mean-pool: four accumulations (one per pooling position) summed in the
+  epilogue, weights pre-scaled by 1/4 -- ``F_POOL``.
 
-Nothing here touches a GPU; ``simulate`` is a torch (CPU) interpreter of the
-program used by the CPU test-suite to pin the schedule against the reference
-module before any CUDA code runs.
+Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by 4 with a zero halo,
+``addr(c, y, x) = base + ((c // 4) * pps + org + y * wp + x) * 4 + c % 4`` with ``wp = w + 2*hx``,
+``pps = (h + 2*hy) * wp``, ``org = hy * wp + hx``.  The halo (hy, hx) covers every live convolution tap
+at that resolution, so the implicit-im2col gather of a tap is the *same* address pattern shifted by a
+constant and needs no bounds checks; 8 consecutive pixels x 4 channels are 128 contiguous bytes -- one
+conflict-free shared-memory wavefront for an mma.sync A fragment, and exactly one no-swizzle K-major
+core matrix of a tcgen05 kind::tf32 operand.
+
+Nothing here touches a GPU; ``simulate`` is a torch (CPU) interpreter of the program used by the CPU
+test-suite to pin the schedule against the reference module before any CUDA code runs.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
 # ---- op kinds (mirrored in csrc/sbc_program.h) ---------------------------
 OP_AFFINE = 0     # dst = 2*src - 1                       (ncsnv2.py:270-271)
-OP_CONV = 1       # k in {1,3} conv, stride 1, pad = dil*(k//2)
 OP_NORM_ELU = 2   # dst = ELU(InstanceNorm++(src))
 OP_ELU = 3        # dst = ELU(src)
 OP_MAXPOOL5 = 4   # dst = maxpool 5x5 stride 1 pad 2
 OP_UPACC = 5      # acc += bilinear(src -> (oh,ow), align_corners=True)
-OP_CONV_MMA = 6   # same contract as OP_CONV, contraction on tensor cores (mma.sync m16n8k8 TF32)
-N_OP_KINDS = 7
-
-PLANE_PAD = 8     # every activation plane is stored with stride h*w + 8 floats: with the stride
-                  # = 8 (mod 16) the (channel t, pixel g) gather of an MMA A-fragment hits 32 banks
-
-
-def PS(h: int, w: int) -> int:
-    return h * w + PLANE_PAD
-
-
-PRECISIONS = ("fp32", "tf32x3", "tf32")
+OP_CONV_MMA = 6   # Conv2d k in {1,3} (+ fused epilogue) on tensor cores (mma.sync m16n8k8 TF32)
 
 # ---- flags ----------------------------------------------------------------
 F_POOL = 1        # conv followed by 2x2 mean-pool (ConvMeanPool)
-F_X3 = 2          # OP_CONV_MMA: 3xTF32 error-compensated product (fp32-equivalent accuracy)
+F_X3 = 2          # 3xTF32 error-compensated product (fp32-equivalent accuracy)
 
-OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout",
-             "h", "w", "ksize", "dil", "w_off", "w_len", "b_rel", "px",
-             "cb", "ks", "scratch", "oh", "ow", "pad0", "tapmask", "pad2")
+PRECISIONS = ("tf32x3", "tf32")
+
+OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout", "h", "w", "ksize", "dil",
+             "w_off", "w_len", "b_rel", "sgeo", "dgeo", "ks", "scratch", "oh", "ow", "pad0", "tapmask",
+             "wbuf")
 OP_WORDS = len(OP_FIELDS)            # 24 int32 = 96 bytes per op
 assert OP_WORDS == 24
+MAX_GEO = 8
+GEO_WORDS = 8                        # h, w, hy, hx, wp, pps, org, pad
+
+
+@dataclass(frozen=True)
+class Geo:
+    h: int
+    w: int
+    hy: int
+    hx: int
+
+    @property
+    def wp(self) -> int:
+        return self.w + 2 * self.hx
+
+    @property
+    def pps(self) -> int:
+        return (self.h + 2 * self.hy) * self.wp
+
+    @property
+    def org(self) -> int:
+        return self.hy * self.wp + self.hx
+
+    def floats(self, c: int) -> int:
+        return ((c + 3) // 4) * self.pps * 4
+
+    def words(self) -> List[int]:
+        return [self.h, self.w, self.hy, self.hx, self.wp, self.pps, self.org, 0]
 
 
 @dataclass
 class Op:
     kind: int
     flags: int = 0
-    src: int = -1       # float offset into the arena
-    dst: int = -1       # raw result store           (-1: none)
-    acc: int = -1       # v += acc[i]; acc[i] = v    (-1: none)
-    edst: int = -1      # edst[i] = ELU(v)           (-1: none)
+    src: object = -1    # float offset into the arena (tensor name until the plan is solved)
+    dst: object = -1    # raw result store           (-1: none)
+    acc: object = -1    # v += acc[i]; acc[i] = v    (-1: none)
+    edst: object = -1   # edst[i] = ELU(v)           (-1: none)
     cin: int = 0
     cout: int = 0
     h: int = 0          # INPUT spatial size
@@ -81,27 +101,30 @@ class Op:
     w_off: int = 0      # float offset of this op's parameter segment in the blob
     w_len: int = 0      # floats (multiple of 4) streamed for this op
     b_rel: int = -1     # bias offset inside the segment (-1: no bias)
-    px: int = 1         # conv tiling: output pixels per thread along W
-    cb: int = 1         # conv tiling: output channels per thread
-    ks: int = 1         # conv tiling: split of the Cin loop across threads
-    scratch: int = -1   # arena offset of the per-op scratch (K-split partials / norm stats)
+    sgeo: int = 0       # geometry index of the input tensor
+    dgeo: int = 0       # geometry index of the output tensors (dst / acc / edst)
+    ks: int = 1         # conv: number of warps that split the K steps of one (tile, cout-tile) unit
+    scratch: object = -1  # arena offset of the per-op scratch (K-split partials / norm statistics)
     oh: int = 0         # OUTPUT spatial size
     ow: int = 0
-    tapmask: int = 0    # OP_CONV_MMA: bit i set = tap i (row-major in the k x k window) can touch the image
+    tapmask: int = 0    # conv: bit i set = tap i (row-major in the k x k window) can touch the image
+    wbuf: object = -1   # arena offset where this op's parameter segment is staged (cp.async.bulk)
     name: str = ""
 
     def words(self) -> List[int]:
-        vals = [getattr(self, f) if not f.startswith("pad") else 0 for f in OP_FIELDS]
+        vals = [getattr(self, f) if f != "pad0" else 0 for f in OP_FIELDS]
         return [int(v) for v in vals]
 
 
 @dataclass
 class Program:
     ops: List[Op]
+    geos: List[Geo]
     arena_floats: int
     blob: np.ndarray                 # float32 parameter blob
-    in_off: int                      # arena offset of the [2,H,W] network input (x, planar re/im)
-    out_off: int                     # arena offset of the [2,H,W] raw network output (before /sigma)
+    in_off: int                      # arena offset of the network input x (2 channels, geometry 0)
+    out_off: int                     # arena offset of the raw network output (before /sigma), geometry 0
+    post_off: int                    # scratch for the sampler phases that follow the network
     H: int
     W: int
     ngf: int
@@ -109,8 +132,7 @@ class Program:
     nthreads: int
     max_w_len: int
     conv_flops: int                  # dense conv FLOPs / forward / sample (reference convention)
-    precision: str = "fp32"
-    post_off: int = 0                # arena offset of the post-network scratch (2*H*W + 4*nthreads floats)
+    precision: str
 
     def op_table(self) -> np.ndarray:
         t = np.zeros((len(self.ops), OP_WORDS), dtype=np.int32)
@@ -118,13 +140,52 @@ class Program:
             t[i] = op.words()
         return t
 
+    def geo_table(self) -> np.ndarray:
+        t = np.zeros((MAX_GEO, GEO_WORDS), dtype=np.int32)
+        for i, g in enumerate(self.geos):
+            t[i] = g.words()
+        return t
+
+    def geo_of(self, h: int, w: int) -> Geo:
+        for g in self.geos:
+            if (g.h, g.w) == (h, w):
+                return g
+        raise KeyError((h, w))
+
+    # ---- arena access helpers (numpy arrays or torch tensors) ----
+    def _index(self, off: int, c: int, h: int, w: int) -> np.ndarray:
+        g = self.geo_of(h, w)
+        cc, yy, xx = np.meshgrid(np.arange(c), np.arange(h), np.arange(w), indexing="ij")
+        return off + ((cc // 4) * g.pps + g.org + yy * g.wp + xx) * 4 + cc % 4
+
+    def read(self, arena, off: int, c: int, h: int, w: int):
+        """[c,h,w] copy of the tensor stored at float offset ``off``."""
+        idx = self._index(off, c, h, w)
+        if isinstance(arena, np.ndarray):
+            return arena[idx]
+        import torch
+        return arena[torch.from_numpy(idx)]
+
+    def write(self, arena, off: int, value, cstore: Optional[int] = None) -> None:
+        """Store a [c,h,w] tensor (zero halo, zero padding channels)."""
+        c, h, w = value.shape
+        g = self.geo_of(h, w)
+        n = g.floats(cstore or c)
+        arena[off:off + n] = 0
+        idx = self._index(off, c, h, w)
+        if isinstance(arena, np.ndarray):
+            arena[idx] = value
+        else:
+            import torch
+            arena[torch.from_numpy(idx)] = value
+
 
 class _Planner:
     """Offline arena planner.
 
-    Tensors are registered with their live interval in units of emitted ops
-    ([born, died)); ``solve`` places them greedily by decreasing size at the lowest
-    offset that does not collide with an already placed tensor whose interval overlaps."""
+    Tensors are registered with their live interval in units of emitted ops ([born, died)); ``solve``
+    places them greedily by decreasing size at the lowest offset that does not collide with an already
+    placed tensor whose interval overlaps."""
 
     def __init__(self, align: int = 4):
         self.align = align
@@ -134,10 +195,12 @@ class _Planner:
         self.offs: Dict[str, int] = {}
         self.peak = 0
 
-    def alloc(self, name: str, n: int, now: int) -> None:
+    def alloc(self, name: str, n: int, now: int, died: Optional[int] = None) -> None:
         assert name not in self.size, name
         self.size[name] = (n + self.align - 1) // self.align * self.align
         self.born[name] = now
+        if died is not None:
+            self.died[name] = died
 
     def free(self, name: str, now: int) -> None:
         assert name in self.size and name not in self.died, name
@@ -161,16 +224,26 @@ class _Planner:
             self.peak = max(self.peak, pos + self.size[n])
 
 
+def tf32_rna(x: np.ndarray) -> np.ndarray:
+    """fp32 -> TF32 (10-bit mantissa), round to nearest with ties away from zero: cvt.rna.tf32.f32."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 class ProgramBuilder:
     """Builds the op list for one (ngf, H, W) instance of NCSNv2Deepest."""
 
+    # largest parameter segment (floats) one slot of the shared-memory ring holds; convs whose fragment
+    # array is bigger are split into cout chunks (each chunk is its own op)
+    SLOT_FLOATS = 9248
+
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
-                 channels: int = 2, nthreads: int = 512, precision: str = "fp32"):
+                 channels: int = 2, nthreads: int = 512, precision: str = "tf32x3"):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % (PRECISIONS,))
-        self.precision = precision
         if H <= 0 or W <= 0 or H % 8 or W % 8:
             raise ValueError("Nt and Nr must be positive multiples of 8 (three 2x mean-pools), got %dx%d" % (H, W))
+        self.precision = precision
         self.sd = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
         self.ngf, self.H, self.W, self.channels = ngf, H, W, channels
         self.nthreads = nthreads
@@ -181,24 +254,43 @@ class ProgramBuilder:
         self.shape: Dict[str, Tuple[int, int, int]] = {}
         self.flops = 0
         self._tmp = 0
+        # geometries: one per resolution; the halo covers every live tap used at that resolution.  The
+        # dilated stages (dilation 2 and 4) run at the lowest resolution (ncsnv2.py:240-254).
+        self.geos: List[Geo] = []
+        for lvl in range(4):
+            h, w = H >> lvl, W >> lvl
+            dils = [1] if lvl < 3 else [1, 2, 4]
+            hy = max([d for d in dils if d < h] + [0])
+            hx = max([d for d in dils if d < w] + [0])
+            self.geos.append(Geo(h, w, hy, hx))
+
+    def gi(self, h: int, w: int) -> int:
+        for i, g in enumerate(self.geos):
+            if (g.h, g.w) == (h, w):
+                return i
+        raise KeyError((h, w))
 
     # -- tensors ----------------------------------------------------------
-    def new(self, name: str, c: int, h: int, w: int) -> str:
-        self.ar.alloc(name, c * PS(h, w), len(self.ops))
+    def new(self, name: str, c: int, h: int, w: int, cstore: Optional[int] = None) -> str:
+        self.ar.alloc(name, self.geos[self.gi(h, w)].floats(cstore or c), len(self.ops))
         self.shape[name] = (c, h, w)
         return name
 
-    def tmp(self, c: int, h: int, w: int, tag: str = "t") -> str:
+    def new_raw(self, name: str, nfloats: int) -> str:
+        self.ar.alloc(name, nfloats, len(self.ops))
+        return name
+
+    def tmp(self, c: int, h: int, w: int, tag: str = "t", cstore: Optional[int] = None) -> str:
         self._tmp += 1
-        return self.new("%s%d" % (tag, self._tmp), c, h, w)
+        return self.new("%s%d" % (tag, self._tmp), c, h, w, cstore)
+
+    def tmp_raw(self, nfloats: int, tag: str) -> str:
+        self._tmp += 1
+        return self.new_raw("%s%d" % (tag, self._tmp), nfloats)
 
     def free(self, *names: str) -> None:
         for n in names:
             self.ar.free(n, len(self.ops))
-
-    def off(self, name: Optional[str]):
-        """Tensor reference; resolved to an arena offset by ``build`` once the plan is solved."""
-        return name
 
     # -- parameter blob ---------------------------------------------------
     def _push(self, arrs: List[np.ndarray]) -> Tuple[int, int, List[int]]:
@@ -218,9 +310,14 @@ class ProgramBuilder:
     # -- ops --------------------------------------------------------------
     def conv(self, prefix: str, src: str, dst: Optional[str] = None, acc: Optional[str] = None,
              edst: Optional[str] = None, dil: int = 1, pool: bool = False) -> None:
-        """One Conv2d (reference ``layers.py:28-60``) + fused epilogue.
+        """One Conv2d (reference ``layers.py:28-60``) + fused epilogue, as an implicit GEMM on tensor cores:
 
-        v = conv(src) + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v)."""
+            D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]   per (live tap, cin chunk)
+
+        v = conv(src) + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v).
+        The weights are packed in mma.sync m16n8k8 B-fragment order: frag[step][ntile][lane] =
+        (hi0, hi1[, lo0, lo1]) where lane = 4*g + t holds B[k = t (+4)][n = g], step = live_tap_index *
+        KC + cin_chunk, hi = TF32(w), lo = TF32(w - hi) (lo only in the 3xTF32 mode)."""
         wt = self.sd[prefix + ".weight"]
         bias = self.sd.get(prefix + ".bias")
         cout, cin, k, k2 = wt.shape
@@ -231,50 +328,16 @@ class ProgramBuilder:
         for t in (dst, acc, edst):
             if t is not None:
                 assert self.shape[t] == (cout, oh, ow), (prefix, t, self.shape[t], (cout, oh, ow))
-        # dense FLOP count, reference convention (conv evaluated at input resolution)
-        self.flops += 2 * h * w * cin * k * k * cout
-        if self.precision != "fp32":
-            self._conv_mma(prefix, wt, bias, src, dst, acc, edst, dil, pool, (cin, h, w), (cout, oh, ow))
-            return
-        # ---- tiling choice (see csrc/sbc_ops.h: conv_partial) ----
-        cb = 8 if cout % 8 == 0 else (4 if cout % 4 == 0 else (2 if cout % 2 == 0 else 1))
-        px = 4 if ow % 4 == 0 else (2 if ow % 2 == 0 else 1)
-        items = oh * (ow // px) * (cout // cb)
-        ks = 1
-        while items * ks * 2 <= self.nthreads and cin % (ks * 2) == 0 and ks < 32:
-            ks *= 2
-        # pack weights [cout/cb][cin][k*k][cb]
-        wp = wt.reshape(cout // cb, cb, cin, k * k).transpose(0, 2, 3, 1)
-        if pool:
-            wp = wp * np.float32(0.25)
-        arrs = [wp] + ([bias] if bias is not None else [])
-        w_off, w_len, rels = self._push(arrs)
-        # K-split partial sums are combined with warp shuffles (ks adjacent lanes): no scratch
-        self.ops.append(Op(OP_CONV, F_POOL if pool else 0, self.off(src), self.off(dst), self.off(acc),
-                           self.off(edst), cin, cout, h, w, k, dil, w_off, w_len,
-                           rels[1] if bias is not None else -1, px, cb, ks,
-                           -1, oh, ow, name=prefix))
-
-    # largest parameter segment (floats) that one slot of the shared-memory ring holds; MMA convs whose
-    # fragment array is bigger are split into cout chunks (each chunk is its own op)
-    SLOT_FLOATS = 9248
-
-    def _conv_mma(self, prefix, wt, bias, src, dst, acc, edst, dil, pool, ishape, oshape) -> None:
-        """Tensor-core conv: implicit GEMM  D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]
-        per (tap, cin chunk) with mma.sync.m16n8k8 TF32 (csrc/sbc_mma.h).  The weights are packed in
-        B-fragment order: frag[step][ntile][lane] = (hi0, hi1[, lo0, lo1]) where lane = 4*g + t holds
-        B[k = t (+4)][n = g], step = live_tap_index * KC + cin_chunk; hi = TF32(w), lo = TF32(w - hi)
-        (lo only in the 3xTF32 mode)."""
-        cin, h, w = ishape
-        cout, oh, ow = oshape
-        k = wt.shape[2]
+        self.flops += 2 * h * w * cin * k * k * cout       # dense count, reference convention
         r = k // 2
         x3 = self.precision == "tf32x3"
-        E = 4 if x3 else 2                          # floats per lane per fragment
+        E = 4 if x3 else 2                                 # floats per lane per fragment
+        sg = self.geos[self.gi(h, w)]
         live = []
         for tap in range(k * k):
             dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
-            if abs(dy) < h and abs(dx) < w:          # otherwise the tap only ever reads zero padding
+            if abs(dy) < h and abs(dx) < w:                # otherwise the tap only ever reads zero padding
+                assert abs(dy) <= sg.hy and abs(dx) <= sg.hx, "halo too small"
                 live.append(tap)
         tapmask = sum(1 << t for t in live)
         KC, NT = (cin + 7) // 8, (cout + 7) // 8
@@ -286,7 +349,7 @@ class ProgramBuilder:
         wpad[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
         g, t = np.arange(32) >> 2, np.arange(32) & 3
         nwarps = self.nthreads // 32
-        ps_out = PS(oh, ow)
+        dgeo = self.geos[self.gi(oh, ow)]
         for nt0 in range(0, NT, nt_chunk):
             ntc = min(nt_chunk, NT - nt0)
             co0, co1 = nt0 * 8, min(cout, (nt0 + ntc) * 8)
@@ -307,12 +370,12 @@ class ProgramBuilder:
             ks = 1
             while units * ks * 2 <= nwarps and ks * 2 <= S:
                 ks *= 2
-            scratch = self.tmp(1, 1, nwarps * 32 * 4, "ksp") if ks > 1 else None
+            scratch = self.tmp_raw(nwarps * 32 * 4, "ksp") if ks > 1 else None
             flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0)
-            shift = lambda name: None if name is None else (name, co0 * ps_out)
-            self.ops.append(Op(OP_CONV_MMA, flags, self.off(src), shift(dst), shift(acc), shift(edst),
-                               cin, co1 - co0, h, w, k, dil, w_off, w_len, rels[1] if bias is not None else -1,
-                               0, 0, ks, self.off(scratch), oh, ow, tapmask=tapmask,
+            shift = lambda name: -1 if name is None else (name, (co0 // 4) * dgeo.pps * 4)
+            self.ops.append(Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin, co1 - co0, h, w, k,
+                               dil, w_off, w_len, rels[1] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
+                               ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask,
                                name=prefix + ("" if nt_chunk == NT else "[co%d:%d]" % (co0, co1))))
             if scratch is not None:
                 self.free(scratch)
@@ -324,34 +387,36 @@ class ProgramBuilder:
         w_off, w_len, _ = self._push([np.concatenate([self.sd[prefix + ".alpha"],
                                                       self.sd[prefix + ".gamma"],
                                                       self.sd[prefix + ".beta"]])])
-        # scratch: per-channel (mean, rstd)
-        scratch = self.tmp(1, 1, 2 * c, "nsc")
-        self.ops.append(Op(OP_NORM_ELU, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w,
-                           w_off=w_off, w_len=w_len, scratch=self.off(scratch), oh=h, ow=w, name=prefix))
+        # scratch: per-warp partial sums of the two statistics passes (4 channels each) + per-channel (mean, M2)
+        nwarps = self.nthreads // 32
+        scratch = self.tmp_raw(2 * nwarps * 4 + 2 * c, "nsc")
+        self.ops.append(Op(OP_NORM_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, w_off=w_off, w_len=w_len,
+                           sgeo=self.gi(h, w), dgeo=self.gi(h, w), scratch=scratch, oh=h, ow=w, name=prefix))
         self.free(scratch)
 
     def elu(self, src: str, dst: str) -> None:
         c, h, w = self.shape[src]
-        self.ops.append(Op(OP_ELU, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w, oh=h, ow=w,
-                           name="elu"))
+        self.ops.append(Op(OP_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, sgeo=self.gi(h, w), dgeo=self.gi(h, w),
+                           oh=h, ow=w, name="elu"))
 
-    def affine(self, src: str, dst: str) -> None:
+    def affine(self, src: str, dst: str, cstore: int) -> None:
+        """dst = 2*src - 1 on the cin real channels; channels cin..cstore-1 of dst are written as zeros."""
         c, h, w = self.shape[src]
-        self.ops.append(Op(OP_AFFINE, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w, oh=h, ow=w,
-                           name="2x-1"))
+        self.ops.append(Op(OP_AFFINE, 0, src, dst, cin=c, cout=cstore, h=h, w=w, sgeo=self.gi(h, w),
+                           dgeo=self.gi(h, w), oh=h, ow=w, name="2x-1"))
 
     def maxpool5(self, src: str, dst: str) -> None:
         c, h, w = self.shape[src]
-        self.ops.append(Op(OP_MAXPOOL5, 0, self.off(src), self.off(dst), cin=c, cout=c, h=h, w=w, oh=h, ow=w,
-                           name="maxpool5"))
+        self.ops.append(Op(OP_MAXPOOL5, 0, src, dst, cin=c, cout=c, h=h, w=w, sgeo=self.gi(h, w), dgeo=self.gi(h, w),
+                           oh=h, ow=w, name="maxpool5"))
 
     def upacc(self, src: str, acc: str, edst: Optional[str] = None) -> None:
         """acc += bilinear(src, size=acc.shape, align_corners=True) (``layers.py:182-183``)."""
         c, h, w = self.shape[src]
         c2, oh, ow = self.shape[acc]
         assert c == c2
-        self.ops.append(Op(OP_UPACC, 0, self.off(src), -1, self.off(acc), self.off(edst), cin=c, cout=c,
-                           h=h, w=w, oh=oh, ow=ow, name="upacc"))
+        self.ops.append(Op(OP_UPACC, 0, src, -1, acc, edst if edst is not None else -1, cin=c, cout=c, h=h, w=w,
+                           sgeo=self.gi(h, w), dgeo=self.gi(oh, ow), oh=oh, ow=ow, name="upacc"))
 
     # -- blocks -----------------------------------------------------------
     def residual(self, p: str, x: str, cout: int, down: bool, dil: Optional[int]) -> str:
@@ -461,14 +526,12 @@ class ProgramBuilder:
     def build(self) -> Program:
         ngf, H, W = self.ngf, self.H, self.W
         xin = self.new("x_in", self.channels, H, W)
-        a = self.tmp(self.channels, H, W)
-        self.affine(xin, a)
+        a = self.tmp(self.channels, H, W, cstore=8)     # begin_conv reads one chunk of 8 input channels
+        self.affine(xin, a, cstore=8)
         o = self.tmp(ngf, H, W, "o")
         self.conv("begin_conv", a, dst=o)
         self.free(a)
         l1 = self.residual("res1.1", self.residual("res1.0", o, ngf, False, None), ngf, False, None)
-        # skip tensors stay live; each stage works on a copy-free continuation:
-        # the first block of the next stage reads the skip (norm1 + shortcut) without modifying it.
         l2 = self._stage("res2", l1, 2 * ngf, None)
         l3 = self._stage("res3", l2, 2 * ngf, None)
         l31 = self._stage("res31", l3, 2 * ngf, None)
@@ -487,28 +550,43 @@ class ProgramBuilder:
         self.conv("end_conv", t, dst=out)
         self.free(t)
         # scratch for the sampler phases that follow the network (residual P*x-y, reductions)
-        post = self.new("post", 1, 1, 2 * H * W + 4 * self.nthreads)   # one plane of 2*H*W + 4*nthr (+pad)
+        post = self.new_raw("post", 2 * H * W + 4 * self.nthreads)
         blob = np.concatenate(self.blob) if self.blob else np.zeros(0, np.float32)
         assert blob.size == self.blob_len
         max_w_len = max(op.w_len for op in self.ops)
+        # ---- staging buffers for the per-op parameter segments: the segment of op i is copied (cp.async.bulk)
+        # while the previous parameterised op runs, so its buffer is live over [prev, i]; the first one is
+        # refilled at the end of every forward for the next one and simply stays allocated.
+        end = len(self.ops) + 1
+        prev = None
+        for i, op in enumerate(self.ops):
+            if op.w_len > 0:
+                name = "wbuf%d" % i
+                if prev is None:
+                    self.ar.alloc(name, op.w_len, 0, end)
+                else:
+                    self.ar.alloc(name, op.w_len, prev, i + 1)
+                op.wbuf = name
+                prev = i
         # ---- solve the arena plan and resolve tensor names to float offsets ----
-        self.ar.solve(len(self.ops) + 1)
+        self.ar.solve(end)
         for op in self.ops:
-            for f in ("src", "dst", "acc", "edst", "scratch"):
+            for f in ("src", "dst", "acc", "edst", "scratch", "wbuf"):
                 v = getattr(op, f)
                 if isinstance(v, tuple):
                     setattr(op, f, self.ar.offs[v[0]] + v[1])
+                elif isinstance(v, str):
+                    setattr(op, f, self.ar.offs[v])
                 else:
-                    setattr(op, f, -1 if (v is None or v == -1) else self.ar.offs[v])
-        return Program(self.ops, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out], H, W, ngf,
-                       self.channels, self.nthreads, max_w_len, self.flops, precision=self.precision,
-                       post_off=self.ar.offs[post])
+                    setattr(op, f, -1 if v is None else int(v))
+        return Program(self.ops, self.geos, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out],
+                       self.ar.offs[post], H, W, ngf, self.channels, self.nthreads, max_w_len, self.flops,
+                       self.precision)
 
     def _stage(self, p: str, skip: str, cout: int, dil: Optional[int]) -> str:
         """Two ResidualBlocks, the first 'down'; ``skip`` must survive (it feeds a RefineBlock later)."""
         cin, h, w = self.shape[skip]
         d = dil or 1
-        # first block, written out so that it does not consume `skip`
         t = self.tmp(cin, h, w)
         self.norm_elu(p + ".0.normalize1", skip, t)
         t2 = self.tmp(cin, h, w)
@@ -530,62 +608,41 @@ class ProgramBuilder:
         return self.residual(p + ".1", out, cout, False, dil)
 
 
-def tf32_rna(x: np.ndarray) -> np.ndarray:
-    """fp32 -> TF32 (10-bit mantissa), round to nearest with ties away from zero: cvt.rna.tf32.f32."""
-    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
-    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
-
-
 def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channels: int = 2,
-                  nthreads: int = 512, precision: str = "fp32") -> Program:
+                  nthreads: int = 512, precision: str = "tf32x3") -> Program:
     return ProgramBuilder(state, ngf, H, W, channels, nthreads, precision).build()
 
 
 # ---------------------------------------------------------------------------
 # torch (CPU) interpreter of a Program -- host-side check of the schedule only
 # ---------------------------------------------------------------------------
-def tensor_view(arena, off: int, c: int, h: int, w: int):
-    """[c,h,w] view of a planar tensor stored at float offset ``off`` with padded plane stride
-    (works for numpy arrays and torch tensors)."""
-    ps = PS(h, w)
-    if isinstance(arena, np.ndarray):
-        return np.lib.stride_tricks.as_strided(arena[off:], (c, h, w), (4 * ps, 4 * w, 4))
-    return arena.as_strided((c, h, w), (ps, w, 1), off)
-
-
 def conv_weights(prog: Program, op: Op):
     """Decode (weight [cout,cin,k,k], bias or None) of a conv op back from the packed blob."""
     import torch
     blob = torch.from_numpy(prog.blob)
     k = op.ksize
-    if op.kind == OP_CONV:
-        cb = op.cb
-        nw = op.cout * op.cin * k * k
-        wp = blob[op.w_off:op.w_off + nw].view(op.cout // cb, op.cin, k * k, cb)
-        wt = wp.permute(0, 3, 1, 2).reshape(op.cout, op.cin, k, k)
-    else:
-        live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
-        KC, NT = (op.cin + 7) // 8, (op.cout + 7) // 8
-        E = 4 if (op.flags & F_X3) else 2
-        n = len(live) * KC * NT * 32 * E
-        frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, E)
-        full = torch.zeros(NT * 8, KC * 8, k * k)
-        g, t = torch.arange(32) >> 2, torch.arange(32) & 3
-        for i, tap in enumerate(live):
-            for kc in range(KC):
-                for nt in range(NT):
-                    lo0 = frag[i, kc, nt, :, 2] if E == 4 else 0.0
-                    lo1 = frag[i, kc, nt, :, 3] if E == 4 else 0.0
-                    full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + lo0
-                    full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + lo1
-        wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
+    live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
+    KC, NT = (op.cin + 7) // 8, (op.cout + 7) // 8
+    E = 4 if (op.flags & F_X3) else 2
+    n = len(live) * KC * NT * 32 * E
+    frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, E)
+    full = torch.zeros(NT * 8, KC * 8, k * k)
+    g, t = torch.arange(32) >> 2, torch.arange(32) & 3
+    for i, tap in enumerate(live):
+        for kc in range(KC):
+            for nt in range(NT):
+                lo0 = frag[i, kc, nt, :, 2] if E == 4 else 0.0
+                lo1 = frag[i, kc, nt, :, 3] if E == 4 else 0.0
+                full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + lo0
+                full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + lo1
+    wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
     bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
     return wt, bias
 
 
 def simulate(prog: Program, x, upto: Optional[int] = None):
-    """Run the program on one sample ``x`` ([channels,H,W] float32 torch tensor) with torch CPU ops
-    (fp32 arithmetic whatever the program's precision mode).
+    """Run the program on one sample ``x`` ([channels,H,W] float32 torch tensor) with torch CPU ops (fp32
+    arithmetic; in "tf32" mode the decoded weights carry their TF32 rounding).
 
     Returns (raw network output [channels,H,W] (before the /sigma of ncsnv2.py:295-298), arena)."""
     import torch
@@ -593,41 +650,38 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
 
     arena = torch.zeros(prog.arena_floats, dtype=torch.float32)
     blob = torch.from_numpy(prog.blob)
-
-    def view(off, c, h, w):
-        return tensor_view(arena, off, c, h, w)
-
-    view(prog.in_off, prog.channels, prog.H, prog.W).copy_(x.float())
+    rd = lambda off, c, h, w: prog.read(arena, off, c, h, w)
+    prog.write(arena, prog.in_off, x.float())
     for i, op in enumerate(prog.ops):
         if upto is not None and i >= upto:
             break
         if op.kind == OP_AFFINE:
-            view(op.dst, op.cin, op.h, op.w).copy_(2 * view(op.src, op.cin, op.h, op.w) - 1.0)
+            prog.write(arena, op.dst, 2 * rd(op.src, op.cin, op.h, op.w) - 1.0, cstore=op.cout)
         elif op.kind == OP_ELU:
-            view(op.dst, op.cin, op.h, op.w).copy_(F.elu(view(op.src, op.cin, op.h, op.w)))
+            prog.write(arena, op.dst, F.elu(rd(op.src, op.cin, op.h, op.w)))
         elif op.kind == OP_MAXPOOL5:
-            view(op.dst, op.cin, op.h, op.w).copy_(
-                F.max_pool2d(view(op.src, op.cin, op.h, op.w)[None], 5, 1, 2)[0])
+            prog.write(arena, op.dst, F.max_pool2d(rd(op.src, op.cin, op.h, op.w)[None], 5, 1, 2)[0])
         elif op.kind == OP_NORM_ELU:
             c = op.cin
-            xs = view(op.src, c, op.h, op.w)
+            xs = rd(op.src, c, op.h, op.w)
             al, ga, be = blob[op.w_off:op.w_off + 3 * c].view(3, c)
             mu = xs.mean(dim=(1, 2))
             m, v = mu.mean(), mu.var()
             mh = (mu - m) / torch.sqrt(v + 1e-5)
             hn = (xs - mu[:, None, None]) / torch.sqrt(xs.var(dim=(1, 2), unbiased=False)[:, None, None] + 1e-5)
             o = ga[:, None, None] * (hn + (mh * al)[:, None, None]) + be[:, None, None]
-            view(op.dst, c, op.h, op.w).copy_(F.elu(o))
+            prog.write(arena, op.dst, F.elu(o))
         elif op.kind == OP_UPACC:
-            s = view(op.src, op.cin, op.h, op.w)
-            a = view(op.acc, op.cin, op.oh, op.ow)
-            a += F.interpolate(s[None], size=(op.oh, op.ow), mode="bilinear", align_corners=True)[0]
+            s = rd(op.src, op.cin, op.h, op.w)
+            a = rd(op.acc, op.cin, op.oh, op.ow)
+            a = a + F.interpolate(s[None], size=(op.oh, op.ow), mode="bilinear", align_corners=True)[0]
+            prog.write(arena, op.acc, a)
             if op.edst >= 0:
-                view(op.edst, op.cin, op.oh, op.ow).copy_(F.elu(a))
-        elif op.kind in (OP_CONV, OP_CONV_MMA):
+                prog.write(arena, op.edst, F.elu(a))
+        elif op.kind == OP_CONV_MMA:
             k = op.ksize
             wt, bias = conv_weights(prog, op)
-            s = view(op.src, op.cin, op.h, op.w)[None]
+            s = rd(op.src, op.cin, op.h, op.w)[None]
             if op.flags & F_POOL:
                 # packed weights already carry the 1/4; conv at full res then 2x2 SUM
                 v = F.conv2d(s, wt, None, 1, op.dil * (k // 2), op.dil)
@@ -638,14 +692,13 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
                 v = F.conv2d(s, wt, bias, 1, op.dil * (k // 2), op.dil)
             v = v[0]
             if op.dst >= 0:
-                view(op.dst, op.cout, op.oh, op.ow).copy_(v)
+                prog.write(arena, op.dst, v)
             if op.acc >= 0:
-                a = view(op.acc, op.cout, op.oh, op.ow)
-                a += v
-                v = a
+                v = rd(op.acc, op.cout, op.oh, op.ow) + v
+                prog.write(arena, op.acc, v)
             if op.edst >= 0:
-                view(op.edst, op.cout, op.oh, op.ow).copy_(F.elu(v))
+                prog.write(arena, op.edst, F.elu(v))
         else:
             raise ValueError(op.kind)
-    out = view(prog.out_off, prog.channels, prog.H, prog.W).clone()
+    out = rd(prog.out_off, prog.channels, prog.H, prog.W).clone()
     return out, arena

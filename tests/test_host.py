@@ -116,6 +116,10 @@ def test_program_tiling_covers_other_geometries():
             p = program.build_program(sd, 8, H, W, precision=prec)
             assert p.conv_flops == 51740672 * (H * W) // 1024
             assert all(op.w_len <= p.max_w_len and op.w_off % 4 == 0 for op in p.ops)
+            assert all(op.w_len == 0 or (op.wbuf >= 0 and op.wbuf % 4 == 0 and op.wbuf + op.w_len <= p.arena_floats)
+                       for op in p.ops)
+    p = program.build_program(sd, 8, 64, 16)
+    assert p.arena_floats * 4 + 256 <= 227 * 1024, "the shipped geometry must fit the B200 shared memory"
     with pytest.raises(ValueError, match="multiples of 8"):
         program.build_program(sd, 8, 60, 16)
 

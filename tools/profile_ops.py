@@ -50,10 +50,9 @@ rows = []
 for i, op in enumerate(prog.ops):
     c = int(d[i])
     key = kinds[op.kind]
-    if op.kind in (1, 6):
-        key = "conv%s %dx%d c%d->%d k%d d%d%s px%d cb%d ks%d" % ("_mma" if op.kind == 6 else "", op.h, op.w, op.cin,
-                                                               op.cout, op.ksize, op.dil,
-                                                               " pool" if op.flags & 1 else "", op.px, op.cb, op.ks)
+    if op.kind == 6:
+        key = "conv_mma %dx%d c%d->%d k%d d%d%s ks%d" % (op.h, op.w, op.cin, op.cout, op.ksize, op.dil,
+                                                        " pool" if op.flags & 1 else "", op.ks)
     else:
         key = "%s %dx%d c%d" % (key, op.h, op.w, op.cin)
     by_kind.setdefault(key, [0, 0])
