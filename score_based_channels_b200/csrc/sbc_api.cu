@@ -83,7 +83,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     int next = -1;
     for (int i = desc->n_ops - 1; i >= 0; i--) {
         SbcOp& o = ops[i];
-        o.pad0 = next;
+        o.next_w = next;
         if (o.w_len > 0) next = i;
         if (o.kind < 0 || o.kind > SBC_OP_LAST) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
         if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
@@ -95,11 +95,24 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
             delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter staging buffer", i);
         }
         if (o.kind == SBC_OP_CONV_MMA) {
+            const int E = 2;
             const bool ok = o.ks >= 1 && o.ks <= SBC_NTHREADS / 32 && (o.ks & (o.ks - 1)) == 0 &&
                             (o.ksize == 1 || o.ksize == 3) && o.tapmask != 0 && (o.ks == 1 || o.scratch >= 0) &&
-                            o.w_off % 4 == 0;
+                            o.cout % 2 == 0 && o.MT == (o.oh * o.ow + 15) / 16 && o.NT == (o.cout + 7) / 8 &&
+                            o.S >= 1 && o.frag_rel >= o.S && o.frag_rel % 4 == 0 &&
+                            o.frag_rel + o.S * o.NT * 32 * E <= o.w_len;
             if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported tensor-core conv", i); }
         }
+        if ((o.kind == SBC_OP_NORM_ELU || o.kind == SBC_OP_ELU || o.kind == SBC_OP_MAXPOOL5 || o.kind == SBC_OP_UPACC) &&
+            o.cin % 8) { delete m; return sbc_fail(SBC_E_ARG, "op %d: channel count must be a multiple of 8", i); }
+    }
+    // parameter segment of the next parameterised op (the last one wraps to the first)
+    for (int i = 0; i < desc->n_ops; i++) {
+        SbcOp& o = ops[i];
+        const int j = o.next_w >= 0 ? o.next_w : next;
+        o.nw_off = j >= 0 ? ops[j].w_off : 0;
+        o.nw_len = j >= 0 ? ops[j].w_len : 0;
+        o.nw_buf = j >= 0 ? ops[j].wbuf : 0;
     }
     m->first_w = next;
 

@@ -94,7 +94,10 @@ __device__ __forceinline__ void sbc_bulk_g2s(void* dst_smem, const void* src_gme
 // ---------------------------------------------------------------------------------------------
 // tensor-core conv (SBC_OP_CONV_MMA): warp-level implicit GEMM on mma.sync m16n8k8 TF32.
 //   X3 = true : 3xTF32 split  (a = a_hi + a_lo, b = b_hi + b_lo;  D += a_lo b_hi + a_hi b_lo + a_hi b_hi)
-//               -> fp32-equivalent accuracy (the parity mode);  X3 = false: plain TF32 operands.
+//               -> fp32-equivalent accuracy (the parity mode);  X3 = false: TF32 operands (cvt.rna).
+// The K loop is the hot loop of the whole sampler; per K step and 16-pixel tile it issues 2 LDS.64 (A), the
+// operand split (8 ALU ops in X3 mode, 4 cvt otherwise) and the MMAs -- the tensor pipe (512 TF32 MAC/clk/SM
+// through mma.sync) is the binding unit, everything else fits in its shadow.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sbc_mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
     asm volatile(
@@ -103,94 +106,119 @@ __device__ __forceinline__ void sbc_mma_tf32(float (&d)[4], const float (&a)[4],
         : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
           "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
-
-#define SBC_MMA_SLOTS 4   // (pixel tile, pooling position) accumulators per warp per pass
-#define SBC_MMA_NTW 2     // cout tiles that share one A gather
-
-__device__ __forceinline__ float sbc_dev_tf32_rn(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+__device__ __forceinline__ float sbc_cvt_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
-__device__ __forceinline__ float sbc_dev_tf32_rz(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// Accumulate K steps [s0, s1) for up to 4 slots (slot j = tile mt0 + (j / nq) * mt_stride, pooling position
-// j % nq) and `ntw` (1 or 2) cout tiles nt0, nt0+1 that share each gathered A fragment.  B fragments come from
-// the staged parameter segment.  A K step costs per slot: 2 address adds + 4 LDS + the operand split.
-template <bool X3>
-__device__ __forceinline__ void sbc_mma_pass(const SbcOp& op, const SbcMmaGeom& M, const SbcGeo& GS,
-                                             const float* arena, const float* wseg, int mt0, int mt_stride,
-                                             int nslots, int nt0, int ntw, int s0, int s1, int lane,
-                                             float (&acc)[SBC_MMA_SLOTS][SBC_MMA_NTW][4]) {
-    const int g = lane >> 2, t = lane & 3;
-    int po0[SBC_MMA_SLOTS], po1[SBC_MMA_SLOTS];
+// Accumulate K steps [s0, s1) for NS pixel-tile slots (row offsets po[j]) and NN cout tiles that share each
+// gathered A fragment.  asrc = arena + op.src + 2*t; bfrag = first B fragment of this lane for cout tile nt0;
+// bstride = floats per K step in the fragment array.
+template <bool X3, int NS, int NN>
+__device__ __forceinline__ void sbc_mma_pass(const float* __restrict__ asrc, const int (&po)[NS][2],
+                                             const int* __restrict__ steptab, const float* __restrict__ bfrag,
+                                             int bstride, int s0, int s1, float (&acc)[NS][NN][4]) {
+#pragma unroll 1
+    for (int s = s0; s < s1; s++) {
+        const int off = steptab[s];
+        const float* bp = bfrag + s * bstride;
+        float bh[NN][2], bl[NN][2];
 #pragma unroll
-    for (int j = 0; j < SBC_MMA_SLOTS; j++) {
-        po0[j] = po1[j] = 0;
-        if (j < nslots) {
-            const int mt = mt0 + (j / M.nq) * mt_stride, quad = j % M.nq;
-            po0[j] = sbc_mma_row_off(op, M, GS, mt, quad, g);
-            po1[j] = sbc_mma_row_off(op, M, GS, mt, quad, g + 8);
-        }
-    }
-    constexpr int E = X3 ? 4 : 2;
-    const int k = op.ksize, r = k >> 1, dil = op.dil;
-    const int cg1 = GS.pps * 4;
-    const float* src = arena + op.src + t;
-    int s = 0;
-    for (int tap = 0; tap < k * k; tap++) {
-        if (!((op.tapmask >> tap) & 1)) continue;
-        const int ky = tap / k, kx = tap - ky * k;
-        const int toff = ((ky - r) * dil * GS.wp + (kx - r) * dil) * 4;
-        for (int kc = 0; kc < M.KC; kc++, s++) {
-            if (s < s0 || s >= s1) continue;
-            const float* bp = src + 2 * kc * cg1 + toff;
-            float bh[SBC_MMA_NTW][2], bl[SBC_MMA_NTW][2];
-#pragma unroll
-            for (int n = 0; n < SBC_MMA_NTW; n++) {
-                bh[n][0] = bh[n][1] = bl[n][0] = bl[n][1] = 0.f;
-                if (n < ntw) {
-                    const float* wp = wseg + ((size_t)(s * M.NT + nt0 + n) * 32 + lane) * E;
-                    if (X3) {
-                        const float4 b = *reinterpret_cast<const float4*>(wp);
-                        bh[n][0] = b.x; bh[n][1] = b.y; bl[n][0] = b.z; bl[n][1] = b.w;
-                    } else {
-                        const float2 b = *reinterpret_cast<const float2*>(wp);
-                        bh[n][0] = b.x; bh[n][1] = b.y;
-                    }
-                }
+        for (int n = 0; n < NN; n++) {
+            const float2 b = *reinterpret_cast<const float2*>(bp + n * 64);
+            if (X3) {   // w = hi + lo exactly; the tensor core truncates lo to its leading 11 bits
+                bh[n][0] = __uint_as_float(__float_as_uint(b.x) & 0xFFFFE000u);
+                bh[n][1] = __uint_as_float(__float_as_uint(b.y) & 0xFFFFE000u);
+                bl[n][0] = b.x - bh[n][0]; bl[n][1] = b.y - bh[n][1];
+            } else {    // pre-rounded to TF32 by the packer
+                bh[n][0] = b.x; bh[n][1] = b.y; bl[n][0] = bl[n][1] = 0.f;
             }
+        }
+        float ah[NS][4], al[NS][4];
 #pragma unroll
-            for (int j = 0; j < SBC_MMA_SLOTS; j++) {
-                if (j < nslots) {
-                    float a[4];
-                    a[0] = bp[po0[j]];
-                    a[1] = bp[po1[j]];
-                    a[2] = bp[cg1 + po0[j]];
-                    a[3] = bp[cg1 + po1[j]];
-                    float ah[4], al[4];
-                    if (X3) {
+        for (int j = 0; j < NS; j++) {
+            float a[4];
+            sbc_mma_a_frag(asrc, off, po[j][0], po[j][1], a);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            ah[i] = sbc_dev_tf32_rz(a[i]);                 // a = ah + (a - ah) exactly
-                            al[i] = sbc_dev_tf32_rz(a[i] - ah[i]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) ah[i] = sbc_dev_tf32_rn(a[i]);
-                    }
-#pragma unroll
-                    for (int n = 0; n < SBC_MMA_NTW; n++) {
-                        if (n < ntw) {
-                            if (X3) {
-                                sbc_mma_tf32(acc[j][n], al, bh[n][0], bh[n][1]);   // small terms first
-                                sbc_mma_tf32(acc[j][n], ah, bl[n][0], bl[n][1]);
-                            }
-                            sbc_mma_tf32(acc[j][n], ah, bh[n][0], bh[n][1]);
-                        }
-                    }
+            for (int i = 0; i < 4; i++) {
+                if (X3) {
+                    ah[j][i] = __uint_as_float(__float_as_uint(a[i]) & 0xFFFFE000u);   // a = ah + al exactly
+                    al[j][i] = a[i] - ah[j][i];                                          // tensor core truncates al
+                } else {
+                    ah[j][i] = sbc_cvt_tf32(a[i]);
                 }
             }
         }
+        if (X3) {   // small terms first; term-major order keeps dependent MMAs NS*NN apart
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], al[j], bh[n][0], bh[n][1]);
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bl[n][0], bl[n][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
     }
+}
+
+// one pass of a warp over NS tiles (mt0, mt0 + mstride, ...; only the first `ntile` are real) x NN cout tiles
+template <bool X3, int NS, int NN>
+__device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
+                                               const float* wseg, const float* asrc, const float* bfrag, int bstride,
+                                               int mt0, int mstride, int ntile, int nt0, int lane) {
+    const int g = lane >> 2;
+    int po[NS][2];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const int mt = mt0 + (j < ntile ? j : 0) * mstride;
+        po[j][0] = sbc_mma_row_off(op, GS, mt, 0, g);
+        po[j][1] = sbc_mma_row_off(op, GS, mt, 0, g + 8);
+    }
+    float acc[NS][NN][4];
+#pragma unroll
+    for (int j = 0; j < NS; j++)
+#pragma unroll
+        for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
+    sbc_mma_pass<X3, NS, NN>(asrc, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, 0, op.S, acc);
+    const int P = op.oh * op.ow;
+#pragma unroll
+    for (int j = 0; j < NS; j++)
+        if (j < ntile) {   // stride-1 conv: source and destination geometry coincide, so do the pixel offsets
+            const int q0 = (mt0 + j * mstride) * 16 + g;
+            const int pd[2] = {q0 < P ? po[j][0] : -1, q0 + 8 < P ? po[j][1] : -1};
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0 + n, lane, acc[j][n]);
+        }
+}
+
+// ConvMeanPool: one output tile, the four pooling positions are the four slots
+template <bool X3, int NN>
+__device__ __forceinline__ void sbc_conv_pooled(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
+                                                const float* wseg, const float* asrc, const float* bfrag, int bstride,
+                                                int mt, int nt0, int s0, int s1, int lane, float (&c)[NN][4]) {
+    const int g = lane >> 2;
+    int po[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        po[j][0] = sbc_mma_row_off(op, GS, mt, j, g);
+        po[j][1] = sbc_mma_row_off(op, GS, mt, j, g + 8);
+    }
+    float acc[4][NN][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
+    sbc_mma_pass<X3, 4, NN>(asrc, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, s0, s1, acc);
+#pragma unroll
+    for (int n = 0; n < NN; n++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) c[n][i] = (acc[0][n][i] + acc[1][n][i]) + (acc[2][n][i] + acc[3][n][i]);
 }
 
 template <bool X3>
@@ -198,35 +226,38 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
                                              const float* wseg, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = SBC_NTHREADS / 32;
-    SbcMmaGeom M;
-    sbc_mma_geom(op, M);
-    float acc[SBC_MMA_SLOTS][SBC_MMA_NTW][4];
+    constexpr int E = 2;   // floats per lane per B fragment
+    const bool pool = (op.flags & SBC_F_POOL) != 0;
     // fresh outputs get their halo re-zeroed (the arena region may have held another tensor)
-    if (op.dst >= 0) sbc_zero_halo(arena + op.dst, GD, op.cout, tid, SBC_NTHREADS);
-    if (op.edst >= 0) sbc_zero_halo(arena + op.edst, GD, op.cout, tid, SBC_NTHREADS);
+    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, tid, SBC_NTHREADS);
+    if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, tid, SBC_NTHREADS);
+
+    const int MT = op.MT, NT = op.NT, S = op.S;
+    const float* asrc = arena + op.src + 2 * (lane & 3);
+    const int bstride = NT * 32 * E;
+    const float* bf0 = wseg + op.frag_rel + lane * E;
 
     if (op.ks > 1) {
-        // fewer (pixel tile, cout tile) units than warps: `ks` warps split the K steps of one unit and the
-        // partial accumulators are combined through shared memory
-        const int ks = op.ks, units = M.MT * M.NT;
-        const int u = warp / ks, kp = warp - u * ks;
-        const int mt = u / M.NT, nt = u - mt * M.NT;
+        // fewer (pixel tile, cout tile) units than warps: `ks` (a power of two) warps split the K steps of one
+        // unit and the partial accumulators are combined through shared memory
+        const int ks = op.ks, units = MT * NT;
+        const int lks = 31 - __clz(ks);
+        const int u = warp >> lks, kp = warp & (ks - 1);
+        const int mt = sbc_div(u, NT, sbc_ilog2(NT)), nt = u - mt * NT;
         float4* part = reinterpret_cast<float4*>(arena + op.scratch);
         if (u < units) {
-#pragma unroll
-            for (int j = 0; j < SBC_MMA_SLOTS; j++)
-#pragma unroll
-                for (int n = 0; n < SBC_MMA_NTW; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
-            sbc_mma_pass<X3>(op, M, GS, arena, wseg, mt, 0, M.nq, nt, 1, (M.S * kp) / ks, (M.S * (kp + 1)) / ks, lane,
-                             acc);
-            float4 c = make_float4(acc[0][0][0], acc[0][0][1], acc[0][0][2], acc[0][0][3]);
-            if (M.nq == 4) {
-#pragma unroll
-                for (int j = 1; j < 4; j++) {
-                    c.x += acc[j][0][0]; c.y += acc[j][0][1]; c.z += acc[j][0][2]; c.w += acc[j][0][3];
-                }
+            const int s0 = (S * kp) >> lks, s1 = (S * (kp + 1)) >> lks;
+            float c[1][4];
+            if (pool) {
+                sbc_conv_pooled<X3, 1>(op, GS, GD, arena, wseg, asrc, bf0 + nt * 32 * E, bstride, mt, nt, s0, s1, lane, c);
+            } else {
+                const int g = lane >> 2;
+                int po[1][2] = {{sbc_mma_row_off(op, GS, mt, 0, g), sbc_mma_row_off(op, GS, mt, 0, g + 8)}};
+                float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
+                sbc_mma_pass<X3, 1, 1>(asrc, po, reinterpret_cast<const int*>(wseg), bf0 + nt * 32 * E, bstride, s0, s1, acc);
+                c[0][0] = acc[0][0][0]; c[0][1] = acc[0][0][1]; c[0][2] = acc[0][0][2]; c[0][3] = acc[0][0][3];
             }
-            part[warp * 32 + lane] = c;
+            part[warp * 32 + lane] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
         }
         __syncthreads();
         if (u < units && kp == 0) {
@@ -235,44 +266,58 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
                 const float4 p = part[(warp + i) * 32 + lane];
                 c[0] += p.x; c[1] += p.y; c[2] += p.z; c[3] += p.w;
             }
-            sbc_mma_epilogue(op, GD, arena, wseg, mt, nt, lane, c);
+            int pd[2];
+            sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
+            sbc_mma_epilogue(op, GD, arena, wseg, pd, mt * 16 + (lane >> 2), nt, lane, c);
         }
         return;
     }
 
-    // enough pixel tiles for every warp: warp w owns tiles w, w+NW, ...; cout tiles are processed in pairs that
-    // share the gathered A fragments
-    const int tpp = SBC_MMA_SLOTS / M.nq;                    // tiles per pass
-    for (int mt0 = warp; mt0 < M.MT; mt0 += tpp * NW) {
-        int ntile = (M.MT - mt0 + NW - 1) / NW;
-        if (ntile > tpp) ntile = tpp;
-        for (int nt0 = 0; nt0 < M.NT; nt0 += SBC_MMA_NTW) {
-            const int ntw = (M.NT - nt0 < SBC_MMA_NTW) ? M.NT - nt0 : SBC_MMA_NTW;
-#pragma unroll
-            for (int j = 0; j < SBC_MMA_SLOTS; j++)
-#pragma unroll
-                for (int n = 0; n < SBC_MMA_NTW; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
-            sbc_mma_pass<X3>(op, M, GS, arena, wseg, mt0, NW, ntile * M.nq, nt0, ntw, 0, M.S, lane, acc);
-#pragma unroll
-            for (int n = 0; n < SBC_MMA_NTW; n++) {
-                if (n >= ntw) continue;
-                if (M.nq == 1) {
-#pragma unroll
-                    for (int j = 0; j < SBC_MMA_SLOTS; j++)
-                        if (j < ntile) sbc_mma_epilogue(op, GD, arena, wseg, mt0 + j * NW, nt0 + n, lane, acc[j][n]);
-                } else if (ntile > 0) {
-                    float c[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) c[i] = acc[0][n][i] + acc[1][n][i] + acc[2][n][i] + acc[3][n][i];
-                    sbc_mma_epilogue(op, GD, arena, wseg, mt0, nt0 + n, lane, c);
+    if (pool) {
+        for (int mt = warp; mt < MT; mt += NW) {
+            int pd[2];
+            sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
+            const int q0 = mt * 16 + (lane >> 2);
+            for (int nt0 = 0; nt0 < NT; nt0 += 2) {
+                if (NT - nt0 >= 2) {
+                    float c[2][4];
+                    sbc_conv_pooled<X3, 2>(op, GS, GD, arena, wseg, asrc, bf0 + nt0 * 32 * E, bstride, mt, nt0, 0, S, lane, c);
+                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0, lane, c[0]);
+                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0 + 1, lane, c[1]);
+                } else {
+                    float c[1][4];
+                    sbc_conv_pooled<X3, 1>(op, GS, GD, arena, wseg, asrc, bf0 + nt0 * 32 * E, bstride, mt, nt0, 0, S, lane, c);
+                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0, lane, c[0]);
                 }
+            }
+        }
+        return;
+    }
+
+    // enough pixel tiles for every warp: warp w owns tiles w, w+NW, ... (up to 4 per pass); cout tiles are
+    // processed in pairs that share the gathered A fragments
+    for (int mt0 = warp; mt0 < MT; mt0 += 4 * NW) {
+        int ntile = (MT - mt0 + NW - 1) / NW;
+        if (ntile > 4) ntile = 4;
+        for (int nt0 = 0; nt0 < NT; nt0 += 2) {
+            const float* bf = bf0 + nt0 * 32 * E;
+            const bool two = NT - nt0 >= 2;
+            if (ntile == 1) {
+                if (two) sbc_conv_tiles<X3, 1, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                else sbc_conv_tiles<X3, 1, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+            } else if (ntile == 2) {
+                if (two) sbc_conv_tiles<X3, 2, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                else sbc_conv_tiles<X3, 2, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+            } else {
+                if (two) sbc_conv_tiles<X3, 4, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                else sbc_conv_tiles<X3, 4, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// InstanceNorm++ + ELU: T threads per channel group, two statistics passes (warp shuffles + one
+// InstanceNorm++ + ELU: T threads per channel quad, two statistics passes (warp shuffles + one
 // shared-memory exchange each), then the fused normalise / affine / ELU pass.
 // scratch: red[2][NW] float4 | mu[C] | m2[C]
 // ---------------------------------------------------------------------------------------------
@@ -290,51 +335,60 @@ __device__ __forceinline__ SbcF4 sbc_warp_sum4(SbcF4 v) {
 __device__ __forceinline__ void sbc_norm_op(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg,
                                             int tid) {
     constexpr int NW = SBC_NTHREADS / 32;
-    const int C = op.cin, ncg = (C + 3) >> 2;
-    const int T = sbc_norm_T(op, SBC_NTHREADS), gpp = SBC_NTHREADS / T, wpg = T / 32;   // groups / pass, warps / group
+    const int C = op.cin, nq = C >> 2;
+    const int T = sbc_norm_T(op, SBC_NTHREADS), lT = 31 - __clz(T);
+    const int gpp = SBC_NTHREADS >> lT, wpg = T >> 5;   // quads / pass, warps / quad
+    const int npass = (nq + gpp - 1) / gpp;
     const int warp = tid >> 5, lane = tid & 31;
     SbcF4* red = reinterpret_cast<SbcF4*>(arena + op.scratch);
-    float* mu = arena + op.scratch + 2 * NW * 4;
-    float* m2s = mu + C;
+    SbcF4* mu4 = red + 2 * NW;
+    SbcF4* m24 = mu4 + nq;
     const float inv = 1.f / (float)(G.h * G.w);
-    const int s = tid % T;
-    for (int cg0 = 0; cg0 < ncg; cg0 += gpp) {
-        const int cg = cg0 + tid / T;
-        const bool active = cg < ncg;
-        SbcF4 z{0.f, 0.f, 0.f, 0.f};
-        SbcF4 sum = active ? sbc_norm_partial_sum(op, G, arena, cg, s, T) : z;
+    const int s = tid & (T - 1), w0 = (tid >> lT) * wpg;
+    const SbcF4 z{0.f, 0.f, 0.f, 0.f};
+    SbcF4 mean = z, m2 = z;
+    for (int pass = 0; pass < npass; pass++) {
+        const int q = pass * gpp + (tid >> lT);
+        const bool active = q < nq;
+        SbcF4 sum = active ? sbc_norm_partial_sum(op, G, arena, q, s, T) : z;
         sum = sbc_warp_sum4(sum);
         if (lane == 0) red[warp] = sum;
         __syncthreads();
-        SbcF4 mean = z;
-        const int w0 = (tid / T) * wpg;
+        mean = z;
         for (int i = 0; i < wpg; i++) { const SbcF4 v = red[w0 + i]; mean.x += v.x; mean.y += v.y; mean.z += v.z; mean.w += v.w; }
         mean.x *= inv; mean.y *= inv; mean.z *= inv; mean.w *= inv;
-        SbcF4 m2 = active ? sbc_norm_partial_m2(op, G, arena, cg, s, T, mean) : z;
-        m2 = sbc_warp_sum4(m2);
-        if (lane == 0) red[NW + warp] = m2;
+        if (active && s == 0) mu4[q] = mean;
+        SbcF4 part = active ? sbc_norm_partial_m2(op, G, arena, q, s, T, mean) : z;
+        part = sbc_warp_sum4(part);
+        if (lane == 0) red[NW + warp] = part;
         __syncthreads();
-        if (active && s == 0) {
-            SbcF4 tot = z;
-            for (int i = 0; i < wpg; i++) { const SbcF4 v = red[NW + w0 + i]; tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w; }
-            const float mm[4] = {mean.x, mean.y, mean.z, mean.w}, tt[4] = {tot.x, tot.y, tot.z, tot.w};
-            for (int j = 0; j < 4; j++)
-                if (4 * cg + j < C) { mu[4 * cg + j] = mm[j]; m2s[4 * cg + j] = tt[j]; }
-        }
-        __syncthreads();
-    }
-    for (int cg0 = 0; cg0 < ncg; cg0 += gpp) {
-        const int cg = cg0 + tid / T;
-        if (cg < ncg) {
-            SbcF4 mean, m2;
-            mean.x = mu[4 * cg]; m2.x = m2s[4 * cg];
-            mean.y = (4 * cg + 1 < C) ? mu[4 * cg + 1] : 0.f; m2.y = (4 * cg + 1 < C) ? m2s[4 * cg + 1] : 0.f;
-            mean.z = (4 * cg + 2 < C) ? mu[4 * cg + 2] : 0.f; m2.z = (4 * cg + 2 < C) ? m2s[4 * cg + 2] : 0.f;
-            mean.w = (4 * cg + 3 < C) ? mu[4 * cg + 3] : 0.f; m2.w = (4 * cg + 3 < C) ? m2s[4 * cg + 3] : 0.f;
-            sbc_norm_apply(op, G, arena, wseg, mu, cg, s, T, mean, m2);
+        m2 = z;
+        for (int i = 0; i < wpg; i++) { const SbcF4 v = red[NW + w0 + i]; m2.x += v.x; m2.y += v.y; m2.z += v.z; m2.w += v.w; }
+        if (npass > 1) {   // several passes: statistics go through shared memory, `red` is reused
+            if (active && s == 0) m24[q] = m2;
+            __syncthreads();
         }
     }
-    sbc_zero_halo(arena + op.dst, G, C, tid, SBC_NTHREADS);
+    for (int pass = 0; pass < npass; pass++) {
+        const int q = pass * gpp + (tid >> lT);
+        if (q < nq) {
+            if (npass > 1) { mean = mu4[q]; m2 = m24[q]; }
+            sbc_norm_apply(op, G, arena, wseg, reinterpret_cast<const float*>(mu4), q, s, T, mean, m2);
+        }
+    }
+    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, C, tid, SBC_NTHREADS);
+}
+
+// block-wide sum of one float per thread; the total is returned to thread 0 only.  red: NW floats.
+__device__ __forceinline__ float sbc_block_sum(float v, float* red, int tid) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    if (tid == 0)
+        for (int i = 0; i < SBC_NTHREADS / 32; i++) s += red[i];
+    return s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,6 +412,10 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
 
     __shared__ float s_hnorm;
     __shared__ SbcStepScalars s_sc;
+    __shared__ float s_red[SBC_NTHREADS / 32];
+    // op records are prefetched global -> shared one op ahead (warp 0, one word per lane), so that decoding an
+    // op never waits on global memory
+    __shared__ __align__(16) SbcOp s_ops[2];
 
     // parameter segments are staged into the (shared-memory) arena with cp.async.bulk one op ahead
     const bool stage = SMEM_ARENA && L.stage_weights != 0;
@@ -366,12 +424,13 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         sbc_mbar_init(&bars[1], 1);
         sbc_fence_barrier_init();
     }
+    if (tid < 32) reinterpret_cast<int*>(&s_ops[0])[tid] = reinterpret_cast<const int*>(L.ops)[tid];
     __syncthreads();
 
     const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
-    const SbcGeo& G0 = L.geo[0];
-    float* ax = arena + L.in_off;             // x: 2-channel tensor (re, im) of geometry 0
+    float* ax = arena + L.in_off;             // x: compact (re, im) pairs [Nt*Nr]
     uint32_t wcount = 0;                      // parameter segments consumed so far (same in every thread)
+    uint32_t opc = 0;                         // ops executed so far (parity selects the op record buffer)
 
     if (stage && tid == 0 && (int)blockIdx.x < L.B && L.first_w >= 0) {
         const SbcOp& o = L.ops[L.first_w];
@@ -385,34 +444,24 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         const bool last_sample = (b + (int)gridDim.x >= L.B);
         // ---------------- load the sample state into the arena ----------------
         if (L.mode == 1) {
-            const float* X = L.X + (size_t)b * ne * 2;
-            for (int e = tid; e < ne; e += SBC_NTHREADS) {
-                const float2 v = reinterpret_cast<const float2*>(X)[e];
-                const int t = e / Nr, r = e - t * Nr;
-                *sbc_px(ax, G0, 0, t, r) = SbcF4{v.x, v.y, 0.f, 0.f};
-            }
+            const float2* X = reinterpret_cast<const float2*>(L.X) + (size_t)b * ne;
+            for (int e = tid; e < ne; e += SBC_NTHREADS) reinterpret_cast<float2*>(ax)[e] = X[e];
             if (L.Hor) {   // ||H||_F^2 once per sample (test_score.py:169)
-                const float* Hc = L.Hor + (size_t)b * ne * 2;
+                const float2* Hc = reinterpret_cast<const float2*>(L.Hor) + (size_t)b * ne;
                 float part = 0.f;
                 for (int e = tid; e < ne; e += SBC_NTHREADS) {
-                    const float2 v = reinterpret_cast<const float2*>(Hc)[e];
+                    const float2 v = Hc[e];
                     part += v.x * v.x + v.y * v.y;
                 }
-                float* red = arena + L.post_off + 2 * ne;
-                red[tid] = part;
-                __syncthreads();
-                if (tid == 0) {
-                    float sum = 0.f;
-                    for (int i = 0; i < SBC_NTHREADS; i++) sum += red[i];
-                    s_hnorm = sum;
-                }
+                const float tot = sbc_block_sum(part, s_red, tid);
+                if (tid == 0) s_hnorm = tot;
             }
         } else {
             const float* fx = L.fx + (size_t)b * L.fxs[0];
             for (int e = tid; e < ne; e += SBC_NTHREADS) {
                 const int t = e / Nr, r = e - t * Nr;
                 const float* q = fx + t * L.fxs[2] + r * L.fxs[3];
-                *sbc_px(ax, G0, 0, t, r) = SbcF4{q[0], q[L.fxs[1]], 0.f, 0.f};
+                reinterpret_cast<float2*>(ax)[e] = make_float2(q[0], q[L.fxs[1]]);
             }
         }
         __syncthreads();
@@ -435,20 +484,24 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
 
             // ---------------- the network: walk the layer program ----------------
             const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && b == 0 && gs == 0 && tid == 0;
-            for (int i = 0; i < L.n_ops; i++) {
+            for (int i = 0; i < L.n_ops; i++, opc++) {
                 if (L.debug_stop >= 0 && i == L.debug_stop) break;
                 if (do_prof) L.prof[i] = clock64();
-                const SbcOp op = L.ops[i];
+                const SbcOp op = s_ops[opc & 1u];
+                // prefetch the next op record (wraps into the next forward)
+                int nxt = 0;
+                if (tid < 32) {
+                    const int j = (i + 1 < L.n_ops) ? i + 1 : 0;
+                    nxt = reinterpret_cast<const int*>(L.ops + j)[tid];
+                }
                 const float* wseg = L.blob + op.w_off;
                 if (op.w_len > 0 && stage) {
                     const uint32_t slot = wcount & 1u;
                     if (tid == 0) {   // prefetch the next parameter segment into its staging buffer
-                        int j = op.pad0;                                        // next op with parameters
-                        if (j < 0 && !(last_step && last_sample)) j = L.first_w;   // wraps into the next forward
-                        if (j >= 0) {
-                            const SbcOp& o = L.ops[j];
-                            sbc_mbar_expect_tx(&bars[slot ^ 1u], (uint32_t)o.w_len * 4u);
-                            sbc_bulk_g2s(arena + o.wbuf, L.blob + o.w_off, (uint32_t)o.w_len * 4u, &bars[slot ^ 1u]);
+                        // next op with parameters; the last one wraps into the next forward
+                        if (op.next_w >= 0 || !(last_step && last_sample)) {
+                            sbc_mbar_expect_tx(&bars[slot ^ 1u], (uint32_t)op.nw_len * 4u);
+                            sbc_bulk_g2s(arena + op.nw_buf, L.blob + op.nw_off, (uint32_t)op.nw_len * 4u, &bars[slot ^ 1u]);
                         }
                     }
                     sbc_mbar_wait(&bars[slot], (wcount >> 1) & 1u);
@@ -480,6 +533,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     default:
                         break;
                 }
+                if (tid < 32) reinterpret_cast<int*>(&s_ops[(opc + 1u) & 1u])[tid] = nxt;
                 __syncthreads();
             }
             if (L.debug_stop >= 0) {   // debugging aid: dump the arena of sample 0 and stop
@@ -489,7 +543,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             }
 
             if (do_prof) L.prof[L.n_ops] = clock64();
-            const float* net = arena + L.out_off;
+            const float* net = arena + L.out_off;   // compact (re, im) pairs
             if (L.mode == 0) {
                 // score = net / sigmas[y]   (ncsnv2.py:295-298)
                 long long lab = L.labels[b];
@@ -498,8 +552,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 const float sg = L.sigmas[lab];
                 float* o = L.fout + (size_t)b * L.channels * ne;
                 for (int e = tid; e < ne; e += SBC_NTHREADS) {
-                    const int t = e / Nr, r = e - t * Nr;
-                    const SbcF4 v = *sbc_px(net, G0, 0, t, r);
+                    const float2 v = reinterpret_cast<const float2*>(net)[e];
                     o[e] = v.x / sg;
                     o[ne + e] = v.y / sg;
                 }
@@ -510,21 +563,15 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 const float* Hc = L.Hor ? L.Hor + (size_t)b * ne * 2 : nullptr;
                 const float* en = L.ext_noise ? L.ext_noise + ((size_t)gs * L.B + b) * ne * 2 : nullptr;
                 float* res = arena + L.post_off;
-                float* red = res + 2 * ne;
-                sbc_dc_residual(ax, G0, res, Pm, Ym, Nt, Nr, L.Np, tid, SBC_NTHREADS);
+                sbc_dc_residual(ax, res, Pm, Ym, Nt, Nr, L.Np, tid, SBC_NTHREADS);
                 __syncthreads();
                 const unsigned long long sid = L.sample_ids ? L.sample_ids[b] : (unsigned long long)b;
                 const uint32_t gstep = (uint32_t)(lvl * L.steps_each + gs % L.steps_each);
-                const float part = sbc_langevin_update(ax, net, G0, res, Pm, Hc, en, s_sc, L.seed, sid, gstep, Nt, Nr,
+                const float part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc, L.seed, sid, gstep, Nt, Nr,
                                                        L.Np, tid, SBC_NTHREADS);
                 if (L.nmse_log && Hc) {
-                    red[tid] = part;
-                    __syncthreads();
-                    if (tid == 0) {
-                        float sum = 0.f;
-                        for (int i = 0; i < SBC_NTHREADS; i++) sum += red[i];
-                        L.nmse_log[(size_t)gs * L.B + b] = sum / s_hnorm;
-                    }
+                    const float tot = sbc_block_sum(part, s_red, tid);
+                    if (tid == 0) L.nmse_log[(size_t)gs * L.B + b] = tot / s_hnorm;
                 }
             }
             __syncthreads();
@@ -532,12 +579,8 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         }
 
         if (L.mode == 1) {   // write the final estimate back (interleaved complex64)
-            float* X = L.X + (size_t)b * ne * 2;
-            for (int e = tid; e < ne; e += SBC_NTHREADS) {
-                const int t = e / Nr, r = e - t * Nr;
-                const SbcF4 v = *sbc_px(ax, G0, 0, t, r);
-                reinterpret_cast<float2*>(X)[e] = make_float2(v.x, v.y);
-            }
+            float2* X = reinterpret_cast<float2*>(L.X) + (size_t)b * ne;
+            for (int e = tid; e < ne; e += SBC_NTHREADS) X[e] = reinterpret_cast<const float2*>(ax)[e];
         }
         __syncthreads();
     }

@@ -1,43 +1,23 @@
-// sbc_mma.h -- per-lane pieces of the tensor-core convolution (SBC_OP_CONV_MMA): geometry, the
-// A-fragment gather (implicit im2col straight from the arena), and the fused epilogue.  Host/device
-// portable like sbc_ops.h so that tests/emu/emu.cpp can emulate a warp lane by lane.
+// sbc_mma.h -- per-lane pieces of the tensor-core convolution (SBC_OP_CONV_MMA): the A-fragment gather
+// (implicit im2col straight from the arena) and the fused epilogue.  Host/device portable like sbc_ops.h so
+// that tests/emu/emu.cpp can emulate a warp lane by lane.
 //
-// Implicit GEMM per (live tap, chunk of 8 input channels):
+// Implicit GEMM per K step s = (live tap, chunk of 8 input channels):
 //     D[16 output pixels, 8 couts] += A[16 pixels, 8 cins] * B[8 cins, 8 couts]
-// with the fragment layout of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32
-//     lane = 4*g + t :  A: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4)      (row = pixel, col = cin)
-//                       B: b0=(k=t,n=g) b1=(k=t+4,n=g)      (packed by program.py: hi0,hi1[,lo0,lo1] per lane)
-//                       C: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)    (row = pixel, col = cout)
-// A tile is 16 consecutive output pixels in row-major order.  Thanks to the zero halo of the layout
-// (SbcGeo) a tap is a constant address offset and the gather has no bounds checks; 8 consecutive pixels x
-// 4 channels are 128 contiguous bytes, so each of the four loads of a fragment is one conflict-free
-// shared-memory wavefront.  ConvMeanPool (SBC_F_POOL) runs four accumulations per tile -- one per
-// position of the 2x2 pooling window, input pixel (2Y+qy, 2X+qx) -- summed in the epilogue (the packed
-// weights carry the 1/4).
+// with the fragment layout of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 and the K index permuted so
+// that the two K columns a lane owns are ADJACENT channels (MMA column t <-> channel 2t, column t+4 <->
+// channel 2t+1; the same permutation is applied to the packed weights, so the contraction is unchanged):
+//     lane = 4*g + t :  A: (a0,a2) = channels (2t, 2t+1) of pixel row g,  (a1,a3) = same of row g+8
+//                       B: b0 = W[cout g][cin 2t], b1 = W[cout g][cin 2t+1]    (packed by program.py)
+//                       C: (c0,c1) = couts (2t, 2t+1) of row g, (c2,c3) = same of row g+8
+// One pixel of one plane is 8 channels = 32 contiguous bytes, so an A fragment is two 8-byte loads per lane
+// and the 8 pixel rows x 4 lanes of a quarter-warp cover 256 contiguous bytes when the pixels are contiguous
+// (conflict-free).  Thanks to the zero halo (SbcGeo) a K step is a constant address offset -- read from the
+// per-op table at the head of the parameter segment (program.py) -- and the gather has no bounds checks.
+// ConvMeanPool (SBC_F_POOL) runs four accumulations per tile, one per position of the 2x2 pooling window
+// (input pixel (2Y+qy, 2X+qx)), summed before the epilogue (the packed weights carry the 1/4).
 #pragma once
 #include "sbc_ops.h"
-
-struct SbcMmaGeom {
-    int P;        // output pixels
-    int MT, NT;   // 16-pixel tiles, 8-cout tiles
-    int KC;       // chunks of 8 input channels
-    int ntaps, S; // live taps, K steps = ntaps * KC
-    int stride;   // 1, or 2 for pooled convs
-    int nq;       // accumulations per tile (1, or 4 for pooled convs)
-};
-
-SBC_HD void sbc_mma_geom(const SbcOp& op, SbcMmaGeom& M) {
-    M.stride = (op.flags & SBC_F_POOL) ? 2 : 1;
-    M.nq = (op.flags & SBC_F_POOL) ? 4 : 1;
-    M.P = op.oh * op.ow;
-    M.MT = (M.P + 15) >> 4;
-    M.NT = (op.cout + 7) >> 3;
-    M.KC = (op.cin + 7) >> 3;
-    int n = 0;
-    for (int tap = 0; tap < op.ksize * op.ksize; tap++) n += (op.tapmask >> tap) & 1;
-    M.ntaps = n;
-    M.S = n * M.KC;
-}
 
 // fp32 -> TF32 operand, round to nearest (ties away): (bits + 0x1000) & ~0x1fff   [finite inputs]
 SBC_HD float sbc_tf32_rn(float x) {
@@ -54,60 +34,65 @@ SBC_HD float sbc_tf32_rz(float x) {
     return v.f;
 }
 
-// float offset (relative to channel-group 0 of the source tensor, lane-in-group 0) of the input pixel that
-// tile row m (0..15) of tile mt reads for pooling position `quad`, before the tap offset.  Rows past the
-// last output pixel are clamped onto it (their results are discarded by the epilogue).
-SBC_HD int sbc_mma_row_off(const SbcOp& op, const SbcMmaGeom& M, const SbcGeo& GS, int mt, int quad, int m) {
-    int q = mt * 16 + m;
-    if (q >= M.P) q = M.P - 1;
-    const int Y = q / op.ow, X = q - Y * op.ow;
-    const int iy = Y * M.stride + (quad >> 1), ix = X * M.stride + (quad & 1);
-    return (GS.org + iy * GS.wp + ix) * 4;
-}
-
-// A fragment of one lane for tap offset (dy, dx) and input-channel chunk kc; po0 / po1 from sbc_mma_row_off
-// for tile rows g and g + 8
-SBC_HD void sbc_mma_a_frag(const SbcOp& op, const SbcGeo& GS, const float* arena, int po0, int po1, int dy, int dx,
-                           int kc, int lane, float (&a)[4]) {
-    const int t = lane & 3;
-    const float* bp = arena + op.src + (2 * kc * GS.pps + dy * GS.wp + dx) * 4 + t;
-    const int cg1 = GS.pps * 4;
-    a[0] = bp[po0];
-    a[1] = bp[po1];
-    a[2] = bp[cg1 + po0];
-    a[3] = bp[cg1 + po1];
-}
-
-// Epilogue of one lane for tile (mt, nt):  v = c + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v)
-// (c0,c1) and (c2,c3) are two adjacent output channels of one pixel: 8-byte stores.
-SBC_HD void sbc_mma_epilogue(const SbcOp& op, const SbcGeo& GD, float* arena, const float* wseg, int mt, int nt,
-                             int lane, const float (&c)[4]) {
-    const int g = lane >> 2, t = lane & 3;
+// float offset (relative to plane 0 of the source tensor) of the input pixel that tile row m (0..15) of tile
+// mt reads for pooling position `quad`, before the K-step offset.  Rows past the last output pixel are
+// clamped onto it (their results are discarded by the epilogue).
+SBC_HD int sbc_mma_row_off(const SbcOp& op, const SbcGeo& GS, int mt, int quad, int m) {
     const int P = op.oh * op.ow;
+    int q = mt * 16 + m;
+    if (q >= P) q = P - 1;
+    const int Y = sbc_div(q, op.ow, op.low), X = q - Y * op.ow;
+    const int sh = (op.flags & SBC_F_POOL) ? 1 : 0;
+    const int iy = (Y << sh) + (quad >> 1), ix = (X << sh) + (quad & 1);
+    return (GS.org + iy * GS.wp + ix) * 8;
+}
+
+// A fragment of one lane: `asrc` = arena + op.src + 2*t, `off` = K-step offset from the op's table
+SBC_HD void sbc_mma_a_frag(const float* asrc, int off, int po0, int po1, float (&a)[4]) {
+    const SbcF2 v0 = *reinterpret_cast<const SbcF2*>(asrc + off + po0);
+    const SbcF2 v1 = *reinterpret_cast<const SbcF2*>(asrc + off + po1);
+    a[0] = v0.x; a[1] = v1.x; a[2] = v0.y; a[3] = v1.y;
+}
+
+// Epilogue of one lane for cout tile nt of one pixel tile:  v = c + bias;  dst <- v;  acc <- (v += acc);
+// edst <- ELU(v).  pd[half] = float offset (org + Y*wp + X) * 8 of the output pixel of tile row g + 8*half in
+// the destination geometry, or -1 when that row is past the last pixel; q0 = index of the pixel of row g.
+// (c0,c1) and (c2,c3) are two adjacent output channels of one pixel: 8-byte accesses.  cout is even.
+SBC_HD void sbc_mma_epilogue(const SbcOp& op, const SbcGeo& GD, float* arena, const float* wseg, const int (&pd)[2],
+                             int q0, int nt, int lane, const float (&c)[4]) {
+    const int t = lane & 3;
     const int co = nt * 8 + 2 * t;
     if (co >= op.cout) return;
-    const bool two = co + 1 < op.cout;
-    const float b0 = (op.b_rel >= 0) ? wseg[op.b_rel + co] : 0.f;
-    const float b1 = (op.b_rel >= 0 && two) ? wseg[op.b_rel + co + 1] : 0.f;
+    float b0 = 0.f, b1 = 0.f;
+    if (op.b_rel >= 0) { b0 = wseg[op.b_rel + co]; b1 = wseg[op.b_rel + co + 1]; }
+    const int cofs = (co >> 3) * GD.pps * 8 + (co & 7);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const int q = mt * 16 + g + half * 8;
-        if (q >= P) continue;
-        const int Y = q / op.ow, X = q - Y * op.ow;
-        const int idx = ((co >> 2) * GD.pps + GD.org + Y * GD.wp + X) * 4 + (co & 3);
-        float v0 = c[2 * half] + b0, v1 = c[2 * half + 1] + b1;
-        if (op.dst >= 0) {
-            arena[op.dst + idx] = v0;
-            if (two) arena[op.dst + idx + 1] = v1;
+        if (pd[half] < 0) continue;
+        SbcF2 v{c[2 * half] + b0, c[2 * half + 1] + b1};
+        if (op.flags & SBC_F_COMPACT) {   // network output: couts (0,1) = (re, im) of element q
+            reinterpret_cast<SbcF2*>(arena + op.dst)[q0 + 8 * half] = v;
+            continue;
         }
+        const int idx = pd[half] + cofs;
+        if (op.dst >= 0) *reinterpret_cast<SbcF2*>(arena + op.dst + idx) = v;
         if (op.acc >= 0) {
-            v0 += arena[op.acc + idx];
-            arena[op.acc + idx] = v0;
-            if (two) { v1 += arena[op.acc + idx + 1]; arena[op.acc + idx + 1] = v1; }
+            SbcF2* ap = reinterpret_cast<SbcF2*>(arena + op.acc + idx);
+            const SbcF2 o = *ap;
+            v.x += o.x; v.y += o.y;
+            *ap = v;
         }
-        if (op.edst >= 0) {
-            arena[op.edst + idx] = sbc_elu(v0);
-            if (two) arena[op.edst + idx + 1] = sbc_elu(v1);
-        }
+        if (op.edst >= 0) *reinterpret_cast<SbcF2*>(arena + op.edst + idx) = SbcF2{sbc_elu(v.x), sbc_elu(v.y)};
+    }
+}
+// destination pixel offsets of one lane for tile mt (see sbc_mma_epilogue)
+SBC_HD void sbc_mma_dst_off(const SbcOp& op, const SbcGeo& GD, int mt, int g, int (&pd)[2]) {
+    const int P = op.oh * op.ow;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int q = mt * 16 + g + 8 * half;
+        if (q >= P) { pd[half] = -1; continue; }
+        const int Y = sbc_div(q, op.ow, op.low), X = q - Y * op.ow;
+        pd[half] = (GD.org + Y * GD.wp + X) * 8;
     }
 }

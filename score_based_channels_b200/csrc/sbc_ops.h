@@ -3,9 +3,15 @@
 // intrinsics, so the same source is compiled by nvcc for the kernel (sbc_kernel.cuh) and by g++ for the
 // CPU thread-emulation harness (tests/emu/emu.cpp) that checks indexing before any GPU time is spent.
 //
-// Layout: see SbcGeo (sbc_program.h): channel-interleaved by 4 (one float4 = 4 channels of a pixel),
-// zero halo.  Every op that writes a tensor writes the interior only and re-zeroes the halo of its
-// fresh outputs (sbc_zero_halo), because arena regions are recycled between tensors.
+// Layout: see SbcGeo (sbc_program.h): channel-interleaved by 8 (one pixel of one plane = 8 channels = two
+// float4 "quads"), zero halo.  Every op that writes a tensor writes the interior only; because arena regions
+// are recycled between tensors, the halo of a fresh output is re-zeroed (sbc_zero_halo) whenever the offline
+// planner cannot prove that it is still zero (flags SBC_F_ZH_DST / SBC_F_ZH_EDST, program.py:_halo_analysis).  The sampler
+// state x and the raw network output are kept *compact*: interleaved (re, im) pairs [Nt*Nr], exactly the
+// complex64 layout of `current` in reference test_score.py:126.
+//
+// The kernel is instruction-issue bound (profiles/): index arithmetic uses shifts whenever the row width is a
+// power of two (SbcGeo.lw >= 0) and falls back to a division otherwise.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -21,9 +27,12 @@
 struct alignas(16) SbcF4 {
     float x, y, z, w;
 };
+struct alignas(8) SbcF2 {
+    float x, y;
+};
 
 // nn.ELU(alpha=1)  (reference ncsnv2/models/layers.py:13).  Device: exp via MUFU.EX2 (absolute error
-// ~1e-7, far inside the parity tolerance); host emulation: expm1f.
+// ~1e-7 = one ulp of the 1.0 that is subtracted, i.e. fp32-level); host emulation: expm1f.
 SBC_HD float sbc_elu(float v) {
 #if defined(__CUDA_ARCH__)
     return v > 0.f ? v : __expf(v) - 1.f;
@@ -33,187 +42,231 @@ SBC_HD float sbc_elu(float v) {
 }
 SBC_HD SbcF4 sbc_elu4(SbcF4 v) { return SbcF4{sbc_elu(v.x), sbc_elu(v.y), sbc_elu(v.z), sbc_elu(v.w)}; }
 
-SBC_HD SbcF4* sbc_px(float* base, const SbcGeo& G, int cg, int y, int x) {
-    return reinterpret_cast<SbcF4*>(base) + (cg * G.pps + G.org + y * G.wp + x);
+// i / d and i % d with d = 2^ld when ld >= 0
+SBC_HD int sbc_div(int i, int d, int ld) { return ld >= 0 ? (i >> ld) : (i / d); }
+SBC_HD int sbc_ilog2(int v) {   // log2(v) if v is a power of two, else -1
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
 }
-SBC_HD const SbcF4* sbc_px(const float* base, const SbcGeo& G, int cg, int y, int x) {
-    return reinterpret_cast<const SbcF4*>(base) + (cg * G.pps + G.org + y * G.wp + x);
+// padded pixel index of interior pixel i = y * w + x
+SBC_HD int sbc_pix(const SbcGeo& G, int i) {
+    const int y = sbc_div(i, G.w, G.lw), x = i - y * G.w;
+    return G.org + y * G.wp + x;
+}
+// visit the interior pixels s, s+T, s+2T, ... (T a power of two): f(padded pixel index).  When the row width is
+// a power of two <= T the walk is one column with a constant address step (no per-pixel index arithmetic).
+template <class F>
+SBC_HD void sbc_for_pixels(const SbcGeo& G, int s, int T, F&& f) {
+    if (G.lw >= 0 && T >= G.w) {
+        const int dy = T >> G.lw, ps = dy * G.wp;
+        int p = G.org + (s >> G.lw) * G.wp + (s & (G.w - 1));
+        for (int y = s >> G.lw; y < G.h; y += dy, p += ps) f(p);
+    } else {
+        const int HW = G.h * G.w;
+        for (int i = s; i < HW; i += T) f(sbc_pix(G, i));
+    }
+}
+// 1 / sqrt(x): MUFU.RSQ on the device (2 ulp), exact division on the host emulation
+SBC_HD float sbc_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.f / sqrtf(x);
+#endif
+}
+// float4 quad q (channels 4q .. 4q+3) of padded pixel p
+SBC_HD SbcF4* sbc_q4(float* base, const SbcGeo& G, int q, int p) {
+    return reinterpret_cast<SbcF4*>(base + ((size_t)((q >> 1) * G.pps + p) * 8 + (q & 1) * 4));
+}
+SBC_HD const SbcF4* sbc_q4(const float* base, const SbcGeo& G, int q, int p) {
+    return reinterpret_cast<const SbcF4*>(base + ((size_t)((q >> 1) * G.pps + p) * 8 + (q & 1) * 4));
 }
 
-// zero the halo cells of a tensor with `c` channels (cg = ceil(c/4) channel groups)
+// zero the halo cells of a tensor with `c` channels: one item = one padded row of one plane
 SBC_HD void sbc_zero_halo(float* t, const SbcGeo& G, int c, int tid, int nthr) {
-    const int ncg = (c + 3) >> 2;
+    const int np = (c + 7) >> 3;
     const int rows = G.h + 2 * G.hy;
-    const int top = G.hy * G.wp;                  // cells in the top (and bottom) band
-    const int side = 2 * G.hx;                    // halo cells per interior row
-    const int per = 2 * top + G.h * side;
     const SbcF4 z{0.f, 0.f, 0.f, 0.f};
-    for (int i = tid; i < ncg * per; i += nthr) {
-        const int cg = i / per;
-        int r = i - cg * per;
-        int cell;
-        if (r < top) cell = r;
-        else if (r < 2 * top) cell = (rows - G.hy) * G.wp + (r - top);
-        else {
-            r -= 2 * top;
-            const int row = r / side, k = r - row * side;
-            cell = (G.hy + row) * G.wp + (k < G.hx ? k : G.w + k);
+    for (int i = tid; i < np * rows; i += nthr) {
+        const int pl = i / rows, row = i - pl * rows;
+        SbcF4* r = reinterpret_cast<SbcF4*>(t + (size_t)(pl * G.pps + row * G.wp) * 8);
+        if (row < G.hy || row >= G.hy + G.h) {
+            for (int k = 0; k < 2 * G.wp; k++) r[k] = z;
+        } else {
+            for (int k = 0; k < 2 * G.hx; k++) { r[k] = z; r[2 * (G.hx + G.w) + k] = z; }
         }
-        reinterpret_cast<SbcF4*>(t)[cg * G.pps + cell] = z;
     }
 }
 
 // ----------------------------------------------------------------------------------------------
-// InstanceNorm2dPlus + ELU (reference normalization.py:163-176).  One float4 lane-item covers the 4
-// channels of a channel group; thread (cg, s) owns pixels s, s+T, s+2T, ... of channel group cg
-// (T = nthr / ncg threads per group).  Statistics are two-pass; the per-thread partials below are
-// combined across the T threads by shuffles + a shared-memory exchange on the device and by a plain
-// loop in the emulation.
+// InstanceNorm2dPlus + ELU (reference normalization.py:163-176).  One float4 item covers the 4 channels of a
+// quad; thread (q, s) owns pixels s, s+T, s+2T, ... of quad q (T = threads per quad, a power of two >= 32 so
+// that warps never straddle quads).  Statistics are two-pass; the per-thread partials below are combined
+// across the T threads by shuffles + a shared-memory exchange on the device and by a plain loop in the
+// emulation.  C must be a multiple of 8.
 // ----------------------------------------------------------------------------------------------
 SBC_HD int sbc_norm_T(const SbcOp& op, int nthr) {
-    const int ncg = (op.cin + 3) >> 2;
-    int T = nthr / ncg;
-    int p = 32;                       // a power of two >= 32 so that warps never straddle channel groups
+    const int nq = op.cin >> 2;
+    int T = nthr / nq;
+    int p = 32;
     while (p * 2 <= T) p *= 2;
     return p;
 }
-SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float* arena, int cg, int s, int T) {
+SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float* arena, int q, int s, int T) {
     SbcF4 a{0.f, 0.f, 0.f, 0.f};
-    const int HW = G.h * G.w;
-#pragma unroll 4
-    for (int i = s; i < HW; i += T) {
-        const int y = i / G.w, x = i - y * G.w;
-        const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
+    const float* src = arena + op.src + (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    sbc_for_pixels(G, s, T, [&](int p) {
+        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 8);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
+    });
     return a;
 }
-SBC_HD SbcF4 sbc_norm_partial_m2(const SbcOp& op, const SbcGeo& G, const float* arena, int cg, int s, int T,
+SBC_HD SbcF4 sbc_norm_partial_m2(const SbcOp& op, const SbcGeo& G, const float* arena, int q, int s, int T,
                                  SbcF4 mean) {
     SbcF4 a{0.f, 0.f, 0.f, 0.f};
-    const int HW = G.h * G.w;
-#pragma unroll 4
-    for (int i = s; i < HW; i += T) {
-        const int y = i / G.w, x = i - y * G.w;
-        const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
+    const float* src = arena + op.src + (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    sbc_for_pixels(G, s, T, [&](int p) {
+        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 8);
         const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
         a.x = fmaf(dx, dx, a.x); a.y = fmaf(dy, dy, a.y); a.z = fmaf(dz, dz, a.z); a.w = fmaf(dw, dw, a.w);
-    }
+    });
     return a;
 }
-// `mu` [C] per-channel means (any addressable memory), mean4 / m2_4: this thread's channel-group statistics
-SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg, const float* mu, int cg,
+// `mu` [C] per-channel means (16-byte aligned); mean4 / m2_4: the statistics of this thread's quad
+SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg, const float* mu, int q,
                            int s, int T, SbcF4 mean4, SbcF4 m2_4) {
-    const int C = op.cin, HW = G.h * G.w;
+    const int C = op.cin, HW = G.h * G.w, nq = C >> 2;
     // cross-channel statistics of the per-channel means: torch.mean / torch.var (unbiased) over C
+    const SbcF4* mu4 = reinterpret_cast<const SbcF4*>(mu);
     float m = 0.f;
-    for (int c = 0; c < C; c++) m += mu[c];
-    m /= (float)C;
+    for (int k = 0; k < nq; k++) { const SbcF4 u = mu4[k]; m += (u.x + u.y) + (u.z + u.w); }
+    m *= 1.f / (float)C;
     float v = 0.f;
-    for (int c = 0; c < C; c++) { const float d = mu[c] - m; v = fmaf(d, d, v); }
-    v /= (float)(C - 1);
-    const float rv = 1.f / sqrtf(v + 1e-5f);
-    const float *alpha = wseg + 4 * cg, *gamma = wseg + C + 4 * cg, *beta = wseg + 2 * C + 4 * cg;
+    for (int k = 0; k < nq; k++) {
+        const SbcF4 u = mu4[k];
+        const float d0 = u.x - m, d1 = u.y - m, d2 = u.z - m, d3 = u.w - m;
+        v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); v = fmaf(d2, d2, v); v = fmaf(d3, d3, v);
+    }
+    v *= 1.f / (float)(C - 1);
+    const float rv = sbc_rsqrt(v + 1e-5f);
+    const SbcF4 al = *reinterpret_cast<const SbcF4*>(wseg + 4 * q);
+    const SbcF4 ga = *reinterpret_cast<const SbcF4*>(wseg + C + 4 * q);
+    const SbcF4 be = *reinterpret_cast<const SbcF4*>(wseg + 2 * C + 4 * q);
     const float inv = 1.f / (float)HW;
-    const float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w};
-    const float m2[4] = {m2_4.x, m2_4.y, m2_4.z, m2_4.w};
-    float a[4], b[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const bool real = 4 * cg + j < C;
-        const float rstd = 1.f / sqrtf(m2[j] * inv + 1e-5f);       // nn.InstanceNorm2d: biased variance
-        a[j] = real ? gamma[j] * rstd : 0.f;
-        b[j] = real ? fmaf(gamma[j], (mean[j] - m) * rv * alpha[j], beta[j]) : 0.f;
-    }
-#pragma unroll 4
-    for (int i = s; i < HW; i += T) {
-        const int y = i / G.w, x = i - y * G.w;
-        const SbcF4 q = *sbc_px(arena + op.src, G, cg, y, x);
+    // nn.InstanceNorm2d: biased variance
+    const float a0 = ga.x * sbc_rsqrt(m2_4.x * inv + 1e-5f), a1 = ga.y * sbc_rsqrt(m2_4.y * inv + 1e-5f);
+    const float a2 = ga.z * sbc_rsqrt(m2_4.z * inv + 1e-5f), a3 = ga.w * sbc_rsqrt(m2_4.w * inv + 1e-5f);
+    const float b0 = fmaf(ga.x, (mean4.x - m) * rv * al.x, be.x), b1 = fmaf(ga.y, (mean4.y - m) * rv * al.y, be.y);
+    const float b2 = fmaf(ga.z, (mean4.z - m) * rv * al.z, be.z), b3 = fmaf(ga.w, (mean4.w - m) * rv * al.w, be.w);
+    const size_t qo = (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    const float* src = arena + op.src + qo;
+    float* dst = arena + op.dst + qo;
+    sbc_for_pixels(G, s, T, [&](int p) {
+        const SbcF4 x = *reinterpret_cast<const SbcF4*>(src + p * 8);
         SbcF4 o;
-        o.x = sbc_elu(fmaf(q.x - mean[0], a[0], b[0]));
-        o.y = sbc_elu(fmaf(q.y - mean[1], a[1], b[1]));
-        o.z = sbc_elu(fmaf(q.z - mean[2], a[2], b[2]));
-        o.w = sbc_elu(fmaf(q.w - mean[3], a[3], b[3]));
-        *sbc_px(arena + op.dst, G, cg, y, x) = o;
-    }
+        o.x = sbc_elu(fmaf(x.x - mean4.x, a0, b0));
+        o.y = sbc_elu(fmaf(x.y - mean4.y, a1, b1));
+        o.z = sbc_elu(fmaf(x.z - mean4.z, a2, b2));
+        o.w = sbc_elu(fmaf(x.w - mean4.w, a3, b3));
+        *reinterpret_cast<SbcF4*>(dst + p * 8) = o;
+    });
 }
 
 // ----------------------------------------------------------------------------------------------
-// element-wise ops (one float4 = 4 channels of one pixel per item)
+// element-wise ops (one float4 quad of one pixel per item)
 // ----------------------------------------------------------------------------------------------
 SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
-    const int HW = G.h * G.w, n = ((op.cin + 3) >> 2) * HW;
-#pragma unroll 4
-    for (int i = tid; i < n; i += nthr) {
-        const int cg = i / HW, r = i - cg * HW, y = r / G.w, x = r - y * G.w;
-        *sbc_px(arena + op.dst, G, cg, y, x) = sbc_elu4(*sbc_px(arena + op.src, G, cg, y, x));
+    const int nq = op.cin >> 2, T = sbc_norm_T(op, nthr), gpp = nthr / T, s = tid & (T - 1);
+    for (int q = tid / T; q < nq; q += gpp) {
+        const size_t qo = (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+        const float* src = arena + op.src + qo;
+        float* dst = arena + op.dst + qo;
+        sbc_for_pixels(G, s, T, [&](int p) {
+            *reinterpret_cast<SbcF4*>(dst + p * 8) = sbc_elu4(*reinterpret_cast<const SbcF4*>(src + p * 8));
+        });
     }
-    sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
+    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
-// dst = 2*src - 1 on channels < cin; channels cin .. cout-1 of dst are zero (ncsnv2.py:270-271)
+// dst (8 stored channels) = 2*x - 1 on channels 0,1 read from the compact state; channels 2..7 zero
+// (ncsnv2.py:270-271; begin_conv then contracts over one chunk of 8 input channels)
 SBC_HD void sbc_affine_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
-    const int HW = G.h * G.w, n = ((op.cout + 3) >> 2) * HW;
-    for (int i = tid; i < n; i += nthr) {
-        const int cg = i / HW, r = i - cg * HW, y = r / G.w, x = r - y * G.w;
+    const int HW = G.h * G.w;
+    const SbcF2* xc = reinterpret_cast<const SbcF2*>(arena + op.src);
+    for (int i = tid; i < 2 * HW; i += nthr) {
+        const int e = i >> 1, p = sbc_pix(G, e);
         SbcF4 o{0.f, 0.f, 0.f, 0.f};
-        if (4 * cg < op.cin) {
-            const SbcF4 v = *sbc_px(arena + op.src, G, cg, y, x);
-            const int c = 4 * cg;
-            o.x = (c < op.cin) ? 2.f * v.x - 1.f : 0.f;
-            o.y = (c + 1 < op.cin) ? 2.f * v.y - 1.f : 0.f;
-            o.z = (c + 2 < op.cin) ? 2.f * v.z - 1.f : 0.f;
-            o.w = (c + 3 < op.cin) ? 2.f * v.w - 1.f : 0.f;
+        if (!(i & 1)) {
+            const SbcF2 v = xc[e];
+            o.x = 2.f * v.x - 1.f;
+            o.y = 2.f * v.y - 1.f;
         }
-        *sbc_px(arena + op.dst, G, cg, y, x) = o;
+        *sbc_q4(arena + op.dst, G, i & 1, p) = o;
     }
-    sbc_zero_halo(arena + op.dst, G, op.cout, tid, nthr);
+    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, 8, tid, nthr);
 }
 
-// MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70); 4 channels per item
+// MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70).  One item = one quad of a column
+// segment of 4 output rows: the horizontal maxima of the 8 input rows it touches are formed once and the
+// four vertical windows slide over them (10 loads per output instead of 25).  H must be a multiple of 4.
+SBC_HD SbcF4 sbc_max4(SbcF4 a, SbcF4 b) {
+    return SbcF4{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)};
+}
 SBC_HD void sbc_maxpool5_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
-    const int H = G.h, W = G.w, HW = H * W, n = ((op.cin + 3) >> 2) * HW;
+    const int H = G.h, W = G.w, HB = H >> 2, per = HB * W, n = (op.cin >> 2) * per, lper = sbc_ilog2(per);
+    const SbcF4 ninf{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int i = tid; i < n; i += nthr) {
-        const int cg = i / HW, r = i - cg * HW, y = r / W, x = r - y * W;
-        SbcF4 m{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        const int y0 = y - 2 < 0 ? 0 : y - 2, y1 = y + 2 >= H ? H - 1 : y + 2;
+        const int q = sbc_div(i, per, lper), r = i - q * per;
+        const int yb = sbc_div(r, W, G.lw), x = r - yb * W, y0 = yb << 2;
         const int x0 = x - 2 < 0 ? 0 : x - 2, x1 = x + 2 >= W ? W - 1 : x + 2;
-        for (int yy = y0; yy <= y1; yy++) {
-            const SbcF4* row = sbc_px(arena + op.src, G, cg, yy, 0);
-            for (int xx = x0; xx <= x1; xx++) {
-                const SbcF4 v = row[xx];
-                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        SbcF4 hm[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int yy = y0 - 2 + k;
+            SbcF4 m = ninf;
+            if (yy >= 0 && yy < H) {
+                const int p = G.org + yy * G.wp;
+                for (int xx = x0; xx <= x1; xx++) m = sbc_max4(m, *sbc_q4(arena + op.src, G, q, p + xx));
             }
+            hm[k] = m;
         }
-        *sbc_px(arena + op.dst, G, cg, y, x) = m;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const SbcF4 m = sbc_max4(sbc_max4(sbc_max4(hm[o], hm[o + 1]), sbc_max4(hm[o + 2], hm[o + 3])), hm[o + 4]);
+            *sbc_q4(arena + op.dst, G, q, G.org + (y0 + o) * G.wp + x) = m;
+        }
     }
-    sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
+    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
 
 // acc += bilinear(src, size=(oh,ow), align_corners=True); optional edst = ELU(acc)  (layers.py:182-183)
 SBC_HD void sbc_upacc_op(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena, int tid, int nthr) {
-    const int H = GS.h, W = GS.w, OH = GD.h, OW = GD.w;
+    const int H = GS.h, W = GS.w, OH = GD.h, OW = GD.w, OHW = OH * OW, lohw = sbc_ilog2(OHW);
     const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-    const int n = ((op.cin + 3) >> 2) * OH * OW;
+    const int n = (op.cin >> 2) * OHW;
     for (int i = tid; i < n; i += nthr) {
-        const int cg = i / (OH * OW), rem = i - cg * (OH * OW);
-        const int y = rem / OW, x = rem - y * OW;
+        const int q = sbc_div(i, OHW, lohw), rem = i - q * OHW;
+        const int y = sbc_div(rem, OW, GD.lw), x = rem - y * OW;
         const float fy = sy * (float)y, fx = sx * (float)x;
         const int y0 = (int)fy, x0 = (int)fx;
         const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
         const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        const SbcF4 p00 = *sbc_px(arena + op.src, GS, cg, y0, x0), p01 = *sbc_px(arena + op.src, GS, cg, y0, x1);
-        const SbcF4 p10 = *sbc_px(arena + op.src, GS, cg, y1, x0), p11 = *sbc_px(arena + op.src, GS, cg, y1, x1);
-        SbcF4* a = sbc_px(arena + op.acc, GD, cg, y, x);
+        const int r0 = GS.org + y0 * GS.wp, r1 = GS.org + y1 * GS.wp;
+        const SbcF4 p00 = *sbc_q4(arena + op.src, GS, q, r0 + x0), p01 = *sbc_q4(arena + op.src, GS, q, r0 + x1);
+        const SbcF4 p10 = *sbc_q4(arena + op.src, GS, q, r1 + x0), p11 = *sbc_q4(arena + op.src, GS, q, r1 + x1);
+        const int pd = GD.org + y * GD.wp + x;
+        SbcF4* a = sbc_q4(arena + op.acc, GD, q, pd);
         SbcF4 v = *a;
         v.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
         v.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
         v.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
         v.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
         *a = v;
-        if (op.edst >= 0) *sbc_px(arena + op.edst, GD, cg, y, x) = sbc_elu4(v);
+        if (op.edst >= 0) *sbc_q4(arena + op.edst, GD, q, pd) = sbc_elu4(v);
     }
-    if (op.edst >= 0) sbc_zero_halo(arena + op.edst, GD, op.cin, tid, nthr);
+    if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cin, tid, nthr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -245,9 +298,8 @@ SBC_HD void sbc_noise_cn01(uint64_t seed, uint64_t sid, uint32_t step, int e, fl
 
 // ----------------------------------------------------------------------------------------------
 // Annealed-Langevin step around the network (reference test_score.py:157-170).
-// x lives in the arena at in_off as a 2-channel tensor of geometry G (channel 0 = re, 1 = im of
-// x[t][r], pixel (y=t, x=r)).  P [Np][Nt], Y [Np][Nr], Hor [Nt][Nr] are interleaved complex64 in global
-// memory.
+// x (compact, [Nt*Nr] (re, im)) lives in the arena at in_off, the raw network output at out_off.
+// P [Np][Nt], Y [Np][Nr], Hor [Nt][Nr] are interleaved complex64 in global memory.
 // ----------------------------------------------------------------------------------------------
 struct SbcStepScalars {
     float sigma;      // sigmas[level]
@@ -257,34 +309,41 @@ struct SbcStepScalars {
 };
 
 // phase 1: res = P @ x - y   (test_score.py:157-158, inner product), planar [2][Np*Nr] into `res`
-SBC_HD void sbc_dc_residual(const float* ax, const SbcGeo& G, float* res, const float* P, const float* Y, int Nt,
-                            int Nr, int Np, int tid, int nthr) {
+SBC_HD void sbc_dc_residual(const float* xc, float* res, const float* P, const float* Y, int Nt, int Nr, int Np,
+                            int tid, int nthr) {
+    const SbcF2* x2 = reinterpret_cast<const SbcF2*>(xc);
+    const SbcF2* P2 = reinterpret_cast<const SbcF2*>(P);
+    const int lnr = sbc_ilog2(Nr);
     for (int o = tid; o < Np * Nr; o += nthr) {
-        const int p = o / Nr, r = o - p * Nr;
+        const int p = sbc_div(o, Nr, lnr), r = o - p * Nr;
         float sr = 0.f, si = 0.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int t = 0; t < Nt; t++) {
-            const float pr = P[2 * (p * Nt + t)], pi = P[2 * (p * Nt + t) + 1];
-            const SbcF4 c = *sbc_px(ax, G, 0, t, r);
-            sr += pr * c.x - pi * c.y;
-            si += pr * c.y + pi * c.x;
+            const SbcF2 pv = P2[p * Nt + t];
+            const SbcF2 c = x2[t * Nr + r];
+            sr += pv.x * c.x - pv.y * c.y;
+            si += pv.x * c.y + pv.y * c.x;
         }
         res[o] = sr - Y[2 * o];
         res[Np * Nr + o] = si - Y[2 * o + 1];
     }
 }
 // phase 2: g = P^H res;  x += alpha*(net/sigma - g/den) + nscale*eps;  per-thread |x-H|^2 partial
-SBC_HD float sbc_langevin_update(float* ax, const float* net, const SbcGeo& G, const float* res, const float* P,
-                                 const float* Hor, const float* ext_noise, const SbcStepScalars& sc, uint64_t seed,
-                                 uint64_t sid, uint32_t gstep, int Nt, int Nr, int Np, int tid, int nthr) {
-    const int ne = Nt * Nr;
+SBC_HD float sbc_langevin_update(float* xc, const float* net, const float* res, const float* P, const float* Hor,
+                                 const float* ext_noise, const SbcStepScalars& sc, uint64_t seed, uint64_t sid,
+                                 uint32_t gstep, int Nt, int Nr, int Np, int tid, int nthr) {
+    const int ne = Nt * Nr, lnr = sbc_ilog2(Nr);
+    SbcF2* x2 = reinterpret_cast<SbcF2*>(xc);
+    const SbcF2* n2 = reinterpret_cast<const SbcF2*>(net);
+    const SbcF2* P2 = reinterpret_cast<const SbcF2*>(P);
     float part = 0.f;
     for (int e = tid; e < ne; e += nthr) {
-        const int t = e / Nr, r = e - t * Nr;
+        const int t = sbc_div(e, Nr, lnr), r = e - t * Nr;
         float gr = 0.f, gi = 0.f;
-#pragma unroll 2
+#pragma unroll 8
         for (int p = 0; p < Np; p++) {   // conj(P[p,t]) * res[p,r]
-            const float pr = P[2 * (p * Nt + t)], pi = -P[2 * (p * Nt + t) + 1];
+            const SbcF2 pv = P2[p * Nt + t];
+            const float pr = pv.x, pi = -pv.y;
             const float cr = res[p * Nr + r], ci = res[Np * Nr + p * Nr + r];
             gr += pr * cr - pi * ci;
             gi += pr * ci + pi * cr;
@@ -292,13 +351,12 @@ SBC_HD float sbc_langevin_update(float* ax, const float* net, const SbcGeo& G, c
         float nr_, ni_;
         if (ext_noise) { nr_ = ext_noise[2 * e]; ni_ = ext_noise[2 * e + 1]; }
         else sbc_noise_cn01(seed, sid, gstep, e, nr_, ni_);
-        SbcF4* xp = sbc_px(ax, G, 0, t, r);
-        const SbcF4 nv = *sbc_px(net, G, 0, t, r);
-        SbcF4 xv = *xp;
+        const SbcF2 nv = n2[e];
+        SbcF2 xv = x2[e];
         const float sr = nv.x / sc.sigma, si = nv.y / sc.sigma;   // ncsnv2.py:295-298
         xv.x = xv.x + sc.alpha * (sr - gr / sc.den) + sc.nscale * nr_;
         xv.y = xv.y + sc.alpha * (si - gi / sc.den) + sc.nscale * ni_;
-        *xp = xv;
+        x2[e] = xv;
         if (Hor) {
             const float dr = xv.x - Hor[2 * e], di = xv.y - Hor[2 * e + 1];
             part += dr * dr + di * di;

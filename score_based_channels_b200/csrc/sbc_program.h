@@ -1,10 +1,12 @@
 // sbc_program.h -- op table + tensor geometry shared by the host program builder (program.py) and the
-// kernel.  One SbcOp = 24 int32 words, in the order of program.py:OP_FIELDS.
+// kernel.  One SbcOp = 32 int32 words, in the order of program.py:OP_FIELDS.  Everything the device code
+// would otherwise derive per op (tile counts, K steps, log2 of the row width, ...) is computed once on the
+// host: the kernel is instruction-issue bound, so no integer division or table walk may sit on its hot path.
 #pragma once
 #include <stdint.h>
 
 enum SbcOpKind : int32_t {
-    SBC_OP_AFFINE = 0,    // dst = 2*src - 1                     (reference ncsnv2/models/ncsnv2.py:270-271)
+    SBC_OP_AFFINE = 0,    // dst = 2*x - 1 from the compact state buffer (reference ncsnv2/models/ncsnv2.py:270-271)
     SBC_OP_NORM_ELU = 2,  // dst = ELU(InstanceNorm2dPlus(src))   (normalization.py:163-176, layers.py:13)
     SBC_OP_ELU = 3,       // dst = ELU(src)
     SBC_OP_MAXPOOL5 = 4,  // MaxPool2d(5, stride 1, pad 2)        (layers.py:70)
@@ -17,17 +19,21 @@ enum SbcOpKind : int32_t {
 enum SbcOpFlags : int32_t {
     SBC_F_POOL = 1,       // conv followed by the 2x2 mean-pool of ConvMeanPool (layers.py:309-313)
     SBC_F_X3 = 2,         // 3xTF32 error-compensated product (fp32-equivalent accuracy)
+    SBC_F_COMPACT = 4,    // conv epilogue writes couts 0,1 as interleaved (re, im) pairs [h*w] (the network output)
+    SBC_F_ZH_DST = 8,     // the halo of the fresh tensor dst must be re-zeroed (decided offline by the planner:
+    SBC_F_ZH_EDST = 16,   // program.py:_halo_analysis); same for edst
 };
 
-// Geometry of every tensor of one resolution: channel-interleaved by 4, zero halo of (hy, hx) pixels.
-//   addr(c, y, x) = base + ((c >> 2) * pps + org + y * wp + x) * 4 + (c & 3)        [floats]
+// Geometry of every tensor of one resolution: channel-interleaved by 8 (one pixel = 8 channels = 32 bytes
+// = the K chunk of one m16n8k8 MMA), zero halo of (hy, hx) pixels.
+//   addr(c, y, x) = base + ((c >> 3) * pps + org + y * wp + x) * 8 + (c & 7)        [floats]
 struct SbcGeo {
     int32_t h, w;        // interior size
     int32_t hy, hx;      // halo (covers every live conv tap at this resolution)
     int32_t wp;          // padded row pitch in pixels = w + 2*hx
     int32_t pps;         // padded plane size in pixels = (h + 2*hy) * wp
     int32_t org;         // pixel index of (0, 0) = hy * wp + hx
-    int32_t pad;
+    int32_t lw;          // log2(w) if w is a power of two, else -1 (division fallback)
 };
 #define SBC_MAX_GEO 8
 
@@ -42,9 +48,17 @@ struct SbcOp {
     int32_t ks;                    // conv: warps that split the K steps of one (pixel tile, cout tile) unit
     int32_t scratch;               // arena offset of op scratch (norm statistics, K-split partials)
     int32_t oh, ow;                // output spatial size
-    int32_t pad0;                  // filled by sbc_model_create: index of the next op with parameters
+    int32_t next_w;                // filled by sbc_model_create: index of the next op with parameters
     int32_t tapmask;               // conv: live taps of the k x k window (bit = ky*k + kx)
     int32_t wbuf;                  // arena offset where the parameter segment is staged
+    // ---- host-derived conv constants ----
+    int32_t MT, NT;                // 16-pixel output tiles, 8-cout tiles
+    int32_t S;                     // K steps = live taps * cin chunks; segment starts with S int32 A offsets
+    int32_t frag_rel;              // offset of the B fragments inside the segment
+    int32_t low;                   // log2(ow) or -1
+    // ---- filled by sbc_model_create: parameter segment of the NEXT parameterised op (wrapping to the first),
+    // so that issuing its cp.async.bulk prefetch needs no dependent global load
+    int32_t nw_off, nw_len, nw_buf;
 };
-static_assert(sizeof(SbcOp) == 96, "SbcOp must be 24 int32 words");
+static_assert(sizeof(SbcOp) == 128, "SbcOp must be 32 int32 words");
 static_assert(sizeof(SbcGeo) == 32, "SbcGeo must be 8 int32 words");

@@ -17,13 +17,14 @@ reference arithmetic):
 * ``ConvMeanPool`` = conv then 2x2 mean-pool: four accumulations (one per pooling position) summed in the
   epilogue, weights pre-scaled by 1/4 -- ``F_POOL``.
 
-Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by 4 with a zero halo,
-``addr(c, y, x) = base + ((c // 4) * pps + org + y * wp + x) * 4 + c % 4`` with ``wp = w + 2*hx``,
+Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by 8 with a zero halo,
+``addr(c, y, x) = base + ((c // 8) * pps + org + y * wp + x) * 8 + c % 8`` with ``wp = w + 2*hx``,
 ``pps = (h + 2*hy) * wp``, ``org = hy * wp + hx``.  The halo (hy, hx) covers every live convolution tap
-at that resolution, so the implicit-im2col gather of a tap is the *same* address pattern shifted by a
-constant and needs no bounds checks; 8 consecutive pixels x 4 channels are 128 contiguous bytes -- one
-conflict-free shared-memory wavefront for an mma.sync A fragment, and exactly one no-swizzle K-major
-core matrix of a tcgen05 kind::tf32 operand.
+at that resolution, so the implicit-im2col gather of a K step (tap, chunk of 8 input channels) is the
+*same* address pattern shifted by a constant -- tabulated per op at the head of its parameter segment --
+and needs no bounds checks; one pixel of one plane is exactly the K = 8 chunk of an m16n8k8 MMA, a lane's
+two K columns are adjacent channels (one 8-byte load) and a quarter-warp covers 256 contiguous bytes.
+The sampler state ``x`` and the raw network output are *compact* (re, im) pair arrays [h*w].
 
 Nothing here touches a GPU; ``simulate`` is a torch (CPU) interpreter of the program used by the CPU
 test-suite to pin the schedule against the reference module before any CUDA code runs.
@@ -49,13 +50,23 @@ F_X3 = 2          # 3xTF32 error-compensated product (fp32-equivalent accuracy)
 
 PRECISIONS = ("tf32x3", "tf32")
 
+F_COMPACT = 4     # conv epilogue writes couts (0,1) as compact (re, im) pairs: the network output
+F_ZH_DST = 8      # the halo of the fresh tensor `dst` must be re-zeroed (set by ProgramBuilder._halo_analysis)
+F_ZH_EDST = 16    # same for `edst`
+
 OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout", "h", "w", "ksize", "dil",
-             "w_off", "w_len", "b_rel", "sgeo", "dgeo", "ks", "scratch", "oh", "ow", "pad0", "tapmask",
-             "wbuf")
-OP_WORDS = len(OP_FIELDS)            # 24 int32 = 96 bytes per op
-assert OP_WORDS == 24
+             "w_off", "w_len", "b_rel", "sgeo", "dgeo", "ks", "scratch", "oh", "ow", "next_w", "tapmask",
+             "wbuf", "MT", "NT", "S", "frag_rel", "low", "nw_off", "nw_len", "nw_buf")
+DEVICE_FILLED = ("next_w", "nw_off", "nw_len", "nw_buf")     # written by sbc_model_create
+OP_WORDS = len(OP_FIELDS)            # 32 int32 = 128 bytes per op
+assert OP_WORDS == 32
 MAX_GEO = 8
-GEO_WORDS = 8                        # h, w, hy, hx, wp, pps, org, pad
+GEO_WORDS = 8                        # h, w, hy, hx, wp, pps, org, lw
+
+
+def ilog2(v: int) -> int:
+    """log2(v) if v is a power of two, else -1 (the device code then divides instead of shifting)."""
+    return v.bit_length() - 1 if v > 0 and not (v & (v - 1)) else -1
 
 
 @dataclass(frozen=True)
@@ -78,10 +89,10 @@ class Geo:
         return self.hy * self.wp + self.hx
 
     def floats(self, c: int) -> int:
-        return ((c + 3) // 4) * self.pps * 4
+        return ((c + 7) // 8) * self.pps * 8
 
     def words(self) -> List[int]:
-        return [self.h, self.w, self.hy, self.hx, self.wp, self.pps, self.org, 0]
+        return [self.h, self.w, self.hy, self.hx, self.wp, self.pps, self.org, ilog2(self.w)]
 
 
 @dataclass
@@ -109,10 +120,15 @@ class Op:
     ow: int = 0
     tapmask: int = 0    # conv: bit i set = tap i (row-major in the k x k window) can touch the image
     wbuf: object = -1   # arena offset where this op's parameter segment is staged (cp.async.bulk)
+    MT: int = 0         # conv: 16-pixel output tiles
+    NT: int = 0         # conv: 8-cout tiles
+    S: int = 0          # conv: K steps (live taps x cin chunks); the segment starts with S int32 A offsets
+    frag_rel: int = 0   # conv: offset of the B fragments inside the segment
+    low: int = -1       # log2(ow) or -1
     name: str = ""
 
     def words(self) -> List[int]:
-        vals = [getattr(self, f) if f != "pad0" else 0 for f in OP_FIELDS]
+        vals = [0 if f in DEVICE_FILLED else getattr(self, f) for f in OP_FIELDS]
         return [int(v) for v in vals]
 
 
@@ -122,8 +138,8 @@ class Program:
     geos: List[Geo]
     arena_floats: int
     blob: np.ndarray                 # float32 parameter blob
-    in_off: int                      # arena offset of the network input x (2 channels, geometry 0)
-    out_off: int                     # arena offset of the raw network output (before /sigma), geometry 0
+    in_off: int                      # arena offset of the network input x: compact (re, im) pairs [H*W]
+    out_off: int                     # arena offset of the raw network output (before /sigma), compact pairs
     post_off: int                    # scratch for the sampler phases that follow the network
     H: int
     W: int
@@ -156,7 +172,7 @@ class Program:
     def _index(self, off: int, c: int, h: int, w: int) -> np.ndarray:
         g = self.geo_of(h, w)
         cc, yy, xx = np.meshgrid(np.arange(c), np.arange(h), np.arange(w), indexing="ij")
-        return off + ((cc // 4) * g.pps + g.org + yy * g.wp + xx) * 4 + cc % 4
+        return off + ((cc // 8) * g.pps + g.org + yy * g.wp + xx) * 8 + cc % 8
 
     def read(self, arena, off: int, c: int, h: int, w: int):
         """[c,h,w] copy of the tensor stored at float offset ``off``."""
@@ -178,6 +194,27 @@ class Program:
         else:
             import torch
             arena[torch.from_numpy(idx)] = value
+
+    def _compact_index(self, off: int) -> np.ndarray:
+        cc, ee = np.meshgrid(np.arange(self.channels), np.arange(self.H * self.W), indexing="ij")
+        return (off + ee * self.channels + cc).reshape(self.channels, self.H, self.W)
+
+    def write_input(self, arena, x) -> None:
+        """Store the network input x [channels,H,W] in its compact form (interleaved (re, im) pairs)."""
+        idx = self._compact_index(self.in_off)
+        if isinstance(arena, np.ndarray):
+            arena[idx] = np.asarray(x, np.float32)
+        else:
+            import torch
+            arena[torch.from_numpy(idx)] = x
+
+    def read_output(self, arena):
+        """[channels,H,W] copy of the raw network output (before the /sigma of ncsnv2.py:295-298)."""
+        idx = self._compact_index(self.out_off)
+        if isinstance(arena, np.ndarray):
+            return arena[idx]
+        import torch
+        return arena[torch.from_numpy(idx)]
 
 
 class _Planner:
@@ -235,7 +272,7 @@ class ProgramBuilder:
 
     # largest parameter segment (floats) one slot of the shared-memory ring holds; convs whose fragment
     # array is bigger are split into cout chunks (each chunk is its own op)
-    SLOT_FLOATS = 9248
+    SLOT_FLOATS = 9300
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
                  channels: int = 2, nthreads: int = 512, precision: str = "tf32x3"):
@@ -262,6 +299,10 @@ class ProgramBuilder:
             dils = [1] if lvl < 3 else [1, 2, 4]
             hy = max([d for d in dils if d < h] + [0])
             hx = max([d for d in dils if d < w] + [0])
+            if w == 2:
+                # the 4 pixel rows of a quarter-warp A gather are (Y,0) (Y,1) (Y+1,0) (Y+1,1): with a row pitch
+                # of 6 pixels (192 B) they fall into disjoint shared-memory banks
+                hx = max(hx, 2)
             self.geos.append(Geo(h, w, hy, hx))
 
     def gi(self, h: int, w: int) -> int:
@@ -309,29 +350,32 @@ class ProgramBuilder:
 
     # -- ops --------------------------------------------------------------
     def conv(self, prefix: str, src: str, dst: Optional[str] = None, acc: Optional[str] = None,
-             edst: Optional[str] = None, dil: int = 1, pool: bool = False) -> None:
+             edst: Optional[str] = None, dil: int = 1, pool: bool = False, compact: bool = False) -> None:
         """One Conv2d (reference ``layers.py:28-60``) + fused epilogue, as an implicit GEMM on tensor cores:
 
-            D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]   per (live tap, cin chunk)
+            D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]   per K step (live tap, cin chunk)
 
         v = conv(src) + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v).
-        The weights are packed in mma.sync m16n8k8 B-fragment order: frag[step][ntile][lane] =
-        (hi0, hi1[, lo0, lo1]) where lane = 4*g + t holds B[k = t (+4)][n = g], step = live_tap_index *
-        KC + cin_chunk, hi = TF32(w), lo = TF32(w - hi) (lo only in the 3xTF32 mode)."""
+        Parameter segment: [S int32 A offsets | B fragments | bias].  ``aoff[s]`` is the float offset
+        (cin_chunk * pps + dy * wp + dx) * 8 that K step s adds to every gathered address.  The weights are in
+        mma.sync m16n8k8 B-fragment order with the K index permuted like the A gather (csrc/sbc_mma.h):
+        frag[step][ntile][lane] = (w0, w1) where lane = 4*g + t holds W[cout g][cin 2t (+1)]: TF32-rounded (rna)
+        in the "tf32" mode, plain fp32 in the 3xTF32 mode (the kernel splits w = hi + lo in registers)."""
         wt = self.sd[prefix + ".weight"]
         bias = self.sd.get(prefix + ".bias")
         cout, cin, k, k2 = wt.shape
         assert k == k2 and k in (1, 3)
+        assert cout % 2 == 0, "the epilogue stores adjacent cout pairs"
         c, h, w = self.shape[src]
-        assert c == cin, (prefix, c, cin)
+        assert c == cin or (c == 8 and cin < 8), (prefix, c, cin)      # begin_conv reads a zero-padded chunk
         oh, ow = (h // 2, w // 2) if pool else (h, w)
-        for t in (dst, acc, edst):
+        for t in (acc, edst) + (() if compact else (dst,)):
             if t is not None:
                 assert self.shape[t] == (cout, oh, ow), (prefix, t, self.shape[t], (cout, oh, ow))
         self.flops += 2 * h * w * cin * k * k * cout       # dense count, reference convention
         r = k // 2
         x3 = self.precision == "tf32x3"
-        E = 4 if x3 else 2                                 # floats per lane per fragment
+        E = 2                                              # floats per lane per fragment
         sg = self.geos[self.gi(h, w)]
         live = []
         for tap in range(k * k):
@@ -341,15 +385,22 @@ class ProgramBuilder:
                 live.append(tap)
         tapmask = sum(1 << t for t in live)
         KC, NT = (cin + 7) // 8, (cout + 7) // 8
-        per_nt = len(live) * KC * 32 * E
+        S = len(live) * KC
+        S4 = (S + 3) // 4 * 4
+        per_nt = S * 32 * E
         nt_chunk = NT
-        while nt_chunk > 1 and per_nt * nt_chunk + 8 * nt_chunk > self.SLOT_FLOATS:
+        while nt_chunk > 1 and S4 + per_nt * nt_chunk + 8 * nt_chunk > self.SLOT_FLOATS:
             nt_chunk //= 2
         wpad = np.zeros((NT * 8, KC * 8, k * k), np.float32)
         wpad[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
         g, t = np.arange(32) >> 2, np.arange(32) & 3
         nwarps = self.nthreads // 32
         dgeo = self.geos[self.gi(oh, ow)]
+        aoff = np.zeros(S4, np.int32)
+        for i, tap in enumerate(live):
+            dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
+            for kc in range(KC):
+                aoff[i * KC + kc] = (kc * sg.pps + dy * sg.wp + dx) * 8
         for nt0 in range(0, NT, nt_chunk):
             ntc = min(nt_chunk, NT - nt0)
             co0, co1 = nt0 * 8, min(cout, (nt0 + ntc) * 8)
@@ -357,25 +408,29 @@ class ProgramBuilder:
             for i, tap in enumerate(live):
                 for kc in range(KC):
                     for nt in range(ntc):
-                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t, tap]
-                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t + 4, tap]
-                        h0, h1 = tf32_rna(w0), tf32_rna(w1)
-                        frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = h0, h1
-                        if x3:
-                            frag[i, kc, nt, :, 2], frag[i, kc, nt, :, 3] = tf32_rna(w0 - h0), tf32_rna(w1 - h1)
-            arrs = [frag] + ([bias[co0:co1]] if bias is not None else [])
+                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + 2 * t, tap]
+                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + 2 * t + 1, tap]
+                        if not x3:
+                            w0, w1 = tf32_rna(w0), tf32_rna(w1)
+                        frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = w0, w1
+            arrs = [aoff.view(np.float32), frag] + ([bias[co0:co1]] if bias is not None else [])
             w_off, w_len, rels = self._push(arrs)
             MT = (oh * ow + 15) // 16
-            units, S = MT * ntc, len(live) * KC
+            units = MT * ntc
             ks = 1
             while units * ks * 2 <= nwarps and ks * 2 <= S:
                 ks *= 2
             scratch = self.tmp_raw(nwarps * 32 * 4, "ksp") if ks > 1 else None
-            flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0)
-            shift = lambda name: -1 if name is None else (name, (co0 // 4) * dgeo.pps * 4)
+            flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0)
+            if compact:
+                assert nt_chunk == NT and cout == 2 and acc is None and edst is None
+                shift = lambda name: -1 if name is None else name
+            else:
+                shift = lambda name: -1 if name is None else (name, (co0 // 8) * dgeo.pps * 8)
             self.ops.append(Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin, co1 - co0, h, w, k,
-                               dil, w_off, w_len, rels[1] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
-                               ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask,
+                               dil, w_off, w_len, rels[2] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
+                               ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask, MT=MT, NT=ntc,
+                               S=S, frag_rel=rels[1], low=ilog2(ow),
                                name=prefix + ("" if nt_chunk == NT else "[co%d:%d]" % (co0, co1))))
             if scratch is not None:
                 self.free(scratch)
@@ -399,10 +454,12 @@ class ProgramBuilder:
         self.ops.append(Op(OP_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, sgeo=self.gi(h, w), dgeo=self.gi(h, w),
                            oh=h, ow=w, name="elu"))
 
-    def affine(self, src: str, dst: str, cstore: int) -> None:
-        """dst = 2*src - 1 on the cin real channels; channels cin..cstore-1 of dst are written as zeros."""
-        c, h, w = self.shape[src]
-        self.ops.append(Op(OP_AFFINE, 0, src, dst, cin=c, cout=cstore, h=h, w=w, sgeo=self.gi(h, w),
+    def affine(self, src: str, dst: str) -> None:
+        """dst (8 stored channels) = 2*x - 1 on the real channels read from the compact state buffer ``src``;
+        the padding channels of dst are written as zeros."""
+        c, h, w = self.shape[dst]
+        assert c == 8 and self.channels == 2
+        self.ops.append(Op(OP_AFFINE, 0, src, dst, cin=self.channels, cout=c, h=h, w=w, sgeo=self.gi(h, w),
                            dgeo=self.gi(h, w), oh=h, ow=w, name="2x-1"))
 
     def maxpool5(self, src: str, dst: str) -> None:
@@ -525,9 +582,10 @@ class ProgramBuilder:
     # -- whole network ----------------------------------------------------
     def build(self) -> Program:
         ngf, H, W = self.ngf, self.H, self.W
-        xin = self.new("x_in", self.channels, H, W)
-        a = self.tmp(self.channels, H, W, cstore=8)     # begin_conv reads one chunk of 8 input channels
-        self.affine(xin, a, cstore=8)
+        assert ngf % 8 == 0, "ngf must be a multiple of 8 (channel planes hold 8 channels)"
+        xin = self.new_raw("x_in", self.channels * H * W)       # compact (re, im) pairs
+        a = self.tmp(8, H, W)                                   # begin_conv reads one chunk of 8 input channels
+        self.affine(xin, a)
         o = self.tmp(ngf, H, W, "o")
         self.conv("begin_conv", a, dst=o)
         self.free(a)
@@ -546,11 +604,11 @@ class ProgramBuilder:
         t = self.tmp(ngf, H, W)
         self.norm_elu("normalizer", r5, t)
         self.free(r5)
-        out = self.new("net_out", self.channels, H, W)
-        self.conv("end_conv", t, dst=out)
+        out = self.new_raw("net_out", self.channels * H * W)    # compact (re, im) pairs
+        self.conv("end_conv", t, dst=out, compact=True)
         self.free(t)
         # scratch for the sampler phases that follow the network (residual P*x-y, reductions)
-        post = self.new_raw("post", 2 * H * W + 4 * self.nthreads)
+        post = self.new_raw("post", 2 * H * W)
         blob = np.concatenate(self.blob) if self.blob else np.zeros(0, np.float32)
         assert blob.size == self.blob_len
         max_w_len = max(op.w_len for op in self.ops)
@@ -579,9 +637,65 @@ class ProgramBuilder:
                     setattr(op, f, self.ar.offs[v])
                 else:
                     setattr(op, f, -1 if v is None else int(v))
+        self._halo_analysis(self.ar.peak, [(self.ar.offs[xin], self.channels * H * W),
+                                           (self.ar.offs[post], 2 * H * W)])
         return Program(self.ops, self.geos, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out],
                        self.ar.offs[post], H, W, ngf, self.channels, self.nthreads, max_w_len, self.flops,
                        self.precision)
+
+    def _halo_analysis(self, arena_floats: int, raw_regions) -> None:
+        """Decide which ops must re-zero the halo of the tensors they create (flags F_ZH_DST / F_ZH_EDST).
+
+        Ops write the interior of their outputs only; a halo is known to be zero when every cell of the plane
+        was last owned by a plane of the SAME geometry at the SAME address (its halo cells coincide and were
+        zero by induction).  The walk assumes an arbitrary arena at the start of every forward pass, and treats
+        raw buffers (parameter staging, scratch, the compact state / output, the sampler scratch) as dirt."""
+        tags = np.full(arena_floats, -1, np.int64)
+
+        def raw(off: int, n: int) -> None:
+            if off >= 0 and n > 0:
+                tags[off:off + n] = -2
+
+        def fresh(off: int, gi: int, c: int) -> bool:
+            g = self.geos[gi]
+            need = False
+            for pl in range((c + 7) // 8):
+                a = off + pl * g.pps * 8
+                key = (gi << 40) | a
+                seg = tags[a:a + g.pps * 8]
+                if not bool((seg == key).all()):
+                    need = True
+                seg[:] = key
+            return need
+
+        for off, n in raw_regions:
+            raw(off, n)
+        nwarps = self.nthreads // 32
+        for op in self.ops:
+            raw(op.wbuf, op.w_len)
+            if op.kind == OP_CONV_MMA:
+                raw(op.scratch, nwarps * 32 * 4)
+                if op.flags & F_COMPACT:
+                    raw(op.dst, self.channels * op.oh * op.ow)
+                elif op.dst >= 0 and fresh(op.dst, op.dgeo, op.cout):
+                    op.flags |= F_ZH_DST
+                if op.edst >= 0 and fresh(op.edst, op.dgeo, op.cout):
+                    op.flags |= F_ZH_EDST
+            elif op.kind == OP_NORM_ELU:
+                raw(op.scratch, 2 * nwarps * 4 + 2 * op.cin)
+                if fresh(op.dst, op.dgeo, op.cin):
+                    op.flags |= F_ZH_DST
+            elif op.kind in (OP_ELU, OP_MAXPOOL5):
+                if fresh(op.dst, op.dgeo, op.cin):
+                    op.flags |= F_ZH_DST
+            elif op.kind == OP_AFFINE:
+                if fresh(op.dst, op.dgeo, op.cout):
+                    op.flags |= F_ZH_DST
+            elif op.kind == OP_UPACC:
+                if op.edst >= 0 and fresh(op.edst, op.dgeo, op.cin):
+                    op.flags |= F_ZH_EDST
+            else:
+                raise ValueError(op.kind)
 
     def _stage(self, p: str, skip: str, cout: int, dil: Optional[int]) -> str:
         """Two ResidualBlocks, the first 'down'; ``skip`` must survive (it feeds a RefineBlock later)."""
@@ -622,19 +736,19 @@ def conv_weights(prog: Program, op: Op):
     blob = torch.from_numpy(prog.blob)
     k = op.ksize
     live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
-    KC, NT = (op.cin + 7) // 8, (op.cout + 7) // 8
-    E = 4 if (op.flags & F_X3) else 2
+    KC, NT = (op.cin + 7) // 8, op.NT
+    assert op.S == len(live) * KC
+    E = 2
     n = len(live) * KC * NT * 32 * E
-    frag = blob[op.w_off:op.w_off + n].view(len(live), KC, NT, 32, E)
+    f0 = op.w_off + op.frag_rel
+    frag = blob[f0:f0 + n].view(len(live), KC, NT, 32, E)
     full = torch.zeros(NT * 8, KC * 8, k * k)
     g, t = torch.arange(32) >> 2, torch.arange(32) & 3
     for i, tap in enumerate(live):
         for kc in range(KC):
             for nt in range(NT):
-                lo0 = frag[i, kc, nt, :, 2] if E == 4 else 0.0
-                lo1 = frag[i, kc, nt, :, 3] if E == 4 else 0.0
-                full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0] + lo0
-                full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1] + lo1
+                full[nt * 8 + g, kc * 8 + 2 * t, tap] = frag[i, kc, nt, :, 0]
+                full[nt * 8 + g, kc * 8 + 2 * t + 1, tap] = frag[i, kc, nt, :, 1]
     wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
     bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
     return wt, bias
@@ -651,12 +765,13 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
     arena = torch.zeros(prog.arena_floats, dtype=torch.float32)
     blob = torch.from_numpy(prog.blob)
     rd = lambda off, c, h, w: prog.read(arena, off, c, h, w)
-    prog.write(arena, prog.in_off, x.float())
+    prog.write_input(arena, x.float())
     for i, op in enumerate(prog.ops):
         if upto is not None and i >= upto:
             break
         if op.kind == OP_AFFINE:
-            prog.write(arena, op.dst, 2 * rd(op.src, op.cin, op.h, op.w) - 1.0, cstore=op.cout)
+            xin = arena[op.src:op.src + op.cin * op.h * op.w].view(op.h, op.w, op.cin).permute(2, 0, 1)
+            prog.write(arena, op.dst, 2 * xin - 1.0, cstore=op.cout)
         elif op.kind == OP_ELU:
             prog.write(arena, op.dst, F.elu(rd(op.src, op.cin, op.h, op.w)))
         elif op.kind == OP_MAXPOOL5:
@@ -681,7 +796,7 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
         elif op.kind == OP_CONV_MMA:
             k = op.ksize
             wt, bias = conv_weights(prog, op)
-            s = rd(op.src, op.cin, op.h, op.w)[None]
+            s = rd(op.src, op.cin, op.h, op.w)[None]       # begin_conv: the real channels of the padded chunk
             if op.flags & F_POOL:
                 # packed weights already carry the 1/4; conv at full res then 2x2 SUM
                 v = F.conv2d(s, wt, None, 1, op.dil * (k // 2), op.dil)
@@ -691,7 +806,9 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
             else:
                 v = F.conv2d(s, wt, bias, 1, op.dil * (k // 2), op.dil)
             v = v[0]
-            if op.dst >= 0:
+            if op.flags & F_COMPACT:
+                arena[op.dst:op.dst + op.cout * op.oh * op.ow] = v.permute(1, 2, 0).reshape(-1)
+            elif op.dst >= 0:
                 prog.write(arena, op.dst, v)
             if op.acc >= 0:
                 v = rd(op.acc, op.cout, op.oh, op.ow) + v
@@ -700,5 +817,5 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
                 prog.write(arena, op.edst, F.elu(v))
         else:
             raise ValueError(op.kind)
-    out = rd(prog.out_off, prog.channels, prog.H, prog.W).clone()
+    out = prog.read_output(arena).clone()
     return out, arena

@@ -11,96 +11,99 @@
 #include "../../score_based_channels_b200/csrc/sbc_ops.h"
 
 // warp-level emulation of the tensor-core conv: every lane's fragments are gathered with the shared
-// per-lane helpers, the m16n8k8 product is done as plain matrices with the operand rounding of the
-// device path (3xTF32: a = trunc(a) + trunc(a - trunc(a)), weights pre-split on the host; TF32: rn),
+// per-lane helpers (K-step offset table, permuted K index), the m16n8k8 product is done as plain matrices
+// with the operand rounding of the device path (3xTF32: a = trunc(a) + (a - trunc(a)), the low parts
+// truncated by the tensor core, weights split the same way; TF32: rna on activations, weights pre-rounded),
 // then the per-lane epilogue runs.
 static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena, const float* wseg, int nthr) {
-    SbcMmaGeom M;
-    sbc_mma_geom(op, M);
     const bool x3 = (op.flags & SBC_F_X3) != 0;
-    const int E = x3 ? 4 : 2;
-    const int k = op.ksize, r = k / 2;
+    const int nq = (op.flags & SBC_F_POOL) ? 4 : 1;
+    const int* steptab = reinterpret_cast<const int*>(wseg);
     for (int t = 0; t < nthr; t++) {
-        if (op.dst >= 0) sbc_zero_halo(arena + op.dst, GD, op.cout, t, nthr);
-        if (op.edst >= 0) sbc_zero_halo(arena + op.edst, GD, op.cout, t, nthr);
+        if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, t, nthr);
+        if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, t, nthr);
     }
-    for (int mt = 0; mt < M.MT; mt++)
-        for (int nt = 0; nt < M.NT; nt++) {
+    for (int mt = 0; mt < op.MT; mt++)
+        for (int nt = 0; nt < op.NT; nt++) {
             float D[16][8];
             memset(D, 0, sizeof D);
-            for (int quad = 0; quad < M.nq; quad++) {
-                int s = 0;
-                for (int tap = 0; tap < k * k; tap++) {
-                    if (!((op.tapmask >> tap) & 1)) continue;
-                    const int dy = (tap / k - r) * op.dil, dx = (tap % k - r) * op.dil;
-                    for (int kc = 0; kc < M.KC; kc++, s++) {
-                        float Ah[16][8], Al[16][8], Bh[8][8], Bl[8][8];
-                        for (int lane = 0; lane < 32; lane++) {
-                            const int g = lane >> 2, t = lane & 3;
-                            const int po0 = sbc_mma_row_off(op, M, GS, mt, quad, g);
-                            const int po1 = sbc_mma_row_off(op, M, GS, mt, quad, g + 8);
-                            float a[4];
-                            sbc_mma_a_frag(op, GS, arena, po0, po1, dy, dx, kc, lane, a);
-                            const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
-                            for (int i = 0; i < 4; i++) {
-                                if (x3) {
-                                    Ah[rr[i]][cc[i]] = sbc_tf32_rz(a[i]);
-                                    Al[rr[i]][cc[i]] = sbc_tf32_rz(a[i] - Ah[rr[i]][cc[i]]);
-                                } else {
-                                    Ah[rr[i]][cc[i]] = sbc_tf32_rn(a[i]);
-                                    Al[rr[i]][cc[i]] = 0.f;
-                                }
+            for (int quad = 0; quad < nq; quad++) {
+                for (int s = 0; s < op.S; s++) {
+                    // MMA-index matrices: column kk of A / row kk of B is MMA K index kk
+                    float Ah[16][8], Al[16][8], Bh[8][8], Bl[8][8];
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g = lane >> 2, t = lane & 3;
+                        const int po0 = sbc_mma_row_off(op, GS, mt, quad, g);
+                        const int po1 = sbc_mma_row_off(op, GS, mt, quad, g + 8);
+                        float a[4];
+                        sbc_mma_a_frag(arena + op.src + 2 * t, steptab[s], po0, po1, a);
+                        const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
+                        for (int i = 0; i < 4; i++) {
+                            if (x3) {
+                                Ah[rr[i]][cc[i]] = sbc_tf32_rz(a[i]);
+                                Al[rr[i]][cc[i]] = sbc_tf32_rz(a[i] - Ah[rr[i]][cc[i]]);
+                            } else {
+                                Ah[rr[i]][cc[i]] = sbc_tf32_rn(a[i]);
+                                Al[rr[i]][cc[i]] = 0.f;
                             }
-                            const float* b = wseg + ((size_t)(s * M.NT + nt) * 32 + lane) * E;
-                            Bh[t][g] = b[0]; Bh[t + 4][g] = b[1];
-                            Bl[t][g] = x3 ? b[2] : 0.f; Bl[t + 4][g] = x3 ? b[3] : 0.f;
                         }
-                        for (int m = 0; m < 16; m++)
-                            for (int n = 0; n < 8; n++) {
-                                float d = D[m][n];
-                                if (x3) {
-                                    for (int kk = 0; kk < 8; kk++) d += Al[m][kk] * Bh[kk][n];
-                                    for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bl[kk][n];
-                                }
-                                for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bh[kk][n];
-                                D[m][n] = d;
+                        const float* b = wseg + op.frag_rel + ((size_t)(s * op.NT + nt) * 32 + lane) * 2;
+                        for (int i = 0; i < 2; i++) {
+                            const int kk = t + 4 * i;
+                            if (x3) {
+                                Bh[kk][g] = sbc_tf32_rz(b[i]);
+                                Bl[kk][g] = sbc_tf32_rz(b[i] - Bh[kk][g]);
+                            } else {
+                                Bh[kk][g] = b[i];
+                                Bl[kk][g] = 0.f;
                             }
+                        }
                     }
+                    for (int m = 0; m < 16; m++)
+                        for (int n = 0; n < 8; n++) {
+                            float d = D[m][n];
+                            if (x3) {
+                                for (int kk = 0; kk < 8; kk++) d += Al[m][kk] * Bh[kk][n];
+                                for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bl[kk][n];
+                            }
+                            for (int kk = 0; kk < 8; kk++) d += Ah[m][kk] * Bh[kk][n];
+                            D[m][n] = d;
+                        }
                 }
             }
             for (int lane = 0; lane < 32; lane++) {
                 const int g = lane >> 2, t = lane & 3;
                 const float c[4] = {D[g][2 * t], D[g][2 * t + 1], D[g + 8][2 * t], D[g + 8][2 * t + 1]};
-                sbc_mma_epilogue(op, GD, arena, wseg, mt, nt, lane, c);
+                int pd[2];
+                sbc_mma_dst_off(op, GD, mt, g, pd);
+                sbc_mma_epilogue(op, GD, arena, wseg, pd, mt * 16 + g, nt, lane, c);
             }
         }
 }
 
 static void norm_op(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg, int nthr) {
-    const int C = op.cin, ncg = (C + 3) >> 2, T = sbc_norm_T(op, nthr);
-    std::vector<float> mu(C), m2(C);
+    const int C = op.cin, nq = C >> 2, T = sbc_norm_T(op, nthr);
     const float inv = 1.f / (float)(G.h * G.w);
-    std::vector<SbcF4> means(ncg), m2s(ncg);
-    for (int cg = 0; cg < ncg; cg++) {
+    std::vector<SbcF4> mu(nq), m2s(nq);
+    for (int q = 0; q < nq; q++) {
         SbcF4 sum{0, 0, 0, 0};
         for (int s = 0; s < T; s++) {
-            const SbcF4 v = sbc_norm_partial_sum(op, G, arena, cg, s, T);
+            const SbcF4 v = sbc_norm_partial_sum(op, G, arena, q, s, T);
             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
         SbcF4 mean{sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv};
         SbcF4 tot{0, 0, 0, 0};
         for (int s = 0; s < T; s++) {
-            const SbcF4 v = sbc_norm_partial_m2(op, G, arena, cg, s, T, mean);
+            const SbcF4 v = sbc_norm_partial_m2(op, G, arena, q, s, T, mean);
             tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
         }
-        means[cg] = mean; m2s[cg] = tot;
-        const float mm[4] = {mean.x, mean.y, mean.z, mean.w};
-        for (int j = 0; j < 4; j++)
-            if (4 * cg + j < C) mu[4 * cg + j] = mm[j];
+        mu[q] = mean; m2s[q] = tot;
     }
-    for (int cg = 0; cg < ncg; cg++)
-        for (int s = 0; s < T; s++) sbc_norm_apply(op, G, arena, wseg, mu.data(), cg, s, T, means[cg], m2s[cg]);
-    for (int t = 0; t < nthr; t++) sbc_zero_halo(arena + op.dst, G, C, t, nthr);
+    for (int q = 0; q < nq; q++)
+        for (int s = 0; s < T; s++)
+            sbc_norm_apply(op, G, arena, wseg, reinterpret_cast<const float*>(mu.data()), q, s, T, mu[q], m2s[q]);
+    if (op.flags & SBC_F_ZH_DST)
+        for (int t = 0; t < nthr; t++) sbc_zero_halo(arena + op.dst, G, C, t, nthr);
 }
 
 extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t* geo_table, const float* blob,
@@ -140,17 +143,16 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t
 }
 
 // one Langevin step after the network has run (net_out already in the arena)
-extern "C" float emu_langevin_step(float* arena, const int32_t* geo_table, int in_off, int out_off, int post_off,
+extern "C" float emu_langevin_step(float* arena, int in_off, int out_off, int post_off,
                                    const float* P, const float* Y, const float* Hor, const float* ext_noise,
                                    float sigma, float alpha, float den, float nscale, uint64_t seed, uint64_t sid,
                                    uint32_t gstep, int Nt, int Nr, int Np, int nthr) {
-    const SbcGeo& G = reinterpret_cast<const SbcGeo*>(geo_table)[0];
     SbcStepScalars sc{sigma, alpha, den, nscale};
     float* res = arena + post_off;
-    for (int t = 0; t < nthr; t++) sbc_dc_residual(arena + in_off, G, res, P, Y, Nt, Nr, Np, t, nthr);
+    for (int t = 0; t < nthr; t++) sbc_dc_residual(arena + in_off, res, P, Y, Nt, Nr, Np, t, nthr);
     float tot = 0.f;
     for (int t = 0; t < nthr; t++)
-        tot += sbc_langevin_update(arena + in_off, arena + out_off, G, res, P, Hor, ext_noise, sc, seed, sid, gstep, Nt,
+        tot += sbc_langevin_update(arena + in_off, arena + out_off, res, P, Hor, ext_noise, sc, seed, sid, gstep, Nt,
                                    Nr, Np, t, nthr);
     return tot;
 }

@@ -115,7 +115,38 @@ def golden_ald(name, ngf, wseed, B, Np, snr_db, levels, steps_each, alpha_step, 
     print(name, "nmse per step (mean over batch)", nmse.mean(1))
 
 
+def golden_real_checkpoint(name="real_ckpt_forward.npz"):
+    """The SHIPPED checkpoint (pretrained_models/score-deepest-cdl-c.pt) on the first shipped CDL-C validation
+    channels at six noise levels: reference module output in fp32 and in fp64.  With trained weights the
+    output at small sigma is an ill-conditioned difference (fp32 vs fp64 differ by up to 3.5e-4 relative), so
+    parity tests bound the error of an implementation by a multiple of the reference's own fp32 error."""
+    from score_based_channels_b200 import entry_common as ec, hdf5_min
+    contents = ec.load_checkpoint("/root/reference/pretrained_models/score-deepest-cdl-c.pt")
+    h = hdf5_min.loadmat_v73("/root/reference/sample_data/CDL-C_Nt64_Nr16_ULA0.50_seed4321.mat")["output_h"]
+    h = h[:6, 0].astype(np.complex64)
+    Hn = np.conj(np.transpose(h, (0, 2, 1))) / 0.363263
+    labels = np.array([0, 500, 1000, 1500, 2000, 2310])
+    sig = contents["model_state"]["sigmas"].numpy()
+    rng = np.random.default_rng(0)
+    x = Hn + sig[labels][:, None, None] * ((rng.standard_normal(Hn.shape) + 1j * rng.standard_normal(Hn.shape)) / np.sqrt(2))
+    xr = np.stack([x.real, x.imag], 1).astype(np.float32)
+    cfg = contents["config"]
+    cfg.device = "cpu"
+    m = NCSNv2Deepest(cfg)
+    print(m.load_state_dict(contents["model_state"]))
+    m.eval()
+    with torch.no_grad():
+        o32 = m(torch.from_numpy(xr), torch.from_numpy(labels)).numpy()
+        torch.set_default_dtype(torch.float64)      # MSFBlock allocates its accumulator with the default dtype
+        o64 = m.double()(torch.from_numpy(xr).double(), torch.from_numpy(labels)).numpy()
+        torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, name), x=xr, y=labels, out32=o32, out64=o64)
+    rel = [float(np.linalg.norm(o32[b] - o64[b]) / np.linalg.norm(o64[b])) for b in range(6)]
+    print(name, "reference fp32 vs fp64 relative error per sample", rel)
+
+
 if __name__ == "__main__":
+    golden_real_checkpoint()
     golden_forward("forward_ngf8.npz", 8, 1, 64, 16, [0, 1000, 2310, 17, 2000], [27.0, 0.5, 1.0, 10.0, 0.05])
     golden_forward("forward_ngf8_32x8.npz", 8, 2, 32, 8, [5, 1500], [20.0, 1.0])
     golden_forward("forward_ngf16.npz", 16, 3, 64, 16, [0, 2310], [27.0, 1.0])

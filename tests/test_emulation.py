@@ -27,7 +27,7 @@ def emu():
     lib = C.CDLL(so)
     lib.emu_run_program.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.emu_langevin_step.restype = C.c_float
-    lib.emu_langevin_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+    lib.emu_langevin_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_uint64,
                                       C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_noise.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
@@ -37,7 +37,7 @@ def emu():
 def run_emu(lib, prog, x, stop=-1):
     # garbage-filled arena: every op must (re)establish the zero halos it relies on
     arena = np.random.default_rng(5).standard_normal(prog.arena_floats).astype(np.float32) * 100
-    prog.write(arena, prog.in_off, np.asarray(x, np.float32))
+    prog.write_input(arena, np.asarray(x, np.float32))
     tab = np.ascontiguousarray(prog.op_table())
     geo = np.ascontiguousarray(prog.geo_table())
     rc = lib.emu_run_program(tab.ctypes.data, tab.shape[0], geo.ctypes.data, prog.blob.ctypes.data, arena.ctypes.data,
@@ -60,7 +60,7 @@ def test_emulated_forward_matches_reference_golden(emu, name, H, W, prec):
     sig = sd["sigmas"]
     for b in range(g["x"].shape[0]):
         arena = run_emu(emu, prog, g["x"][b])
-        out = prog.read(arena, prog.out_off, 2, H, W) / sig[int(g["y"][b])]
+        out = prog.read_output(arena) / sig[int(g["y"][b])]
         rel = np.linalg.norm(out - g["out"][b]) / np.linalg.norm(g["out"][b])
         assert rel < FWD_TOL[prec], (name, b, rel)
 
@@ -76,6 +76,10 @@ def test_emulated_ops_match_simulator_op_by_op(emu, prec):
         _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
         ea = run_emu(emu, prog, x, stop=k)
         op = prog.ops[k - 1]
+        if op.flags & program.F_COMPACT:
+            e, r = prog.read_output(ea), prog.read_output(ra.numpy())
+            assert np.abs(e - r).max() / (np.abs(r).max() + 1e-6) < 5e-5, (k - 1, op.name)
+            continue
         for off in (op.dst, op.acc, op.edst):
             if off >= 0:
                 e = prog.read(ea, off, op.cout, op.oh, op.ow)
@@ -100,12 +104,11 @@ def test_emulated_langevin_step_matches_oracle(emu):
     arena = run_emu(emu, prog, xr)
     P = np.ascontiguousarray(g["P"][b]); Y = np.ascontiguousarray(g["Y"][b]); H = np.ascontiguousarray(g["H"][b])
     en = np.ascontiguousarray(g["ext_noise"][0, b])
-    geo = np.ascontiguousarray(prog.geo_table())
-    tot = emu.emu_langevin_step(arena.ctypes.data, geo.ctypes.data, prog.in_off, prog.out_off, prog.post_off, P.ctypes.data,
+    tot = emu.emu_langevin_step(arena.ctypes.data, prog.in_off, prog.out_off, prog.post_off, P.ctypes.data,
                                 Y.ctypes.data, H.ctypes.data, en.ctypes.data, sigma, alpha, den, nscale, 0, 0, 0, Nt,
                                 Nr, Np, prog.nthreads)
-    xv = prog.read(arena, prog.in_off, 2, Nt, Nr)
-    x1 = xv[0] + 1j * xv[1]
+    xv = arena[prog.in_off:prog.in_off + 2 * Nt * Nr].reshape(Nt, Nr, 2)
+    x1 = xv[..., 0] + 1j * xv[..., 1]
     ref = g["xs"][0, b]
     assert np.abs(x1 - ref).max() < 1e-5 * np.abs(ref).max()
     nm = tot / np.sum(np.abs(H) ** 2)

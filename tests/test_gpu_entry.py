@@ -50,23 +50,27 @@ def test_tune_hparams_entry_point_small(tmp_path, monkeypatch):
 
 
 @need
-def test_real_checkpoint_forward_matches_oracle():
-    """Shipped weights (ngf=8), shipped channels: fused forward vs the CPU oracle at three noise levels."""
-    from oracle import oracle as orc
-    from score_based_channels_b200 import entry_common as ec, hdf5_min
+def test_real_checkpoint_forward_matches_reference_golden():
+    """Shipped weights (ngf=8), shipped channels, six noise levels: fused forward vs the reference module's own
+    output (tests/golden/real_ckpt_forward.npz, made by tests/golden/make_golden.py).  With trained weights the
+    output at small sigma is an ill-conditioned difference: the reference's OWN fp32 output deviates from its
+    fp64 output by e32 = 1.4e-6 ... 3.5e-4 (relative L2).  Tolerances, per sample, on the error vs the fp64
+    reference: fp32-equivalent mode (tf32x3) <= 3 * e32 + 2e-6; TF32 mode <= 4096 * e32 (unit roundoff ratio
+    2^13, half of it) and <= 6e-3 wherever the problem is well conditioned (e32 < 5e-6)."""
+    from conftest import GOLDEN
+    from score_based_channels_b200 import entry_common as ec
     dev = torch.device("cuda:0")
+    g = np.load(os.path.join(GOLDEN, "real_ckpt_forward.npz"))
     contents = ec.load_checkpoint(CKPT)
-    sd = {k: v.numpy() for k, v in contents["model_state"].items()}
-    h = hdf5_min.loadmat_v73(MAT)["output_h"][:6, 0].astype(np.complex64)
-    Hn = np.conj(np.transpose(h, (0, 2, 1))) / 0.363263
-    labels = np.array([0, 500, 1000, 1500, 2000, 2310])
-    rng = np.random.default_rng(0)
-    x = Hn + sd["sigmas"][labels][:, None, None] * ((rng.standard_normal(Hn.shape) + 1j * rng.standard_normal(Hn.shape)) / np.sqrt(2))
-    xr = np.stack([x.real, x.imag], 1).astype(np.float32)
-    ref = orc.OracleNet(sd, 8, 64, 16).forward(xr, labels)
-    for prec, tol in (("tf32x3", 2e-5), ("tf32", 6e-3)):
+    rel = lambda a, b: float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
+    for prec in ("tf32x3", "tf32"):
         m = ec.build_model(contents["config"], contents["model_state"], dev, prec)
-        out = m(torch.from_numpy(xr).to(dev), torch.from_numpy(labels).to(dev)).cpu().numpy()
-        for b in range(6):
-            rel = np.linalg.norm(out[b] - ref[b]) / np.linalg.norm(ref[b])
-            assert rel < tol, (prec, b, rel)
+        out = m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)).cpu().numpy().astype(np.float64)
+        for b in range(out.shape[0]):
+            e32, e = rel(g["out32"][b].astype(np.float64), g["out64"][b]), rel(out[b], g["out64"][b])
+            if prec == "tf32x3":
+                assert e <= 3 * e32 + 2e-6, (prec, b, e, e32)
+            else:
+                assert e <= 4096 * e32, (prec, b, e, e32)
+                if e32 < 5e-6:
+                    assert e < 6e-3, (prec, b, e)
