@@ -38,6 +38,7 @@ struct SbcModel {
     int first_w = -1;
     bool arena_in_smem = false;
     bool stage = false;
+    bool x3 = false;               // every conv of the program uses the 3xTF32 product
     size_t smem_bytes = 0;
     long long launches = 0;
     long long* d_prof = nullptr;   // optional per-op clock stamps (sbc_set_profile_buffer)
@@ -80,7 +81,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     // validate + annotate the op table (pad0 := index of the next op that has parameters)
     std::vector<SbcOp> ops(desc->n_ops);
     memcpy(ops.data(), desc->op_table, sizeof(SbcOp) * (size_t)desc->n_ops);
-    int next = -1;
+    int next = -1, nconv = 0;
     for (int i = desc->n_ops - 1; i >= 0; i--) {
         SbcOp& o = ops[i];
         o.next_w = next;
@@ -102,6 +103,9 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
                             o.S >= 1 && o.frag_rel >= o.S && o.frag_rel % 4 == 0 &&
                             o.frag_rel + o.S * o.NT * 32 * E <= o.w_len;
             if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported tensor-core conv", i); }
+            const bool ox3 = (o.flags & SBC_F_X3) != 0;
+            if (nconv++ == 0) m->x3 = ox3;
+            else if (m->x3 != ox3) { delete m; return sbc_fail(SBC_E_ARG, "op %d: mixed conv precisions", i); }
         }
         if ((o.kind == SBC_OP_NORM_ELU || o.kind == SBC_OP_ELU || o.kind == SBC_OP_MAXPOOL5 || o.kind == SBC_OP_UPACC) &&
             o.cin % 8) { delete m; return sbc_fail(SBC_E_ARG, "op %d: channel count must be a multiple of 8", i); }
@@ -118,7 +122,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
 
     // where do activations live, and are parameters staged through shared memory?
     cudaFuncAttributes fa{};
-    SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true>));
+    SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true, true>));
     const int dyn_max = m->smem_optin - (int)fa.sharedSizeBytes;   // opt-in limit covers static + dynamic
     const size_t arena_bytes = (size_t)desc->arena_floats * 4;
     const size_t misc = 64;
@@ -136,8 +140,10 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
     m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr; m->d.geo_table = nullptr;   // host pointers are not retained
 
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     *handle_out = m;
     return SBC_OK;
 }
@@ -176,6 +182,7 @@ static void fill_common(const SbcModel* m, SbcLaunch& L) {
     L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
     L.gws = m->d_gws; L.stage_weights = m->stage ? 1 : 0; L.debug_stop = -1;
     L.prof = m->d_prof;
+    L.dbg = env_int("SBC_DBG", 0);
 }
 
 static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
@@ -183,10 +190,13 @@ static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
     const int grid = L.B < m->num_sms ? L.B : m->num_sms;
     size_t smem = m->smem_bytes;
     if (L.debug_stop >= 0) L.stage_weights = 0;   // debug runs read parameters straight from global memory
-    if (m->arena_in_smem)
-        sbc_ald_kernel<true><<<grid, SBC_NTHREADS, smem, st>>>(L);
-    else
-        sbc_ald_kernel<false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+    if (m->arena_in_smem) {
+        if (m->x3) sbc_ald_kernel<true, true><<<grid, SBC_NTHREADS, smem, st>>>(L);
+        else sbc_ald_kernel<true, false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+    } else {
+        if (m->x3) sbc_ald_kernel<false, true><<<grid, SBC_NTHREADS, smem, st>>>(L);
+        else sbc_ald_kernel<false, false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+    }
     SBC_CUDA(cudaGetLastError());
     m->launches++;
     return SBC_OK;

@@ -54,6 +54,8 @@ struct SbcLaunch {
     int stage_weights;       // 1: cp.async.bulk double buffering, 0: read parameters from global/L2
     int debug_stop;          // >=0: stop sample 0 / step 0 before op `debug_stop`, dump the arena
     float* debug_out;
+    int dbg;                 // timing experiments only (env SBC_DBG): 1 skip K loops, 2 skip conv epilogues,
+                             // 4 skip non-conv op bodies, 16 skip every op body (results are garbage)
     long long* prof;         // optional [n_ops+2] clock64() stamps of CTA 0, first sample, first step
 };
 
@@ -95,9 +97,10 @@ __device__ __forceinline__ void sbc_bulk_g2s(void* dst_smem, const void* src_gme
 // tensor-core conv (SBC_OP_CONV_MMA): warp-level implicit GEMM on mma.sync m16n8k8 TF32.
 //   X3 = true : 3xTF32 split  (a = a_hi + a_lo, b = b_hi + b_lo;  D += a_lo b_hi + a_hi b_lo + a_hi b_hi)
 //               -> fp32-equivalent accuracy (the parity mode);  X3 = false: TF32 operands (cvt.rna).
-// The K loop is the hot loop of the whole sampler; per K step and 16-pixel tile it issues 2 LDS.64 (A), the
-// operand split (8 ALU ops in X3 mode, 4 cvt otherwise) and the MMAs -- the tensor pipe (512 TF32 MAC/clk/SM
-// through mma.sync) is the binding unit, everything else fits in its shadow.
+// The K loop is the hot loop of the whole sampler.  Per K step and 16-pixel tile it issues one ldmatrix.x4 (the
+// whole A fragment, shared-memory arena), the operand split (8 ALU ops in X3 mode, 4 cvt otherwise) and the
+// MMAs -- the tensor pipe (mma.sync TF32: one m16n8k8 per 8 cycles per SM sub-partition) is the binding unit.
+// The tensor core ignores the low 13 mantissa bits of a TF32 operand, so a_hi / b_hi are passed unmasked.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sbc_mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
     asm volatile(
@@ -111,14 +114,61 @@ __device__ __forceinline__ float sbc_cvt_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ void sbc_ldmatrix_x4(float (&a)[4], uint32_t saddr) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(saddr));
+    a[0] = __uint_as_float(r0); a[1] = __uint_as_float(r1); a[2] = __uint_as_float(r2); a[3] = __uint_as_float(r3);
+}
+
+// Per-lane A addressing of one warp for one conv op.
+//   SMEM: sbase = shared address of (src plane 0, channel half lane>>4); po[j][0] = byte offset of pixel row
+//         lane & 15 of slot j (ldmatrix row address)
+//   else: gsrc = arena + op.src + t; po[j][0/1] = float offsets of pixel rows g / g + 8
+template <bool SMEM>
+struct SbcALane {
+    uint32_t sbase;
+    const float* gsrc;
+    __device__ __forceinline__ SbcALane(const SbcOp& op, float* arena, int lane) {
+        if (SMEM) { sbase = sbc_smem_u32(arena + op.src) + (uint32_t)(lane >> 4) * 16u; gsrc = nullptr; }
+        else { sbase = 0; gsrc = arena + op.src + (lane & 3); }
+    }
+    __device__ __forceinline__ void rows(const SbcOp& op, const SbcGeo& GS, int mt, int quad, int lane, int (&po)[2]) const {
+        if (SMEM) {
+            po[0] = sbc_mma_row_off(op, GS, mt, quad, lane & 15) * 4;
+            po[1] = 0;
+        } else {
+            po[0] = sbc_mma_row_off(op, GS, mt, quad, lane >> 2);
+            po[1] = sbc_mma_row_off(op, GS, mt, quad, (lane >> 2) + 8);
+        }
+    }
+    __device__ __forceinline__ void frag(int off, const int (&po)[2], float (&a)[4]) const {
+        if (SMEM) sbc_ldmatrix_x4(a, sbase + (uint32_t)(off * 4 + po[0]));
+        else sbc_mma_a_frag(gsrc, off, po[0], po[1], a);
+    }
+};
 
 // Accumulate K steps [s0, s1) for NS pixel-tile slots (row offsets po[j]) and NN cout tiles that share each
-// gathered A fragment.  asrc = arena + op.src + 2*t; bfrag = first B fragment of this lane for cout tile nt0;
-// bstride = floats per K step in the fragment array.
-template <bool X3, int NS, int NN>
-__device__ __forceinline__ void sbc_mma_pass(const float* __restrict__ asrc, const int (&po)[NS][2],
+// gathered A fragment.  bfrag = first B fragment of this lane for cout tile nt0; bstride = floats per K step in
+// the fragment array.  A dependent mma.sync chain advances one link per ~HMMA latency, far slower than the pipe
+// rate, so when a warp owns fewer than 4 (tile, cout tile) accumulators the three 3xTF32 terms (resp. even / odd
+// K steps in TF32 mode) go to separate accumulator copies that are summed at the end.
+template <bool X3, bool SMEM, int NS, int NN>
+__device__ __forceinline__ void sbc_mma_pass(const SbcALane<SMEM>& A, const int (&po)[NS][2],
                                              const int* __restrict__ steptab, const float* __restrict__ bfrag,
                                              int bstride, int s0, int s1, float (&acc)[NS][NN][4]) {
+    constexpr bool SPLIT = NS * NN < 4;
+    constexpr int NC = SPLIT ? (X3 ? 3 : 2) : 1;
+    float accx[NC > 1 ? NC - 1 : 1][NS][NN][4];
+    if (SPLIT) {
+#pragma unroll
+        for (int c = 0; c < NC - 1; c++)
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int n = 0; n < NN; n++) accx[c][j][n][0] = accx[c][j][n][1] = accx[c][j][n][2] = accx[c][j][n][3] = 0.f;
+    }
 #pragma unroll 1
     for (int s = s0; s < s1; s++) {
         const int off = steptab[s];
@@ -127,115 +177,140 @@ __device__ __forceinline__ void sbc_mma_pass(const float* __restrict__ asrc, con
 #pragma unroll
         for (int n = 0; n < NN; n++) {
             const float2 b = *reinterpret_cast<const float2*>(bp + n * 64);
-            if (X3) {   // w = hi + lo exactly; the tensor core truncates lo to its leading 11 bits
-                bh[n][0] = __uint_as_float(__float_as_uint(b.x) & 0xFFFFE000u);
-                bh[n][1] = __uint_as_float(__float_as_uint(b.y) & 0xFFFFE000u);
-                bl[n][0] = b.x - bh[n][0]; bl[n][1] = b.y - bh[n][1];
-            } else {    // pre-rounded to TF32 by the packer
-                bh[n][0] = b.x; bh[n][1] = b.y; bl[n][0] = bl[n][1] = 0.f;
+            bh[n][0] = b.x; bh[n][1] = b.y;       // X3: plain fp32 (hi part = what the tensor core reads of it)
+            if (X3) {                              // w = hi + lo exactly; the tensor core truncates lo to 11 bits
+                bl[n][0] = b.x - __uint_as_float(__float_as_uint(b.x) & 0xFFFFE000u);
+                bl[n][1] = b.y - __uint_as_float(__float_as_uint(b.y) & 0xFFFFE000u);
+            } else {
+                bl[n][0] = bl[n][1] = 0.f;
             }
         }
         float ah[NS][4], al[NS][4];
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            float a[4];
-            sbc_mma_a_frag(asrc, off, po[j][0], po[j][1], a);
+            A.frag(off, po[j], ah[j]);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (X3) {
-                    ah[j][i] = __uint_as_float(__float_as_uint(a[i]) & 0xFFFFE000u);   // a = ah + al exactly
-                    al[j][i] = a[i] - ah[j][i];                                          // tensor core truncates al
-                } else {
-                    ah[j][i] = sbc_cvt_tf32(a[i]);
-                }
+                if (X3) al[j][i] = ah[j][i] - __uint_as_float(__float_as_uint(ah[j][i]) & 0xFFFFE000u);
+                else ah[j][i] = sbc_cvt_tf32(ah[j][i]);
             }
         }
         if (X3) {   // small terms first; term-major order keeps dependent MMAs NS*NN apart
 #pragma unroll
             for (int j = 0; j < NS; j++)
 #pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], al[j], bh[n][0], bh[n][1]);
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[0][j][n] : acc[j][n], al[j], bh[n][0], bh[n][1]);
 #pragma unroll
             for (int j = 0; j < NS; j++)
 #pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bl[n][0], bl[n][1]);
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[1][j][n] : acc[j][n], ah[j], bl[n][0], bl[n][1]);
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
+        } else if (SPLIT) {
+            if ((s - s0) & 1) {
+#pragma unroll
+                for (int j = 0; j < NS; j++)
+#pragma unroll
+                    for (int n = 0; n < NN; n++) sbc_mma_tf32(accx[0][j][n], ah[j], bh[n][0], bh[n][1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NS; j++)
+#pragma unroll
+                    for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
         }
+    }
+    if (SPLIT) {
 #pragma unroll
         for (int j = 0; j < NS; j++)
 #pragma unroll
-            for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
+            for (int n = 0; n < NN; n++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float small = accx[0][j][n][i];
+                    if (NC > 2) small += accx[NC - 2][j][n][i];
+                    acc[j][n][i] += small;
+                }
     }
 }
 
 // one pass of a warp over NS tiles (mt0, mt0 + mstride, ...; only the first `ntile` are real) x NN cout tiles
-template <bool X3, int NS, int NN>
+template <bool X3, bool SMEM, int NS, int NN>
 __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
-                                               const float* wseg, const float* asrc, const float* bfrag, int bstride,
-                                               int mt0, int mstride, int ntile, int nt0, int lane) {
-    const int g = lane >> 2;
+                                               const float* wseg, const SbcALane<SMEM>& A, const float* bfrag,
+                                               int bstride, int mt0, int mstride, int ntile, int nt0, int lane,
+                                               long long* stamp) {
     int po[NS][2];
 #pragma unroll
-    for (int j = 0; j < NS; j++) {
-        const int mt = mt0 + (j < ntile ? j : 0) * mstride;
-        po[j][0] = sbc_mma_row_off(op, GS, mt, 0, g);
-        po[j][1] = sbc_mma_row_off(op, GS, mt, 0, g + 8);
-    }
+    for (int j = 0; j < NS; j++) A.rows(op, GS, mt0 + (j < ntile ? j : 0) * mstride, 0, lane, po[j]);
     float acc[NS][NN][4];
 #pragma unroll
     for (int j = 0; j < NS; j++)
 #pragma unroll
         for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
-    sbc_mma_pass<X3, NS, NN>(asrc, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, 0, op.S, acc);
-    const int P = op.oh * op.ow;
+    if (stamp) stamp[1] = clock64();
+    sbc_mma_pass<X3, SMEM, NS, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, 0, op.S, acc);
+    if (stamp) stamp[2] = clock64();
+    const SbcEpi e = sbc_epi(op, GD);
 #pragma unroll
     for (int j = 0; j < NS; j++)
-        if (j < ntile) {   // stride-1 conv: source and destination geometry coincide, so do the pixel offsets
-            const int q0 = (mt0 + j * mstride) * 16 + g;
-            const int pd[2] = {q0 < P ? po[j][0] : -1, q0 + 8 < P ? po[j][1] : -1};
+        if (j < ntile) {
+            const int mt = mt0 + j * mstride;
+            int pd[2];
+            sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
 #pragma unroll
-            for (int n = 0; n < NN; n++) sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0 + n, lane, acc[j][n]);
+            for (int n = 0; n < NN; n++)
+                sbc_mma_epilogue(e, arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt0 + n, lane, acc[j][n][0],
+                                 acc[j][n][1], acc[j][n][2], acc[j][n][3]);
         }
 }
 
 // ConvMeanPool: one output tile, the four pooling positions are the four slots
-template <bool X3, int NN>
-__device__ __forceinline__ void sbc_conv_pooled(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
-                                                const float* wseg, const float* asrc, const float* bfrag, int bstride,
-                                                int mt, int nt0, int s0, int s1, int lane, float (&c)[NN][4]) {
-    const int g = lane >> 2;
+template <bool X3, bool SMEM, int NN>
+__device__ __forceinline__ void sbc_conv_pooled(const SbcOp& op, const SbcGeo& GS, const float* wseg,
+                                                const SbcALane<SMEM>& A, const float* bfrag, int bstride, int mt,
+                                                int s0, int s1, int lane, float (&c)[NN][4]) {
     int po[4][2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        po[j][0] = sbc_mma_row_off(op, GS, mt, j, g);
-        po[j][1] = sbc_mma_row_off(op, GS, mt, j, g + 8);
-    }
+    for (int j = 0; j < 4; j++) A.rows(op, GS, mt, j, lane, po[j]);
     float acc[4][NN][4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
-    sbc_mma_pass<X3, 4, NN>(asrc, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, s0, s1, acc);
+    sbc_mma_pass<X3, SMEM, 4, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, s0, s1, acc);
 #pragma unroll
     for (int n = 0; n < NN; n++)
 #pragma unroll
         for (int i = 0; i < 4; i++) c[n][i] = (acc[0][n][i] + acc[1][n][i]) + (acc[2][n][i] + acc[3][n][i]);
 }
 
-template <bool X3>
-__device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
-                                             const float* wseg, int tid) {
+template <bool X3, bool SMEM>
+__device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS, const SbcGeo& GD, float* arena,
+                                             const float* wseg, int tid, long long* stamp, int dbg) {
+    SbcOp op = op_;
+    if (dbg & 1) op.S = 0;                                      // timing experiment: no K steps
+    if (dbg & 2) { op.dst = op.acc = op.edst = -1; op.flags &= ~SBC_F_COMPACT; }   // timing experiment: no stores
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = SBC_NTHREADS / 32;
     constexpr int E = 2;   // floats per lane per B fragment
     const bool pool = (op.flags & SBC_F_POOL) != 0;
-    // fresh outputs get their halo re-zeroed (the arena region may have held another tensor)
+    // fresh outputs get their halo re-zeroed when the planner could not prove it clean
     if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, tid, SBC_NTHREADS);
     if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, tid, SBC_NTHREADS);
 
     const int MT = op.MT, NT = op.NT, S = op.S;
-    const float* asrc = arena + op.src + 2 * (lane & 3);
+    const SbcALane<SMEM> A(op, arena, lane);
     const int bstride = NT * 32 * E;
     const float* bf0 = wseg + op.frag_rel + lane * E;
+    if (stamp) stamp[0] = clock64();
 
     if (op.ks > 1) {
         // fewer (pixel tile, cout tile) units than warps: `ks` (a power of two) warps split the K steps of one
@@ -249,12 +324,12 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
             const int s0 = (S * kp) >> lks, s1 = (S * (kp + 1)) >> lks;
             float c[1][4];
             if (pool) {
-                sbc_conv_pooled<X3, 1>(op, GS, GD, arena, wseg, asrc, bf0 + nt * 32 * E, bstride, mt, nt, s0, s1, lane, c);
+                sbc_conv_pooled<X3, SMEM, 1>(op, GS, wseg, A, bf0 + nt * 32 * E, bstride, mt, s0, s1, lane, c);
             } else {
-                const int g = lane >> 2;
-                int po[1][2] = {{sbc_mma_row_off(op, GS, mt, 0, g), sbc_mma_row_off(op, GS, mt, 0, g + 8)}};
+                int po[1][2];
+                A.rows(op, GS, mt, 0, lane, po[0]);
                 float acc[1][1][4] = {{{0.f, 0.f, 0.f, 0.f}}};
-                sbc_mma_pass<X3, 1, 1>(asrc, po, reinterpret_cast<const int*>(wseg), bf0 + nt * 32 * E, bstride, s0, s1, acc);
+                sbc_mma_pass<X3, SMEM, 1, 1>(A, po, reinterpret_cast<const int*>(wseg), bf0 + nt * 32 * E, bstride, s0, s1, acc);
                 c[0][0] = acc[0][0][0]; c[0][1] = acc[0][0][1]; c[0][2] = acc[0][0][2]; c[0][3] = acc[0][0][3];
             }
             part[warp * 32 + lane] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
@@ -268,12 +343,13 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
             }
             int pd[2];
             sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
-            sbc_mma_epilogue(op, GD, arena, wseg, pd, mt * 16 + (lane >> 2), nt, lane, c);
+            sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0], c[1], c[2], c[3]);
         }
         return;
     }
 
     if (pool) {
+        const SbcEpi e = sbc_epi(op, GD);
         for (int mt = warp; mt < MT; mt += NW) {
             int pd[2];
             sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
@@ -281,13 +357,13 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
             for (int nt0 = 0; nt0 < NT; nt0 += 2) {
                 if (NT - nt0 >= 2) {
                     float c[2][4];
-                    sbc_conv_pooled<X3, 2>(op, GS, GD, arena, wseg, asrc, bf0 + nt0 * 32 * E, bstride, mt, nt0, 0, S, lane, c);
-                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0, lane, c[0]);
-                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0 + 1, lane, c[1]);
+                    sbc_conv_pooled<X3, SMEM, 2>(op, GS, wseg, A, bf0 + nt0 * 32 * E, bstride, mt, 0, S, lane, c);
+                    sbc_mma_epilogue(e, arena, wseg, pd[0], pd[1], q0, nt0, lane, c[0][0], c[0][1], c[0][2], c[0][3]);
+                    sbc_mma_epilogue(e, arena, wseg, pd[0], pd[1], q0, nt0 + 1, lane, c[1][0], c[1][1], c[1][2], c[1][3]);
                 } else {
                     float c[1][4];
-                    sbc_conv_pooled<X3, 1>(op, GS, GD, arena, wseg, asrc, bf0 + nt0 * 32 * E, bstride, mt, nt0, 0, S, lane, c);
-                    sbc_mma_epilogue(op, GD, arena, wseg, pd, q0, nt0, lane, c[0]);
+                    sbc_conv_pooled<X3, SMEM, 1>(op, GS, wseg, A, bf0 + nt0 * 32 * E, bstride, mt, 0, S, lane, c);
+                    sbc_mma_epilogue(e, arena, wseg, pd[0], pd[1], q0, nt0, lane, c[0][0], c[0][1], c[0][2], c[0][3]);
                 }
             }
         }
@@ -303,14 +379,14 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op, const SbcGeo& GS, 
             const float* bf = bf0 + nt0 * 32 * E;
             const bool two = NT - nt0 >= 2;
             if (ntile == 1) {
-                if (two) sbc_conv_tiles<X3, 1, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
-                else sbc_conv_tiles<X3, 1, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                if (two) sbc_conv_tiles<X3, SMEM, 1, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, 1, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             } else if (ntile == 2) {
-                if (two) sbc_conv_tiles<X3, 2, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
-                else sbc_conv_tiles<X3, 2, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                if (two) sbc_conv_tiles<X3, SMEM, 2, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, 2, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             } else {
-                if (two) sbc_conv_tiles<X3, 4, 2>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
-                else sbc_conv_tiles<X3, 4, 1>(op, GS, GD, arena, wseg, asrc, bf, bstride, mt0, NW, ntile, nt0, lane);
+                if (two) sbc_conv_tiles<X3, SMEM, 4, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, 4, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             }
         }
     }
@@ -336,14 +412,13 @@ __device__ __forceinline__ void sbc_norm_op(const SbcOp& op, const SbcGeo& G, fl
                                             int tid) {
     constexpr int NW = SBC_NTHREADS / 32;
     const int C = op.cin, nq = C >> 2;
-    const int T = sbc_norm_T(op, SBC_NTHREADS), lT = 31 - __clz(T);
+    const int T = op.MT, lT = op.NT, npass = op.S;      // host-derived (program.py:norm_elu)
     const int gpp = SBC_NTHREADS >> lT, wpg = T >> 5;   // quads / pass, warps / quad
-    const int npass = (nq + gpp - 1) / gpp;
     const int warp = tid >> 5, lane = tid & 31;
     SbcF4* red = reinterpret_cast<SbcF4*>(arena + op.scratch);
     SbcF4* mu4 = red + 2 * NW;
     SbcF4* m24 = mu4 + nq;
-    const float inv = 1.f / (float)(G.h * G.w);
+    const float inv = __int_as_float(op.frag_rel);      // 1 / (h*w)
     const int s = tid & (T - 1), w0 = (tid >> lT) * wpg;
     const SbcF4 z{0.f, 0.f, 0.f, 0.f};
     SbcF4 mean = z, m2 = z;
@@ -394,7 +469,7 @@ __device__ __forceinline__ float sbc_block_sum(float v, float* red, int tid) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool SMEM_ARENA>
+template <bool SMEM_ARENA, bool X3>
 __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_constant__ SbcLaunch L) {
     extern __shared__ __align__(128) unsigned char sbc_smem_raw[];
     float* smem_f = reinterpret_cast<float*>(sbc_smem_raw);
@@ -413,9 +488,10 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
     __shared__ float s_hnorm;
     __shared__ SbcStepScalars s_sc;
     __shared__ float s_red[SBC_NTHREADS / 32];
-    // op records are prefetched global -> shared one op ahead (warp 0, one word per lane), so that decoding an
-    // op never waits on global memory
-    __shared__ __align__(16) SbcOp s_ops[2];
+    // op records are prefetched global -> shared TWO ops ahead (warp 0, one word per lane; the word loaded
+    // during op i is parked in a register and stored at the start of op i+1), so that neither decoding an op
+    // nor the barrier that ends a short op ever waits on global memory
+    __shared__ __align__(16) SbcOp s_ops[4];
 
     // parameter segments are staged into the (shared-memory) arena with cp.async.bulk one op ahead
     const bool stage = SMEM_ARENA && L.stage_weights != 0;
@@ -424,7 +500,13 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         sbc_mbar_init(&bars[1], 1);
         sbc_fence_barrier_init();
     }
-    if (tid < 32) reinterpret_cast<int*>(&s_ops[0])[tid] = reinterpret_cast<const int*>(L.ops)[tid];
+    int pend = 0;                             // warp 0: word `tid` of the op record two ops ahead
+    if (tid < 32) {
+        const int* o32 = reinterpret_cast<const int*>(L.ops);
+        reinterpret_cast<int*>(&s_ops[0])[tid] = o32[tid];
+        reinterpret_cast<int*>(&s_ops[1])[tid] = o32[(L.n_ops > 1 ? 32 : 0) + tid];
+        pend = o32[(2 % L.n_ops) * 32 + tid];
+    }
     __syncthreads();
 
     const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
@@ -483,16 +565,17 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             }
 
             // ---------------- the network: walk the layer program ----------------
-            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && b == 0 && gs == 0 && tid == 0;
+            // stamps of CTA 0, first sample, second step when there is one (warm instruction cache)
+            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && b == 0 && gs == (nsteps > 1 ? 1 : 0) && tid == 0;
             for (int i = 0; i < L.n_ops; i++, opc++) {
                 if (L.debug_stop >= 0 && i == L.debug_stop) break;
                 if (do_prof) L.prof[i] = clock64();
-                const SbcOp op = s_ops[opc & 1u];
-                // prefetch the next op record (wraps into the next forward)
-                int nxt = 0;
-                if (tid < 32) {
-                    const int j = (i + 1 < L.n_ops) ? i + 1 : 0;
-                    nxt = reinterpret_cast<const int*>(L.ops + j)[tid];
+                const SbcOp op = s_ops[opc & 3u];
+                if (tid < 32) {   // park op i+2 (loaded during the previous op), start loading op i+3 (wrapping)
+                    reinterpret_cast<int*>(&s_ops[(opc + 2u) & 3u])[tid] = pend;
+                    int j = i + 3;
+                    while (j >= L.n_ops) j -= L.n_ops;
+                    pend = reinterpret_cast<const int*>(L.ops + j)[tid];
                 }
                 const float* wseg = L.blob + op.w_off;
                 if (op.w_len > 0 && stage) {
@@ -510,10 +593,13 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 }
                 const SbcGeo& GS = L.geo[op.sgeo];
                 const SbcGeo& GD = L.geo[op.dgeo];
-                switch (op.kind) {
+                long long* sub = do_prof ? L.prof + L.n_ops + 2 + 4 * i : nullptr;   // intra-op stamps (thread 0)
+                if (sub) sub[0] = sub[1] = sub[2] = sub[3] = 0;
+                int kind = op.kind;
+                if ((L.dbg & 16) || ((L.dbg & 4) && kind != SBC_OP_CONV_MMA)) kind = -1;   // timing experiments
+                switch (kind) {
                     case SBC_OP_CONV_MMA:
-                        if (op.flags & SBC_F_X3) sbc_conv_mma<true>(op, GS, GD, arena, wseg, tid);
-                        else sbc_conv_mma<false>(op, GS, GD, arena, wseg, tid);
+                        sbc_conv_mma<X3, SMEM_ARENA>(op, GS, GD, arena, wseg, tid, sub, L.dbg);
                         break;
                     case SBC_OP_NORM_ELU:
                         sbc_norm_op(op, GS, arena, wseg, tid);
@@ -533,7 +619,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     default:
                         break;
                 }
-                if (tid < 32) reinterpret_cast<int*>(&s_ops[(opc + 1u) & 1u])[tid] = nxt;
+                if (sub) sub[3] = clock64();
                 __syncthreads();
             }
             if (L.debug_stop >= 0) {   // debugging aid: dump the arena of sample 0 and stop

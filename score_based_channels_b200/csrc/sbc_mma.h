@@ -4,18 +4,18 @@
 //
 // Implicit GEMM per K step s = (live tap, chunk of 8 input channels):
 //     D[16 output pixels, 8 couts] += A[16 pixels, 8 cins] * B[8 cins, 8 couts]
-// with the fragment layout of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 and the K index permuted so
-// that the two K columns a lane owns are ADJACENT channels (MMA column t <-> channel 2t, column t+4 <->
-// channel 2t+1; the same permutation is applied to the packed weights, so the contraction is unchanged):
-//     lane = 4*g + t :  A: (a0,a2) = channels (2t, 2t+1) of pixel row g,  (a1,a3) = same of row g+8
-//                       B: b0 = W[cout g][cin 2t], b1 = W[cout g][cin 2t+1]    (packed by program.py)
+// with the fragment layout of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32
+//     lane = 4*g + t :  A: a0=(row g, k=t) a1=(row g+8, k=t) a2=(row g, k=t+4) a3=(row g+8, k=t+4)
+//                       B: b0 = W[cout g][cin t], b1 = W[cout g][cin t+4]       (packed by program.py)
 //                       C: (c0,c1) = couts (2t, 2t+1) of row g, (c2,c3) = same of row g+8
-// One pixel of one plane is 8 channels = 32 contiguous bytes, so an A fragment is two 8-byte loads per lane
-// and the 8 pixel rows x 4 lanes of a quarter-warp cover 256 contiguous bytes when the pixels are contiguous
-// (conflict-free).  Thanks to the zero halo (SbcGeo) a K step is a constant address offset -- read from the
-// per-op table at the head of the parameter segment (program.py) -- and the gather has no bounds checks.
-// ConvMeanPool (SBC_F_POOL) runs four accumulations per tile, one per position of the 2x2 pooling window
-// (input pixel (2Y+qy, 2X+qx)), summed before the epilogue (the packed weights carry the 1/4).
+// rows = output pixels, k = input channel within the chunk.  One pixel of one plane is 8 channels = 32
+// contiguous bytes = two 16-byte rows of the 8x8 b16 matrices ldmatrix moves, so with the arena in shared
+// memory ONE ldmatrix.x4 per lane delivers the whole A fragment already in register order (matrix 0/1 =
+// channels 0-3 of pixel rows 0-7 / 8-15, matrix 2/3 = channels 4-7; lane l supplies the address of pixel row
+// l & 15, channel half l >> 4).  Thanks to the zero halo (SbcGeo) a K step is a constant address offset --
+// read from the per-op table at the head of the parameter segment (program.py) -- and the gather has no bounds
+// checks.  ConvMeanPool (SBC_F_POOL) runs four accumulations per tile, one per position of the 2x2 pooling
+// window (input pixel (2Y+qy, 2X+qx)), summed before the epilogue (the packed weights carry the 1/4).
 #pragma once
 #include "sbc_ops.h"
 
@@ -47,42 +47,53 @@ SBC_HD int sbc_mma_row_off(const SbcOp& op, const SbcGeo& GS, int mt, int quad, 
     return (GS.org + iy * GS.wp + ix) * 8;
 }
 
-// A fragment of one lane: `asrc` = arena + op.src + 2*t, `off` = K-step offset from the op's table
+// A fragment of one lane from plain loads (global-memory arena, CPU emulation): `asrc` = arena + op.src + t,
+// `off` = K-step offset from the op's table, po0 / po1 = sbc_mma_row_off of tile rows g / g + 8
 SBC_HD void sbc_mma_a_frag(const float* asrc, int off, int po0, int po1, float (&a)[4]) {
-    const SbcF2 v0 = *reinterpret_cast<const SbcF2*>(asrc + off + po0);
-    const SbcF2 v1 = *reinterpret_cast<const SbcF2*>(asrc + off + po1);
-    a[0] = v0.x; a[1] = v1.x; a[2] = v0.y; a[3] = v1.y;
+    a[0] = asrc[off + po0];
+    a[1] = asrc[off + po1];
+    a[2] = asrc[off + po0 + 4];
+    a[3] = asrc[off + po1 + 4];
+}
+
+// what the epilogue needs from the op
+struct SbcEpi {
+    int dst, acc, edst, flags, cout, b_rel, pps8;
+};
+SBC_HD SbcEpi sbc_epi(const SbcOp& op, const SbcGeo& GD) {
+    return SbcEpi{op.dst, op.acc, op.edst, op.flags, op.cout, op.b_rel, GD.pps * 8};
 }
 
 // Epilogue of one lane for cout tile nt of one pixel tile:  v = c + bias;  dst <- v;  acc <- (v += acc);
-// edst <- ELU(v).  pd[half] = float offset (org + Y*wp + X) * 8 of the output pixel of tile row g + 8*half in
+// edst <- ELU(v).  pd0 / pd1 = float offset (org + Y*wp + X) * 8 of the output pixel of tile rows g / g + 8 in
 // the destination geometry, or -1 when that row is past the last pixel; q0 = index of the pixel of row g.
 // (c0,c1) and (c2,c3) are two adjacent output channels of one pixel: 8-byte accesses.  cout is even.
-SBC_HD void sbc_mma_epilogue(const SbcOp& op, const SbcGeo& GD, float* arena, const float* wseg, const int (&pd)[2],
-                             int q0, int nt, int lane, const float (&c)[4]) {
+SBC_HD void sbc_mma_epilogue(SbcEpi e, float* arena, const float* wseg, int pd0, int pd1, int q0, int nt,
+                                     int lane, float c0, float c1, float c2, float c3) {
     const int t = lane & 3;
     const int co = nt * 8 + 2 * t;
-    if (co >= op.cout) return;
+    if (co >= e.cout) return;
     float b0 = 0.f, b1 = 0.f;
-    if (op.b_rel >= 0) { b0 = wseg[op.b_rel + co]; b1 = wseg[op.b_rel + co + 1]; }
-    const int cofs = (co >> 3) * GD.pps * 8 + (co & 7);
+    if (e.b_rel >= 0) { b0 = wseg[e.b_rel + co]; b1 = wseg[e.b_rel + co + 1]; }
+    const int cofs = (co >> 3) * e.pps8 + (co & 7);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        if (pd[half] < 0) continue;
-        SbcF2 v{c[2 * half] + b0, c[2 * half + 1] + b1};
-        if (op.flags & SBC_F_COMPACT) {   // network output: couts (0,1) = (re, im) of element q
-            reinterpret_cast<SbcF2*>(arena + op.dst)[q0 + 8 * half] = v;
+        const int pd = half ? pd1 : pd0;
+        if (pd < 0) continue;
+        SbcF2 v{(half ? c2 : c0) + b0, (half ? c3 : c1) + b1};
+        if (e.flags & SBC_F_COMPACT) {   // network output: couts (0,1) = (re, im) of element q
+            reinterpret_cast<SbcF2*>(arena + e.dst)[q0 + 8 * half] = v;
             continue;
         }
-        const int idx = pd[half] + cofs;
-        if (op.dst >= 0) *reinterpret_cast<SbcF2*>(arena + op.dst + idx) = v;
-        if (op.acc >= 0) {
-            SbcF2* ap = reinterpret_cast<SbcF2*>(arena + op.acc + idx);
+        const int idx = pd + cofs;
+        if (e.dst >= 0) *reinterpret_cast<SbcF2*>(arena + e.dst + idx) = v;
+        if (e.acc >= 0) {
+            SbcF2* ap = reinterpret_cast<SbcF2*>(arena + e.acc + idx);
             const SbcF2 o = *ap;
             v.x += o.x; v.y += o.y;
             *ap = v;
         }
-        if (op.edst >= 0) *reinterpret_cast<SbcF2*>(arena + op.edst + idx) = SbcF2{sbc_elu(v.x), sbc_elu(v.y)};
+        if (e.edst >= 0) *reinterpret_cast<SbcF2*>(arena + e.edst + idx) = SbcF2{sbc_elu(v.x), sbc_elu(v.y)};
     }
 }
 // destination pixel offsets of one lane for tile mt (see sbc_mma_epilogue)

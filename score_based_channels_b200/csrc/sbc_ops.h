@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define SBC_HD __host__ __device__ __forceinline__
+#define SBC_HD_OUTLINE __host__ __device__ __noinline__   // one copy: the kernel's instruction footprint matters
 #else
 #define SBC_HD static inline
+#define SBC_HD_OUTLINE static
 #endif
 
 struct alignas(16) SbcF4 {
@@ -42,13 +44,19 @@ SBC_HD float sbc_elu(float v) {
 }
 SBC_HD SbcF4 sbc_elu4(SbcF4 v) { return SbcF4{sbc_elu(v.x), sbc_elu(v.y), sbc_elu(v.z), sbc_elu(v.w)}; }
 
-// i / d and i % d with d = 2^ld when ld >= 0
-SBC_HD int sbc_div(int i, int d, int ld) { return ld >= 0 ? (i >> ld) : (i / d); }
+// i / d with d = 2^ld when ld >= 0; the general division is kept out of line (it is ~30 instructions and
+// would otherwise be replicated at every call site of a kernel whose instruction-cache footprint matters)
+SBC_HD_OUTLINE int sbc_div_slow(int i, int d) { return i / d; }
+SBC_HD int sbc_div(int i, int d, int ld) { return ld >= 0 ? (i >> ld) : sbc_div_slow(i, d); }
 SBC_HD int sbc_ilog2(int v) {   // log2(v) if v is a power of two, else -1
     if (v <= 0 || (v & (v - 1))) return -1;
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz(v);
+#else
     int l = 0;
     while ((1 << l) < v) l++;
     return l;
+#endif
 }
 // padded pixel index of interior pixel i = y * w + x
 SBC_HD int sbc_pix(const SbcGeo& G, int i) {
@@ -84,20 +92,25 @@ SBC_HD const SbcF4* sbc_q4(const float* base, const SbcGeo& G, int q, int p) {
     return reinterpret_cast<const SbcF4*>(base + ((size_t)((q >> 1) * G.pps + p) * 8 + (q & 1) * 4));
 }
 
-// zero the halo cells of a tensor with `c` channels: one item = one padded row of one plane
-SBC_HD void sbc_zero_halo(float* t, const SbcGeo& G, int c, int tid, int nthr) {
+// zero the halo cells of a tensor with `c` channels: one item = one padded row of one plane.  Out of line
+// (scalar arguments, so that the caller's structs stay in registers).
+SBC_HD_OUTLINE void sbc_zero_halo_impl(float* t, int h, int w, int hy, int hx, int wp, int pps, int c, int tid,
+                                       int nthr) {
     const int np = (c + 7) >> 3;
-    const int rows = G.h + 2 * G.hy;
+    const int rows = h + 2 * hy;
     const SbcF4 z{0.f, 0.f, 0.f, 0.f};
     for (int i = tid; i < np * rows; i += nthr) {
         const int pl = i / rows, row = i - pl * rows;
-        SbcF4* r = reinterpret_cast<SbcF4*>(t + (size_t)(pl * G.pps + row * G.wp) * 8);
-        if (row < G.hy || row >= G.hy + G.h) {
-            for (int k = 0; k < 2 * G.wp; k++) r[k] = z;
+        SbcF4* r = reinterpret_cast<SbcF4*>(t + (size_t)(pl * pps + row * wp) * 8);
+        if (row < hy || row >= hy + h) {
+            for (int k = 0; k < 2 * wp; k++) r[k] = z;
         } else {
-            for (int k = 0; k < 2 * G.hx; k++) { r[k] = z; r[2 * (G.hx + G.w) + k] = z; }
+            for (int k = 0; k < 2 * hx; k++) { r[k] = z; r[2 * (hx + w) + k] = z; }
         }
     }
+}
+SBC_HD void sbc_zero_halo(float* t, const SbcGeo& G, int c, int tid, int nthr) {
+    sbc_zero_halo_impl(t, G.h, G.w, G.hy, G.hx, G.wp, G.pps, c, tid, nthr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -108,11 +121,13 @@ SBC_HD void sbc_zero_halo(float* t, const SbcGeo& G, int c, int tid, int nthr) {
 // emulation.  C must be a multiple of 8.
 // ----------------------------------------------------------------------------------------------
 SBC_HD int sbc_norm_T(const SbcOp& op, int nthr) {
-    const int nq = op.cin >> 2;
-    int T = nthr / nq;
-    int p = 32;
-    while (p * 2 <= T) p *= 2;
-    return p;
+    (void)nthr;
+    return op.MT;   // threads per quad: largest power of two <= nthr / (C/4), at least 32 (program.py)
+}
+SBC_HD float sbc_bits_f(int32_t b) {
+    union { int32_t i; float f; } v;
+    v.i = b;
+    return v.f;
 }
 SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float* arena, int q, int s, int T) {
     SbcF4 a{0.f, 0.f, 0.f, 0.f};
@@ -137,24 +152,25 @@ SBC_HD SbcF4 sbc_norm_partial_m2(const SbcOp& op, const SbcGeo& G, const float* 
 // `mu` [C] per-channel means (16-byte aligned); mean4 / m2_4: the statistics of this thread's quad
 SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const float* wseg, const float* mu, int q,
                            int s, int T, SbcF4 mean4, SbcF4 m2_4) {
-    const int C = op.cin, HW = G.h * G.w, nq = C >> 2;
+    const int C = op.cin, nq = C >> 2;
     // cross-channel statistics of the per-channel means: torch.mean / torch.var (unbiased) over C
+    // (four independent partial sums: the dependent-add chain is what costs on a latency-bound SM)
     const SbcF4* mu4 = reinterpret_cast<const SbcF4*>(mu);
-    float m = 0.f;
-    for (int k = 0; k < nq; k++) { const SbcF4 u = mu4[k]; m += (u.x + u.y) + (u.z + u.w); }
-    m *= 1.f / (float)C;
-    float v = 0.f;
+    SbcF4 ms{0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nq; k++) { const SbcF4 u = mu4[k]; ms.x += u.x; ms.y += u.y; ms.z += u.z; ms.w += u.w; }
+    const float m = ((ms.x + ms.y) + (ms.z + ms.w)) * sbc_bits_f(op.low);        // * 1/C
+    SbcF4 vs{0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < nq; k++) {
         const SbcF4 u = mu4[k];
         const float d0 = u.x - m, d1 = u.y - m, d2 = u.z - m, d3 = u.w - m;
-        v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); v = fmaf(d2, d2, v); v = fmaf(d3, d3, v);
+        vs.x = fmaf(d0, d0, vs.x); vs.y = fmaf(d1, d1, vs.y); vs.z = fmaf(d2, d2, vs.z); vs.w = fmaf(d3, d3, vs.w);
     }
-    v *= 1.f / (float)(C - 1);
+    const float v = ((vs.x + vs.y) + (vs.z + vs.w)) * sbc_bits_f(op.tapmask);    // * 1/(C-1)
     const float rv = sbc_rsqrt(v + 1e-5f);
     const SbcF4 al = *reinterpret_cast<const SbcF4*>(wseg + 4 * q);
     const SbcF4 ga = *reinterpret_cast<const SbcF4*>(wseg + C + 4 * q);
     const SbcF4 be = *reinterpret_cast<const SbcF4*>(wseg + 2 * C + 4 * q);
-    const float inv = 1.f / (float)HW;
+    const float inv = sbc_bits_f(op.frag_rel);                                  // 1/HW
     // nn.InstanceNorm2d: biased variance
     const float a0 = ga.x * sbc_rsqrt(m2_4.x * inv + 1e-5f), a1 = ga.y * sbc_rsqrt(m2_4.y * inv + 1e-5f);
     const float a2 = ga.z * sbc_rsqrt(m2_4.z * inv + 1e-5f), a3 = ga.w * sbc_rsqrt(m2_4.w * inv + 1e-5f);
@@ -178,8 +194,8 @@ SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const
 // element-wise ops (one float4 quad of one pixel per item)
 // ----------------------------------------------------------------------------------------------
 SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
-    const int nq = op.cin >> 2, T = sbc_norm_T(op, nthr), gpp = nthr / T, s = tid & (T - 1);
-    for (int q = tid / T; q < nq; q += gpp) {
+    const int nq = op.cin >> 2, T = op.MT, lT = op.NT, gpp = nthr >> lT, s = tid & (T - 1);
+    for (int q = tid >> lT; q < nq; q += gpp) {
         const size_t qo = (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
         const float* src = arena + op.src + qo;
         float* dst = arena + op.dst + qo;

@@ -51,7 +51,9 @@ struct SbcOp {
     int32_t next_w;                // filled by sbc_model_create: index of the next op with parameters
     int32_t tapmask;               // conv: live taps of the k x k window (bit = ky*k + kx)
     int32_t wbuf;                  // arena offset where the parameter segment is staged
-    // ---- host-derived conv constants ----
+    // ---- host-derived constants.  conv: as named.  NORM_ELU / ELU reuse the words: MT = T (threads per channel
+    // quad, a power of two >= 32), NT = log2 T, S = number of passes over the quads; NORM_ELU also: frag_rel, low,
+    // tapmask = float bits of 1/(h*w), 1/C, 1/(C-1) ----
     int32_t MT, NT;                // 16-pixel output tiles, 8-cout tiles
     int32_t S;                     // K steps = live taps * cin chunks; segment starts with S int32 A offsets
     int32_t frag_rel;              // offset of the B fragments inside the segment

@@ -22,8 +22,8 @@ Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by
 ``pps = (h + 2*hy) * wp``, ``org = hy * wp + hx``.  The halo (hy, hx) covers every live convolution tap
 at that resolution, so the implicit-im2col gather of a K step (tap, chunk of 8 input channels) is the
 *same* address pattern shifted by a constant -- tabulated per op at the head of its parameter segment --
-and needs no bounds checks; one pixel of one plane is exactly the K = 8 chunk of an m16n8k8 MMA, a lane's
-two K columns are adjacent channels (one 8-byte load) and a quarter-warp covers 256 contiguous bytes.
+and needs no bounds checks; one pixel of one plane is exactly the K = 8 chunk of an m16n8k8 MMA = two
+16-byte ldmatrix rows, so one ldmatrix.x4 per lane loads a whole A fragment in register order.
 The sampler state ``x`` and the raw network output are *compact* (re, im) pair arrays [h*w].
 
 Nothing here touches a GPU; ``simulate`` is a torch (CPU) interpreter of the program used by the CPU
@@ -358,8 +358,8 @@ class ProgramBuilder:
         v = conv(src) + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v).
         Parameter segment: [S int32 A offsets | B fragments | bias].  ``aoff[s]`` is the float offset
         (cin_chunk * pps + dy * wp + dx) * 8 that K step s adds to every gathered address.  The weights are in
-        mma.sync m16n8k8 B-fragment order with the K index permuted like the A gather (csrc/sbc_mma.h):
-        frag[step][ntile][lane] = (w0, w1) where lane = 4*g + t holds W[cout g][cin 2t (+1)]: TF32-rounded (rna)
+        mma.sync m16n8k8 B-fragment order (csrc/sbc_mma.h):
+        frag[step][ntile][lane] = (w0, w1) where lane = 4*g + t holds W[cout g][cin t (+4)]: TF32-rounded (rna)
         in the "tf32" mode, plain fp32 in the 3xTF32 mode (the kernel splits w = hi + lo in registers)."""
         wt = self.sd[prefix + ".weight"]
         bias = self.sd.get(prefix + ".bias")
@@ -408,8 +408,8 @@ class ProgramBuilder:
             for i, tap in enumerate(live):
                 for kc in range(KC):
                     for nt in range(ntc):
-                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + 2 * t, tap]
-                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + 2 * t + 1, tap]
+                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t, tap]
+                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t + 4, tap]
                         if not x3:
                             w0, w1 = tf32_rna(w0), tf32_rna(w1)
                         frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = w0, w1
@@ -445,14 +445,28 @@ class ProgramBuilder:
         # scratch: per-warp partial sums of the two statistics passes (4 channels each) + per-channel (mean, M2)
         nwarps = self.nthreads // 32
         scratch = self.tmp_raw(2 * nwarps * 4 + 2 * c, "nsc")
+        T, lT, npass = self._quad_threads(c)
+        fb = lambda v: int(np.float32(v).view(np.int32))
         self.ops.append(Op(OP_NORM_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, w_off=w_off, w_len=w_len,
-                           sgeo=self.gi(h, w), dgeo=self.gi(h, w), scratch=scratch, oh=h, ow=w, name=prefix))
+                           sgeo=self.gi(h, w), dgeo=self.gi(h, w), scratch=scratch, oh=h, ow=w, MT=T, NT=lT, S=npass,
+                           frag_rel=fb(1.0 / (h * w)), low=fb(1.0 / c), tapmask=fb(1.0 / (c - 1)), name=prefix))
         self.free(scratch)
+
+    def _quad_threads(self, c: int) -> Tuple[int, int, int]:
+        """(T, log2 T, passes): T = threads per channel quad = largest power of two <= nthreads / (c/4), >= 32."""
+        assert c % 8 == 0
+        nq = c // 4
+        T = 32
+        while T * 2 <= self.nthreads // nq:
+            T *= 2
+        gpp = self.nthreads // T
+        return T, T.bit_length() - 1, (nq + gpp - 1) // gpp
 
     def elu(self, src: str, dst: str) -> None:
         c, h, w = self.shape[src]
+        T, lT, npass = self._quad_threads(c)
         self.ops.append(Op(OP_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, sgeo=self.gi(h, w), dgeo=self.gi(h, w),
-                           oh=h, ow=w, name="elu"))
+                           oh=h, ow=w, MT=T, NT=lT, S=npass, name="elu"))
 
     def affine(self, src: str, dst: str) -> None:
         """dst (8 stored channels) = 2*x - 1 on the real channels read from the compact state buffer ``src``;
@@ -747,8 +761,8 @@ def conv_weights(prog: Program, op: Op):
     for i, tap in enumerate(live):
         for kc in range(KC):
             for nt in range(NT):
-                full[nt * 8 + g, kc * 8 + 2 * t, tap] = frag[i, kc, nt, :, 0]
-                full[nt * 8 + g, kc * 8 + 2 * t + 1, tap] = frag[i, kc, nt, :, 1]
+                full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0]
+                full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1]
     wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
     bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
     return wt, bias

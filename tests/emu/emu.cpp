@@ -11,7 +11,7 @@
 #include "../../score_based_channels_b200/csrc/sbc_ops.h"
 
 // warp-level emulation of the tensor-core conv: every lane's fragments are gathered with the shared
-// per-lane helpers (K-step offset table, permuted K index), the m16n8k8 product is done as plain matrices
+// per-lane helpers (K-step offset table), the m16n8k8 product is done as plain matrices
 // with the operand rounding of the device path (3xTF32: a = trunc(a) + (a - trunc(a)), the low parts
 // truncated by the tensor core, weights split the same way; TF32: rna on activations, weights pre-rounded),
 // then the per-lane epilogue runs.
@@ -36,7 +36,7 @@ static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float*
                         const int po0 = sbc_mma_row_off(op, GS, mt, quad, g);
                         const int po1 = sbc_mma_row_off(op, GS, mt, quad, g + 8);
                         float a[4];
-                        sbc_mma_a_frag(arena + op.src + 2 * t, steptab[s], po0, po1, a);
+                        sbc_mma_a_frag(arena + op.src + t, steptab[s], po0, po1, a);
                         const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
                         for (int i = 0; i < 4; i++) {
                             if (x3) {
@@ -76,7 +76,7 @@ static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float*
                 const float c[4] = {D[g][2 * t], D[g][2 * t + 1], D[g + 8][2 * t], D[g + 8][2 * t + 1]};
                 int pd[2];
                 sbc_mma_dst_off(op, GD, mt, g, pd);
-                sbc_mma_epilogue(op, GD, arena, wseg, pd, mt * 16 + g, nt, lane, c);
+                sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + g, nt, lane, c[0], c[1], c[2], c[3]);
             }
         }
 }

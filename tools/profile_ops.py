@@ -31,7 +31,7 @@ e1.record()
 torch.cuda.synchronize()
 print("precision %s forward B=%d: %.3f ms per launch" % (PREC, B, e0.elapsed_time(e1) / 10))
 
-stamps = torch.zeros(len(prog.ops) + 2, dtype=torch.int64, device=dev)
+stamps = torch.zeros(5 * len(prog.ops) + 2, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, stamps.data_ptr()), "prof")
 P = torch.from_numpy(synth.qpsk_pilots(B, 64, 38)).to(dev)
 H = torch.from_numpy(synth.cdl_like_channels(B)).to(dev)
@@ -40,10 +40,12 @@ X0 = torch.randn_like(H)
 sampler.ald_run(m, P, Y, X0, H, noise_var=1.0, alpha_step=3e-11, beta=0.01, level_begin=0, level_end=1, steps_each=2)
 torch.cuda.synchronize()
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, None), "prof")
-st = stamps.cpu().numpy()
+full = stamps.cpu().numpy()
+st = full[:len(prog.ops) + 2]
+sub = full[len(prog.ops) + 2:].reshape(len(prog.ops), 4)
 d = np.diff(st)
 tot = st[-1] - st[0]
-print("CTA0 first step: %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
+print("CTA0 second step (warm): %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
 kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "conv_mma"}
 by_kind = {}
 rows = []
@@ -58,11 +60,17 @@ for i, op in enumerate(prog.ops):
     by_kind.setdefault(key, [0, 0])
     by_kind[key][0] += c
     by_kind[key][1] += 1
-    rows.append((i, op.name, key, c))
+    ss = sub[i]
+    phases = ""
+    if ss[0] > 0 and ss[3] > 0:   # start->prologue | ->loop entry | loop | epilogue | barrier+tail
+        e = int(st[i + 1])
+        phases = " | pro %d ent %d loop %d epi %d bar %d" % (ss[0] - st[i], max(ss[1] - ss[0], 0), max(ss[2] - ss[1], 0),
+                                                          ss[3] - max(ss[2], ss[0]), e - ss[3])
+    rows.append((i, op.name, key + phases, c))
 print("\n== by op class (cycles, count, cycles/op, share of network)")
 net = st[-2] - st[0]
 for k, (c, n) in sorted(by_kind.items(), key=lambda kv: -kv[1][0]):
     print("%-48s %9d %4d %8.0f %6.2f%%" % (k, c, n, c / n, 100.0 * c / net))
 print("\n== every op")
 for r in rows:
-    print("%3d %-40s %-46s %8d" % r)
+    print("%3d %-36s %8d  %s" % (r[0], r[1], r[3], r[2]))
