@@ -43,6 +43,8 @@ struct SbcModel {
     long long launches = 0;
     long long* d_prof = nullptr;   // optional per-op clock stamps (sbc_set_profile_buffer)
     SbcGeo geo[SBC_MAX_GEO];
+    int n_geo = 0;
+    int halo_off[SBC_MAX_GEO] = {0};
 };
 
 extern "C" int sbc_version(void) { return SBC_VERSION; }
@@ -74,6 +76,13 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     if (!desc->geo_table || desc->n_geo <= 0 || desc->n_geo > SBC_MAX_GEO) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: bad geometry table"); }
     memset(m->geo, 0, sizeof m->geo);
     memcpy(m->geo, desc->geo_table, sizeof(SbcGeo) * (size_t)desc->n_geo);
+    m->n_geo = desc->n_geo;
+    int halo_total = 0;   // uint16 entries of the per-geometry halo-pixel lists (shared misc region)
+    for (int g = 0; g < desc->n_geo; g++) {
+        if (m->geo[g].pps > 65535) { delete m; return sbc_fail(SBC_E_UNSUPPORTED, "geometry %d: plane too large", g); }
+        m->halo_off[g] = halo_total;
+        halo_total += m->geo[g].pps - m->geo[g].h * m->geo[g].w;
+    }
     if (m->geo[0].h != desc->Nt || m->geo[0].w != desc->Nr) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: geometry 0 must be Nt x Nr"); }
     SBC_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
     SBC_CUDA(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -122,10 +131,10 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
 
     // where do activations live, and are parameters staged through shared memory?
     cudaFuncAttributes fa{};
-    SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true, true>));
+    SBC_CUDA(cudaFuncGetAttributes(&fa, sbc_ald_kernel<true, true, true>));
     const int dyn_max = m->smem_optin - (int)fa.sharedSizeBytes;   // opt-in limit covers static + dynamic
     const size_t arena_bytes = (size_t)desc->arena_floats * 4;
-    const size_t misc = 64;
+    const size_t misc = ((size_t)SBC_MISC_BARS + (size_t)halo_total * 2 + 15) / 16 * 16;
     m->arena_in_smem = !env_int("SBC_FORCE_GLOBAL_ARENA", 0) && arena_bytes + misc <= (size_t)dyn_max;
     // parameter staging buffers live inside the arena: staging needs the arena in shared memory
     m->stage = m->arena_in_smem && env_int("SBC_STAGE_WEIGHTS", 1) != 0;
@@ -140,10 +149,14 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
     m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr; m->d.geo_table = nullptr;   // host pointers are not retained
 
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     *handle_out = m;
     return SBC_OK;
 }
@@ -177,6 +190,8 @@ static void fill_common(const SbcModel* m, SbcLaunch& L) {
     memset(&L, 0, sizeof L);
     L.ops = m->d_ops; L.n_ops = m->d.n_ops; L.first_w = m->first_w; L.blob = m->d_blob;
     memcpy(L.geo, m->geo, sizeof L.geo);
+    L.n_geo = m->n_geo;
+    memcpy(L.halo_off, m->halo_off, sizeof L.halo_off);
     L.arena_floats = m->d.arena_floats; L.in_off = m->d.in_off; L.out_off = m->d.out_off; L.post_off = m->d.post_off;
     L.Nt = m->d.Nt; L.Nr = m->d.Nr; L.channels = m->d.channels; L.max_w_len = m->d.max_w_len;
     L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
@@ -190,13 +205,16 @@ static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
     const int grid = L.B < m->num_sms ? L.B : m->num_sms;
     size_t smem = m->smem_bytes;
     if (L.debug_stop >= 0) L.stage_weights = 0;   // debug runs read parameters straight from global memory
+    const bool instr = L.prof != nullptr || L.debug_stop >= 0 || L.dbg != 0;
+#define SBC_LAUNCH(A, X, I) sbc_ald_kernel<A, X, I><<<grid, SBC_NTHREADS, smem, st>>>(L)
     if (m->arena_in_smem) {
-        if (m->x3) sbc_ald_kernel<true, true><<<grid, SBC_NTHREADS, smem, st>>>(L);
-        else sbc_ald_kernel<true, false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+        if (m->x3) { if (instr) SBC_LAUNCH(true, true, true); else SBC_LAUNCH(true, true, false); }
+        else { if (instr) SBC_LAUNCH(true, false, true); else SBC_LAUNCH(true, false, false); }
     } else {
-        if (m->x3) sbc_ald_kernel<false, true><<<grid, SBC_NTHREADS, smem, st>>>(L);
-        else sbc_ald_kernel<false, false><<<grid, SBC_NTHREADS, smem, st>>>(L);
+        if (m->x3) { if (instr) SBC_LAUNCH(false, true, true); else SBC_LAUNCH(false, true, false); }
+        else { if (instr) SBC_LAUNCH(false, false, true); else SBC_LAUNCH(false, false, false); }
     }
+#undef SBC_LAUNCH
     SBC_CUDA(cudaGetLastError());
     m->launches++;
     return SBC_OK;

@@ -24,6 +24,8 @@ struct SbcLaunch {
     int first_w;             // index of the first op with parameters
     const float* blob;       // packed parameters
     SbcGeo geo[SBC_MAX_GEO]; // tensor geometries (geo[0] = network input / output resolution)
+    int n_geo;
+    int halo_off[SBC_MAX_GEO];   // start (uint16 units) of geometry g's halo-pixel list in the shared misc region
     int arena_floats, in_off, out_off, post_off;
     int Nt, Nr, channels, max_w_len;
     int mode;                // 0 = forward (NCSNv2Deepest.forward), 1 = annealed Langevin
@@ -241,6 +243,84 @@ __device__ __forceinline__ void sbc_mma_pass(const SbcALane<SMEM>& A, const int 
     }
 }
 
+// Fused epilogue of one lane for NS tiles x NN cout tiles, phase-batched: all bias / accumulator loads are
+// issued before any is consumed and every (uniform) branch is taken once per pass instead of once per tile, so
+// the load and MUFU latencies of the tiles overlap.  Semantics = sbc_mma_epilogue (sbc_mma.h) per tile.
+template <int NS, int NN>
+__device__ __forceinline__ void sbc_epilogue_batch(const SbcEpi& e, float* arena, const float* wseg,
+                                                   const int (&pd)[NS][2], const int (&q0)[NS], int nt0, int lane,
+                                                   float (&acc)[NS][NN][4]) {
+    const int t = lane & 3;
+    int cofs[NN];
+    bool live[NN];
+#pragma unroll
+    for (int n = 0; n < NN; n++) {
+        const int co = (nt0 + n) * 8 + 2 * t;
+        live[n] = co < e.cout;
+        cofs[n] = (co >> 3) * e.pps8 + (co & 7);
+        if (e.b_rel >= 0 && live[n]) {
+            const float2 b = *reinterpret_cast<const float2*>(wseg + e.b_rel + co);   // co is even, b_rel % 4 == 0
+#pragma unroll
+            for (int j = 0; j < NS; j++) { acc[j][n][0] += b.x; acc[j][n][1] += b.y; acc[j][n][2] += b.x; acc[j][n][3] += b.y; }
+        }
+    }
+    if (e.flags & SBC_F_COMPACT) {   // network output: couts (0,1) = (re, im) of element q
+        if (live[0] && t == 0) {
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                    if (pd[j][half] >= 0)
+                        reinterpret_cast<float2*>(arena + e.dst)[q0[j] + 8 * half] = make_float2(acc[j][0][2 * half], acc[j][0][2 * half + 1]);
+        }
+        return;
+    }
+    if (e.dst >= 0) {
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                    if (live[n] && pd[j][half] >= 0)
+                        *reinterpret_cast<float2*>(arena + e.dst + pd[j][half] + cofs[n]) = make_float2(acc[j][n][2 * half], acc[j][n][2 * half + 1]);
+    }
+    if (e.acc >= 0) {
+        float2 old[NS][NN][2];
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                    old[j][n][half] = (live[n] && pd[j][half] >= 0)
+                                          ? *reinterpret_cast<const float2*>(arena + e.acc + pd[j][half] + cofs[n])
+                                          : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++)
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    acc[j][n][2 * half] += old[j][n][half].x;
+                    acc[j][n][2 * half + 1] += old[j][n][half].y;
+                    if (live[n] && pd[j][half] >= 0)
+                        *reinterpret_cast<float2*>(arena + e.acc + pd[j][half] + cofs[n]) = make_float2(acc[j][n][2 * half], acc[j][n][2 * half + 1]);
+                }
+    }
+    if (e.edst >= 0) {
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                    if (live[n] && pd[j][half] >= 0)
+                        *reinterpret_cast<float2*>(arena + e.edst + pd[j][half] + cofs[n]) =
+                            make_float2(sbc_elu(acc[j][n][2 * half]), sbc_elu(acc[j][n][2 * half + 1]));
+    }
+}
+
 // one pass of a warp over NS tiles (mt0, mt0 + mstride, ...; only the first `ntile` are real) x NN cout tiles
 template <bool X3, bool SMEM, int NS, int NN>
 __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
@@ -248,8 +328,20 @@ __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS
                                                int bstride, int mt0, int mstride, int ntile, int nt0, int lane,
                                                long long* stamp) {
     int po[NS][2];
+    A.rows(op, GS, mt0, 0, lane, po[0]);
+    if (NS > 1) {
+        // tiles mt0 + j*mstride: when the tile stride is a whole number of image rows and no row is clamped, the
+        // pixel offsets advance by a constant
+        const int pstep = mstride * 16;
+        if (op.low >= 0 && (pstep & (op.ow - 1)) == 0 && (mt0 + (NS - 1) * mstride) * 16 + 16 <= op.oh * op.ow) {
+            const int step = (pstep >> op.low) * GS.wp * (SMEM ? 32 : 8);
 #pragma unroll
-    for (int j = 0; j < NS; j++) A.rows(op, GS, mt0 + (j < ntile ? j : 0) * mstride, 0, lane, po[j]);
+            for (int j = 1; j < NS; j++) { po[j][0] = po[0][0] + j * step; po[j][1] = po[0][1] + j * step; }
+        } else {
+#pragma unroll
+            for (int j = 1; j < NS; j++) A.rows(op, GS, mt0 + (j < ntile ? j : 0) * mstride, 0, lane, po[j]);
+        }
+    }
     float acc[NS][NN][4];
 #pragma unroll
     for (int j = 0; j < NS; j++)
@@ -259,17 +351,15 @@ __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS
     sbc_mma_pass<X3, SMEM, NS, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, 0, op.S, acc);
     if (stamp) stamp[2] = clock64();
     const SbcEpi e = sbc_epi(op, GD);
+    int pd[NS][2], q0[NS];
 #pragma unroll
-    for (int j = 0; j < NS; j++)
-        if (j < ntile) {
-            const int mt = mt0 + j * mstride;
-            int pd[2];
-            sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
-#pragma unroll
-            for (int n = 0; n < NN; n++)
-                sbc_mma_epilogue(e, arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt0 + n, lane, acc[j][n][0],
-                                 acc[j][n][1], acc[j][n][2], acc[j][n][3]);
-        }
+    for (int j = 0; j < NS; j++) {
+        const int mt = mt0 + j * mstride;
+        q0[j] = mt * 16 + (lane >> 2);
+        if (j < ntile) sbc_mma_dst_off(op, GD, mt, lane >> 2, pd[j]);
+        else pd[j][0] = pd[j][1] = -1;
+    }
+    sbc_epilogue_batch<NS, NN>(e, arena, wseg, pd, q0, nt0, lane, acc);
 }
 
 // ConvMeanPool: one output tile, the four pooling positions are the four slots
@@ -302,9 +392,6 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
     constexpr int NW = SBC_NTHREADS / 32;
     constexpr int E = 2;   // floats per lane per B fragment
     const bool pool = (op.flags & SBC_F_POOL) != 0;
-    // fresh outputs get their halo re-zeroed when the planner could not prove it clean
-    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, tid, SBC_NTHREADS);
-    if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, tid, SBC_NTHREADS);
 
     const int MT = op.MT, NT = op.NT, S = op.S;
     const SbcALane<SMEM> A(op, arena, lane);
@@ -451,7 +538,19 @@ __device__ __forceinline__ void sbc_norm_op(const SbcOp& op, const SbcGeo& G, fl
             sbc_norm_apply(op, G, arena, wseg, reinterpret_cast<const float*>(mu4), q, s, T, mean, m2);
         }
     }
-    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, C, tid, SBC_NTHREADS);
+}
+
+// Halo zeroing from a per-geometry list of halo pixel indices kept in shared memory (built once per launch):
+// one float4 store per item, no index arithmetic.  hl = list of geometry g, nh = its length.
+__device__ __forceinline__ void sbc_zero_halo_list(float* t, const SbcGeo& G, const uint16_t* hl, int nh, int c,
+                                                   int tid) {
+    const int np = (c + 7) >> 3;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pl = 0; pl < np; pl++) {
+        float* base = t + (size_t)pl * G.pps * 8;
+        for (int k = tid; k < 2 * nh; k += SBC_NTHREADS)
+            *reinterpret_cast<float4*>(base + (int)hl[k >> 1] * 8 + (k & 1) * 4) = z;
+    }
 }
 
 // block-wide sum of one float per thread; the total is returned to thread 0 only.  red: NW floats.
@@ -469,7 +568,11 @@ __device__ __forceinline__ float sbc_block_sum(float v, float* red, int tid) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool SMEM_ARENA, bool X3>
+#define SBC_MISC_BARS 64      // bytes reserved for the two mbarriers at the head of the shared misc region
+
+// INSTR = true: the instrumented build of the same kernel (per-op clock stamps, debug arena dump, timing
+// experiments); the production instantiation carries none of that code in its op loop.
+template <bool SMEM_ARENA, bool X3, bool INSTR>
 __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_constant__ SbcLaunch L) {
     extern __shared__ __align__(128) unsigned char sbc_smem_raw[];
     float* smem_f = reinterpret_cast<float*>(sbc_smem_raw);
@@ -484,10 +587,12 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         arena = L.gws + (size_t)blockIdx.x * (size_t)L.arena_floats;
     }
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_f + off);   // off is a multiple of 4 floats
+    uint16_t* halo = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(bars) + SBC_MISC_BARS);
 
     __shared__ float s_hnorm;
     __shared__ SbcStepScalars s_sc;
     __shared__ float s_red[SBC_NTHREADS / 32];
+    __shared__ int s_hcnt[SBC_MAX_GEO];
     // op records are prefetched global -> shared TWO ops ahead (warp 0, one word per lane; the word loaded
     // during op i is parked in a register and stored at the start of op i+1), so that neither decoding an op
     // nor the barrier that ends a short op ever waits on global memory
@@ -506,6 +611,17 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         reinterpret_cast<int*>(&s_ops[0])[tid] = o32[tid];
         reinterpret_cast<int*>(&s_ops[1])[tid] = o32[(L.n_ops > 1 ? 32 : 0) + tid];
         pend = o32[(2 % L.n_ops) * 32 + tid];
+    }
+    if (tid < SBC_MAX_GEO) s_hcnt[tid] = 0;
+    __syncthreads();
+    // halo-pixel lists, one per geometry (order is irrelevant): used by sbc_zero_halo_list
+    for (int g = 0; g < L.n_geo; g++) {
+        const SbcGeo& G = L.geo[g];
+        for (int p = tid; p < G.pps; p += SBC_NTHREADS) {
+            const int row = p / G.wp, col = p - row * G.wp;
+            if (row < G.hy || row >= G.hy + G.h || col < G.hx || col >= G.hx + G.w)
+                halo[L.halo_off[g] + atomicAdd(&s_hcnt[g], 1)] = (uint16_t)p;
+        }
     }
     __syncthreads();
 
@@ -565,16 +681,18 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
             }
 
             // ---------------- the network: walk the layer program ----------------
-            // stamps of CTA 0, first sample, second step when there is one (warm instruction cache)
-            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && b == 0 && gs == (nsteps > 1 ? 1 : 0) && tid == 0;
+            // INSTR: stamps of CTA 0, first sample, second step when there is one (warm instruction cache)
+            const bool do_prof = INSTR && (L.prof != nullptr) && blockIdx.x == 0 && b == 0 &&
+                                 gs == (nsteps > 1 ? 1 : 0) && tid == 0;
             for (int i = 0; i < L.n_ops; i++, opc++) {
-                if (L.debug_stop >= 0 && i == L.debug_stop) break;
-                if (do_prof) L.prof[i] = clock64();
+                if (INSTR && L.debug_stop >= 0 && i == L.debug_stop) break;
+                if (INSTR && do_prof) L.prof[i] = clock64();
                 const SbcOp op = s_ops[opc & 3u];
                 if (tid < 32) {   // park op i+2 (loaded during the previous op), start loading op i+3 (wrapping)
                     reinterpret_cast<int*>(&s_ops[(opc + 2u) & 3u])[tid] = pend;
                     int j = i + 3;
-                    while (j >= L.n_ops) j -= L.n_ops;
+                    if (j >= L.n_ops) j -= L.n_ops;
+                    if (j >= L.n_ops) j = 0;
                     pend = reinterpret_cast<const int*>(L.ops + j)[tid];
                 }
                 const float* wseg = L.blob + op.w_off;
@@ -593,42 +711,44 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 }
                 const SbcGeo& GS = L.geo[op.sgeo];
                 const SbcGeo& GD = L.geo[op.dgeo];
-                long long* sub = do_prof ? L.prof + L.n_ops + 2 + 4 * i : nullptr;   // intra-op stamps (thread 0)
-                if (sub) sub[0] = sub[1] = sub[2] = sub[3] = 0;
-                int kind = op.kind;
-                if ((L.dbg & 16) || ((L.dbg & 4) && kind != SBC_OP_CONV_MMA)) kind = -1;   // timing experiments
-                switch (kind) {
-                    case SBC_OP_CONV_MMA:
-                        sbc_conv_mma<X3, SMEM_ARENA>(op, GS, GD, arena, wseg, tid, sub, L.dbg);
-                        break;
-                    case SBC_OP_NORM_ELU:
-                        sbc_norm_op(op, GS, arena, wseg, tid);
-                        break;
-                    case SBC_OP_ELU:
-                        sbc_elu_op(op, GS, arena, tid, SBC_NTHREADS);
-                        break;
-                    case SBC_OP_AFFINE:
-                        sbc_affine_op(op, GS, arena, tid, SBC_NTHREADS);
-                        break;
-                    case SBC_OP_MAXPOOL5:
-                        sbc_maxpool5_op(op, GS, arena, tid, SBC_NTHREADS);
-                        break;
-                    case SBC_OP_UPACC:
-                        sbc_upacc_op(op, GS, GD, arena, tid, SBC_NTHREADS);
-                        break;
-                    default:
-                        break;
+                long long* sub = nullptr;
+                int kind = op.kind, dbg = 0;
+                if (INSTR) {
+                    sub = do_prof ? L.prof + L.n_ops + 2 + 4 * i : nullptr;   // intra-op stamps (thread 0)
+                    if (sub) sub[0] = sub[1] = sub[2] = sub[3] = 0;
+                    dbg = L.dbg;
+                    if ((dbg & 16) || ((dbg & 4) && kind != SBC_OP_CONV_MMA)) kind = -1;   // timing experiments
                 }
-                if (sub) sub[3] = clock64();
+                if (kind == SBC_OP_CONV_MMA) {
+                    sbc_conv_mma<X3, SMEM_ARENA>(op, GS, GD, arena, wseg, tid, sub, dbg);
+                } else if (kind == SBC_OP_NORM_ELU) {
+                    sbc_norm_op(op, GS, arena, wseg, tid);
+                } else if (kind == SBC_OP_MAXPOOL5) {
+                    sbc_maxpool5_op(op, GS, arena, tid, SBC_NTHREADS);
+                } else if (kind == SBC_OP_ELU) {
+                    sbc_elu_op(op, GS, arena, tid, SBC_NTHREADS);
+                } else if (kind == SBC_OP_UPACC) {
+                    sbc_upacc_op(op, GS, GD, arena, tid, SBC_NTHREADS);
+                } else if (kind == SBC_OP_AFFINE) {
+                    sbc_affine_op(op, GS, arena, tid, SBC_NTHREADS);
+                }
+                // fresh outputs whose halo the planner could not prove clean (interior and halo cells are disjoint)
+                if (op.flags & (SBC_F_ZH_DST | SBC_F_ZH_EDST)) {
+                    const uint16_t* hl = halo + L.halo_off[op.dgeo];
+                    const int nh = GD.pps - GD.h * GD.w;
+                    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo_list(arena + op.dst, GD, hl, nh, op.cout, tid);
+                    if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo_list(arena + op.edst, GD, hl, nh, op.cout, tid);
+                }
+                if (INSTR && sub) sub[3] = clock64();
                 __syncthreads();
             }
-            if (L.debug_stop >= 0) {   // debugging aid: dump the arena of sample 0 and stop
+            if (INSTR && L.debug_stop >= 0) {   // debugging aid: dump the arena of sample 0 and stop
                 if (b == 0)
                     for (int i = tid; i < L.arena_floats; i += SBC_NTHREADS) L.debug_out[i] = arena[i];
                 return;
             }
 
-            if (do_prof) L.prof[L.n_ops] = clock64();
+            if (INSTR && do_prof) L.prof[L.n_ops] = clock64();
             const float* net = arena + L.out_off;   // compact (re, im) pairs
             if (L.mode == 0) {
                 // score = net / sigmas[y]   (ncsnv2.py:295-298)
@@ -661,7 +781,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 }
             }
             __syncthreads();
-            if (do_prof) L.prof[L.n_ops + 1] = clock64();
+            if (INSTR && do_prof) L.prof[L.n_ops + 1] = clock64();
         }
 
         if (L.mode == 1) {   // write the final estimate back (interleaved complex64)

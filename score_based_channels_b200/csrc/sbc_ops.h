@@ -4,9 +4,11 @@
 // CPU thread-emulation harness (tests/emu/emu.cpp) that checks indexing before any GPU time is spent.
 //
 // Layout: see SbcGeo (sbc_program.h): channel-interleaved by 8 (one pixel of one plane = 8 channels = two
-// float4 "quads"), zero halo.  Every op that writes a tensor writes the interior only; because arena regions
-// are recycled between tensors, the halo of a fresh output is re-zeroed (sbc_zero_halo) whenever the offline
-// planner cannot prove that it is still zero (flags SBC_F_ZH_DST / SBC_F_ZH_EDST, program.py:_halo_analysis).  The sampler
+// float4 "quads"), zero halo.  Every op body writes the interior only; because arena regions are recycled
+// between tensors, the CALLER re-zeroes the halo of a fresh output (op.cout channels at op.dst / op.edst)
+// whenever the offline planner cannot prove that it is still zero (flags SBC_F_ZH_DST / SBC_F_ZH_EDST,
+// program.py:_halo_analysis): sbc_zero_halo here (CPU emulation, global-arena path), a list-driven version in
+// sbc_kernel.cuh.  The sampler
 // state x and the raw network output are kept *compact*: interleaved (re, im) pairs [Nt*Nr], exactly the
 // complex64 layout of `current` in reference test_score.py:126.
 //
@@ -203,7 +205,6 @@ SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, 
             *reinterpret_cast<SbcF4*>(dst + p * 8) = sbc_elu4(*reinterpret_cast<const SbcF4*>(src + p * 8));
         });
     }
-    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
 // dst (8 stored channels) = 2*x - 1 on channels 0,1 read from the compact state; channels 2..7 zero
 // (ncsnv2.py:270-271; begin_conv then contracts over one chunk of 8 input channels)
@@ -220,7 +221,6 @@ SBC_HD void sbc_affine_op(const SbcOp& op, const SbcGeo& G, float* arena, int ti
         }
         *sbc_q4(arena + op.dst, G, i & 1, p) = o;
     }
-    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, 8, tid, nthr);
 }
 
 // MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70).  One item = one quad of a column
@@ -253,7 +253,6 @@ SBC_HD void sbc_maxpool5_op(const SbcOp& op, const SbcGeo& G, float* arena, int 
             *sbc_q4(arena + op.dst, G, q, G.org + (y0 + o) * G.wp + x) = m;
         }
     }
-    if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, G, op.cin, tid, nthr);
 }
 
 // acc += bilinear(src, size=(oh,ow), align_corners=True); optional edst = ELU(acc)  (layers.py:182-183)
@@ -282,7 +281,6 @@ SBC_HD void sbc_upacc_op(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, fl
         *a = v;
         if (op.edst >= 0) *sbc_q4(arena + op.edst, GD, q, pd) = sbc_elu4(v);
     }
-    if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cin, tid, nthr);
 }
 
 // ----------------------------------------------------------------------------------------------

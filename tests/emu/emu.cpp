@@ -19,10 +19,6 @@ static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float*
     const bool x3 = (op.flags & SBC_F_X3) != 0;
     const int nq = (op.flags & SBC_F_POOL) ? 4 : 1;
     const int* steptab = reinterpret_cast<const int*>(wseg);
-    for (int t = 0; t < nthr; t++) {
-        if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, t, nthr);
-        if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, t, nthr);
-    }
     for (int mt = 0; mt < op.MT; mt++)
         for (int nt = 0; nt < op.NT; nt++) {
             float D[16][8];
@@ -102,8 +98,6 @@ static void norm_op(const SbcOp& op, const SbcGeo& G, float* arena, const float*
     for (int q = 0; q < nq; q++)
         for (int s = 0; s < T; s++)
             sbc_norm_apply(op, G, arena, wseg, reinterpret_cast<const float*>(mu.data()), q, s, T, mu[q], m2s[q]);
-    if (op.flags & SBC_F_ZH_DST)
-        for (int t = 0; t < nthr; t++) sbc_zero_halo(arena + op.dst, G, C, t, nthr);
 }
 
 extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t* geo_table, const float* blob,
@@ -137,6 +131,11 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t
                 break;
             default:
                 return -2;
+        }
+        // the caller of an op body re-zeroes the halos the planner flagged (see sbc_ops.h)
+        for (int t = 0; t < nthr; t++) {
+            if (op.flags & SBC_F_ZH_DST) sbc_zero_halo(arena + op.dst, GD, op.cout, t, nthr);
+            if (op.flags & SBC_F_ZH_EDST) sbc_zero_halo(arena + op.edst, GD, op.cout, t, nthr);
         }
     }
     return 0;
