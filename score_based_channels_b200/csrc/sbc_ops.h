@@ -226,12 +226,32 @@ SBC_HD void sbc_affine_op(const SbcOp& op, const SbcGeo& G, float* arena, int ti
 // MaxPool2d(5, 1, 2) with implicit -inf padding (reference layers.py:70).  One item = one quad of a column
 // segment of 4 output rows: the horizontal maxima of the 8 input rows it touches are formed once and the
 // four vertical windows slide over them (10 loads per output instead of 25).  H must be a multiple of 4.
+// Maps with at most one output pixel-quad per thread use the direct form instead.
 SBC_HD SbcF4 sbc_max4(SbcF4 a, SbcF4 b) {
     return SbcF4{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)};
 }
 SBC_HD void sbc_maxpool5_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
-    const int H = G.h, W = G.w, HB = H >> 2, per = HB * W, n = (op.cin >> 2) * per, lper = sbc_ilog2(per);
+    const int H = G.h, W = G.w, nq = op.cin >> 2;
     const SbcF4 ninf{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (nq * H * W <= nthr || (H & 3)) {
+        // small maps: one output pixel per thread keeps the per-thread instruction chain short (the SM is
+        // latency bound on such ops, not load bound)
+        const int HW = H * W, lhw = sbc_ilog2(HW);
+        for (int i = tid; i < nq * HW; i += nthr) {
+            const int q = sbc_div(i, HW, lhw), r = i - q * HW;
+            const int y = sbc_div(r, W, G.lw), x = r - y * W;
+            const int y0 = y - 2 < 0 ? 0 : y - 2, y1 = y + 2 >= H ? H - 1 : y + 2;
+            const int x0 = x - 2 < 0 ? 0 : x - 2, x1 = x + 2 >= W ? W - 1 : x + 2;
+            SbcF4 m = ninf;
+            for (int yy = y0; yy <= y1; yy++) {
+                const int p = G.org + yy * G.wp;
+                for (int xx = x0; xx <= x1; xx++) m = sbc_max4(m, *sbc_q4(arena + op.src, G, q, p + xx));
+            }
+            *sbc_q4(arena + op.dst, G, q, G.org + y * G.wp + x) = m;
+        }
+        return;
+    }
+    const int HB = H >> 2, per = HB * W, n = nq * per, lper = sbc_ilog2(per);
     for (int i = tid; i < n; i += nthr) {
         const int q = sbc_div(i, per, lper), r = i - q * per;
         const int yb = sbc_div(r, W, G.lw), x = r - yb * W, y0 = yb << 2;

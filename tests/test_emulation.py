@@ -120,3 +120,15 @@ def test_device_noise_matches_oracle_noise(emu):
     emu.emu_noise(77, 5, 1234, 1024, out.ctypes.data)
     ref = orc.noise(77, 5, 1234, 1024)
     assert np.allclose(out, ref, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("H,W", [(24, 8), (40, 24), (72, 16)])
+def test_emulated_forward_on_non_power_of_two_geometries(emu, H, W):
+    """Row widths / pixel counts that are not powers of two take the division fall-backs of the device
+    code (sbc_div, sbc_for_pixels, direct max-pool); checked against the oracle."""
+    sd = params.random_state(8, seed=5)
+    x = (np.random.default_rng(1).standard_normal((2, H, W)) * 2).astype(np.float32)
+    ref = orc.OracleNet(sd, 8, H, W).forward(x[None], np.array([1200]))[0]
+    prog = program.build_program(sd, 8, H, W)
+    out = prog.read_output(run_emu(emu, prog, x)) / sd["sigmas"][1200]
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 2e-5

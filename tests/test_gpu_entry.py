@@ -74,3 +74,41 @@ def test_real_checkpoint_forward_matches_reference_golden():
                 assert e <= 4096 * e32, (prec, b, e, e32)
                 if e32 < 5e-6:
                     assert e < 6e-3, (prec, b, e)
+
+
+@need
+def test_tf32_mode_trajectory_nmse_within_1e3_of_fp32_equivalent_mode():
+    """north_star tolerance for the fast mode: with the SHIPPED checkpoint, shipped channels and identical
+    pilots / noise (same Philox seed), the per-channel NMSE of the TF32 mode stays within 1e-3 (linear units)
+    of the fp32-equivalent mode at every logged step of a sub-sampled full-range schedule and at the end --
+    although the TF32 *forward* is off by tens of percent at the smallest sigmas (the update is alpha-weighted
+    and the data term makes the dynamics contractive, SURVEY.md section 7 hard part 3)."""
+    from score_based_channels_b200 import entry_common as ec, hdf5_min, sampler, synth
+    dev = torch.device("cuda:0")
+    contents = ec.load_checkpoint(CKPT)
+    h = hdf5_min.loadmat_v73(MAT)["output_h"][:32, 0].astype(np.complex64)
+    Hn = (np.conj(np.transpose(h, (0, 2, 1))) / 0.363263).astype(np.complex64)
+    B, Nt, Nr, Np = Hn.shape[0], 64, 16, 38
+    P = synth.qpsk_pilots(B, Nt, Np, seed=1)
+    snr = np.array([0.0, 10.0, 20.0, 30.0])[np.arange(B) % 4]
+    nv = synth.snr_to_noise_var(snr, Nt).astype(np.float32)
+    Y = synth.received_pilots(P, Hn, nv, seed=2)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(3))
+    tt = lambda a: torch.from_numpy(a).to(dev)
+    res = {}
+    for prec in ("tf32x3", "tf32"):
+        m = ec.build_model(contents["config"], contents["model_state"], dev, prec)
+        X = tt(X0)
+        logs = []
+        # every 7th level across the whole schedule (331 levels x 3 steps), chained launches, same seed
+        for lvl in range(0, 2311, 7):
+            X, nl = sampler.ald_run(m, tt(P), tt(Y), X, tt(Hn), noise_var=tt(nv), alpha_step=3e-11, beta=0.01,
+                                    level_begin=lvl, level_end=lvl + 1, steps_each=3, seed=77)
+            logs.append(nl)
+        res[prec] = torch.cat(logs).cpu().numpy()
+    d = np.abs(res["tf32"] - res["tf32x3"])
+    assert np.isfinite(res["tf32"]).all() and np.isfinite(res["tf32x3"]).all()
+    assert d[-1].max() < 1e-3, ("final", d[-1].max())
+    assert d.max() < 1e-3 * max(1.0, res["tf32x3"].max()), ("trajectory", d.max())
+    # sanity: the sampler is estimating (even on this 7x sub-sampled schedule NMSE at 30 dB is far below 0 dB)
+    assert res["tf32x3"][-1, snr == 30.0].mean() < 0.5 * res["tf32x3"][-1, snr == 0.0].mean()

@@ -284,3 +284,32 @@ def test_debug_arena_matches_schedule_simulator_op_by_op(dev, prec):
                 r = prog.read(ra, off, op.cout, op.oh, op.ow)
                 d, s = np.abs(e - r).max(), np.abs(r).max() + 1e-6
                 assert d / s < 5e-5, (k - 1, op.name, d, s)
+
+
+@pytest.mark.parametrize("Nt,Nr", [(24, 8), (40, 24)])
+def test_non_power_of_two_antenna_counts_match_oracle(dev, Nt, Nr):
+    """Geometries whose row widths are not powers of two (division fall-backs, direct max-pool, ragged last
+    pixel tile): forward and a short ALD run against the oracle."""
+    from oracle import oracle as orc
+    sd, m = _model(8, 5, dev)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((3, 2, Nt, Nr)) * 2).astype(np.float32)
+    y = np.array([0, 1200, 2310])
+    out = m(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)).cpu().numpy()
+    net = orc.OracleNet(sd, 8, Nt, Nr)
+    ref = net.forward(x, y)
+    for b in range(3):
+        assert _rel(out[b], ref[b]) < 2e-5, (Nt, Nr, b, _rel(out[b], ref[b]))
+    B, Np = 3, max(2, int(0.6 * Nt))
+    H = synth.cdl_like_channels(B, Nt, Nr)
+    P = synth.qpsk_pilots(B, Nt, Np)
+    nv = float(synth.snr_to_noise_var(10.0, Nt))
+    Y = synth.received_pilots(P, H, nv)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(4))
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=SIGMA_END, level_begin=0, level_end=2, steps_each=3,
+              seed=5)
+    tt = lambda a: torch.from_numpy(a).to(dev)
+    X, nlog = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), **kw)
+    Xo, nlo = net.ald(P, Y, X0, H, **kw)
+    assert np.abs(X.cpu().numpy() - Xo).max() < 2e-5 * np.abs(Xo).max()
+    assert np.allclose(nlog.cpu().numpy(), nlo, rtol=1e-4)
