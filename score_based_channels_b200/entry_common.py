@@ -47,6 +47,13 @@ def pick_device(gpu: int) -> Tuple[torch.device, int, int]:
     return dev, rank, ws
 
 
+def finalize() -> None:
+    """Tear down torch.distributed at the end of an entry point started under torchrun."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def ald_over_snr(diffuser, val_P, val_H, init_val_H, noise_range, alpha_step, beta_noise, sigma_end, num_levels,
                  steps_each, seed: int, id_base: int = 0, generator: Optional[torch.Generator] = None):
     """The SNR loop + ALD loop of test_score.py:118-171 for one (pilots, channels, init) set, with every SNR

@@ -135,3 +135,4 @@ def main(argv=None):
 
 if __name__ == '__main__':
     main()
+    ec.finalize()
