@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SBC_VERSION 100   /* 0.1.0 */
+#define SBC_VERSION 101   /* 0.1.1: sbc_ald_args gained dc_boost / stop_step (appended) */
 
 enum {
     SBC_OK = 0,
@@ -94,6 +94,10 @@ typedef struct sbc_ald_args {
     uint64_t seed;
     const uint64_t* sample_ids; /* [B] global sample ids (NULL: 0..B-1) */
     const void* ext_noise;    /* [steps,B,Nt,Nr] complex64 unit-power noise replacing the RNG, or NULL */
+    const float* dc_boost;    /* [B] multiplier of the data-consistency term or NULL (= 1)   (test_mmse.py:25,246) */
+    const int32_t* stop_step; /* [B] last step index a sample executes (early stop, `target_stop` of
+                               * test_mmse.py:173,260-263) or NULL (all steps); later NMSE-log rows of that
+                               * sample are left untouched */
 } sbc_ald_args;
 
 int sbc_version(void);

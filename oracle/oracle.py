@@ -32,7 +32,8 @@ class _AldArgs(C.Structure):
                 ("P", C.c_void_p), ("Y", C.c_void_p), ("X", C.c_void_p), ("H_oracle", C.c_void_p),
                 ("noise_var", C.c_void_p), ("alpha_step", C.c_void_p), ("beta", C.c_void_p),
                 ("sigmas", C.c_void_p), ("sigma_end", C.c_double), ("nmse_log", C.c_void_p),
-                ("seed", C.c_uint64), ("sample_ids", C.c_void_p), ("ext_noise", C.c_void_p)]
+                ("seed", C.c_uint64), ("sample_ids", C.c_void_p), ("ext_noise", C.c_void_p),
+                ("dc_boost", C.c_void_p), ("stop_step", C.c_void_p)]
 
 
 def lib():
@@ -85,7 +86,8 @@ class OracleNet:
         return out
 
     def ald(self, P, Y, X0, H=None, *, noise_var, alpha_step, beta, sigma_end, level_begin=0,
-            level_end=None, steps_each=3, seed=0, sample_ids=None, ext_noise=None, log=True):
+            level_end=None, steps_each=3, seed=0, sample_ids=None, ext_noise=None, log=True, dc_boost=None,
+            stop_step=None):
         """Annealed Langevin loop of test_score.py:135-171 for a batch with per-sample scalars.
 
         P [B,Np,Nt], Y [B,Np,Nr], X0/H [B,Nt,Nr] complex64.  Returns (X_final, nmse_log[steps,B] or None)."""
@@ -103,11 +105,14 @@ class OracleNet:
         en = _c64(ext_noise) if ext_noise is not None else None
         if en is not None:
             assert en.shape == (nsteps, B, Nt, Nr)
+        db = _f32(np.broadcast_to(np.asarray(dc_boost, np.float32), (B,))) if dc_boost is not None else None
+        st = np.ascontiguousarray(np.broadcast_to(np.asarray(stop_step, np.int32), (B,))) if stop_step is not None else None
         a = _AldArgs(B, Nt, Nr, Np, level_begin, level_end, steps_each, P.ctypes.data, Y.ctypes.data,
                      X.ctypes.data, Hc.ctypes.data if Hc is not None else None, nv.ctypes.data, al.ctypes.data,
                      be.ctypes.data, self.sigmas.ctypes.data, float(sigma_end),
                      nlog.ctypes.data if nlog is not None else None, int(seed),
-                     ids.ctypes.data if ids is not None else None, en.ctypes.data if en is not None else None)
+                     ids.ctypes.data if ids is not None else None, en.ctypes.data if en is not None else None,
+                     db.ctypes.data if db is not None else None, st.ctypes.data if st is not None else None)
         self.L.orc_ald_run(self.h, C.byref(a))
         return X, nlog
 

@@ -33,7 +33,8 @@ class AldArgs(C.Structure):
                 ("P", C.c_void_p), ("Y", C.c_void_p), ("X", C.c_void_p), ("H_oracle", C.c_void_p),
                 ("noise_var", C.c_void_p), ("alpha_step", C.c_void_p), ("beta", C.c_void_p),
                 ("sigma_end", C.c_double), ("nmse_log", C.c_void_p), ("seed", C.c_uint64),
-                ("sample_ids", C.c_void_p), ("ext_noise", C.c_void_p)]
+                ("sample_ids", C.c_void_p), ("ext_noise", C.c_void_p), ("dc_boost", C.c_void_p),
+                ("stop_step", C.c_void_p)]
 
 
 _lib = None

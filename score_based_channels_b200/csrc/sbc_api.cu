@@ -256,6 +256,7 @@ static void fill_ald(SbcLaunch& L, const sbc_ald_args* a) {
     L.noise_var = a->noise_var; L.alpha_step = a->alpha_step; L.beta = a->beta; L.sigma_end = a->sigma_end;
     L.nmse_log = a->nmse_log; L.seed = a->seed; L.sample_ids = (const unsigned long long*)a->sample_ids;
     L.ext_noise = (const float*)a->ext_noise;
+    L.dc_boost = a->dc_boost; L.stop_step = a->stop_step;
 }
 
 extern "C" int sbc_ald_run(void* handle, const sbc_ald_args* a, void* stream) {
@@ -303,7 +304,7 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
     SBC_CUDA(cudaSetDevice(m->device));
     const size_t B = a->B, ne = (size_t)a->Nt * a->Nr, steps = (size_t)(a->level_end - a->level_begin) * a->steps_each;
     const size_t nP = B * a->Np * a->Nt * 8, nY = B * a->Np * a->Nr * 8, nX = B * ne * 8;
-    DevBuf dP, dY, dX, dH, dnv, dal, dbe, dlog, dids, dn;
+    DevBuf dP, dY, dX, dH, dnv, dal, dbe, dlog, dids, dn, ddb, dst;
     if (dP.alloc(nP) || dY.alloc(nY) || dX.alloc(nX) || dnv.alloc(B * 4) || dal.alloc(B * 4) || dbe.alloc(B * 4))
         return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
     SBC_CUDA(cudaMemcpy(dP.p, a->P, nP, cudaMemcpyHostToDevice));
@@ -333,6 +334,17 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
         if (dn.alloc(steps * nX)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
         SBC_CUDA(cudaMemcpy(dn.p, a->ext_noise, steps * nX, cudaMemcpyHostToDevice));
         d.ext_noise = dn.p;
+    }
+    if (a->dc_boost) {
+        if (ddb.alloc(B * 4)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        SBC_CUDA(cudaMemcpy(ddb.p, a->dc_boost, B * 4, cudaMemcpyHostToDevice));
+        d.dc_boost = (const float*)ddb.p;
+    }
+    if (a->stop_step) {
+        if (dst.alloc(B * 4)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+        SBC_CUDA(cudaMemcpy(dst.p, a->stop_step, B * 4, cudaMemcpyHostToDevice));
+        d.stop_step = (const int32_t*)dst.p;
+        if (a->nmse_log) SBC_CUDA(cudaMemcpy(dlog.p, a->nmse_log, steps * B * 4, cudaMemcpyHostToDevice));   // untouched rows
     }
     rc = sbc_ald_run(handle, &d, nullptr);
     if (rc) return rc;

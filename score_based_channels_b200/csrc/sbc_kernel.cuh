@@ -51,6 +51,8 @@ struct SbcLaunch {
     unsigned long long seed;
     const unsigned long long* sample_ids;  // [B] or null
     const float* ext_noise;  // [steps,B,Nt,Nr] complex64 or null
+    const float* dc_boost;   // [B] or null (= 1)
+    const int* stop_step;    // [B] or null: last step index executed by a sample
     // execution
     float* gws;              // global arena workspace (when the arena does not fit in shared memory)
     int stage_weights;       // 1: cp.async.bulk double buffering, 0: read parameters from global/L2
@@ -664,8 +666,14 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
         }
         __syncthreads();
 
-        for (int gs = 0; gs < nsteps; gs++) {
-            const bool last_step = (gs + 1 == nsteps);
+        // early stop (test_mmse.py:260-263): the sample executes steps 0 .. stop_step[b] only
+        int nsteps_b = nsteps;
+        if (L.mode == 1 && L.stop_step) {
+            const int st = L.stop_step[b] + 1;
+            nsteps_b = st < 1 ? 1 : (st < nsteps ? st : nsteps);   // at least step 0, like the reference loop
+        }
+        for (int gs = 0; gs < nsteps_b; gs++) {
+            const bool last_step = (gs + 1 == nsteps_b);
             int lvl = 0;
             if (L.mode == 1) {
                 lvl = L.level_begin + gs / L.steps_each;
@@ -675,7 +683,8 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     const double alpha = (double)L.alpha_step[b] * ratio * ratio;
                     s_sc.sigma = L.sigmas[lvl];
                     s_sc.alpha = (float)alpha;
-                    s_sc.den = (float)((double)L.noise_var[b] / 2. + sigma * sigma);
+                    // data-consistency weight 1 / (local_noise/2 + sigma^2), optionally boosted (test_mmse.py:246)
+                    s_sc.den = (float)((double)L.noise_var[b] / 2. + sigma * sigma) / (L.dc_boost ? L.dc_boost[b] : 1.f);
                     s_sc.nscale = (float)sqrt(2. * alpha * (double)L.beta[b]);
                 }
             }

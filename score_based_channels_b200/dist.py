@@ -63,3 +63,17 @@ def run_sharded(fn: Callable[[int, int], torch.Tensor], total: int) -> torch.Ten
     rank, ws = world()
     lo, hi = shard_range(total, rank, ws)
     return gather_columns(fn(lo, hi), total)
+
+
+def gather_rows(local: torch.Tensor, total: int) -> torch.Tensor:
+    """All-gather a [B_local, ...] real tensor whose rows are this rank's `shard_range(total, ...)` slice into the
+    full [total, ...] tensor (every rank gets it)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    per = (total + ws - 1) // ws
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad.contiguous())
+    return torch.cat(bufs, dim=0)[:total]

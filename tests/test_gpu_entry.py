@@ -112,3 +112,28 @@ def test_tf32_mode_trajectory_nmse_within_1e3_of_fp32_equivalent_mode():
     assert d.max() < 1e-3 * max(1.0, res["tf32x3"].max()), ("trajectory", d.max())
     # sanity: the sampler is estimating (even on this 7x sub-sampled schedule NMSE at 30 dB is far below 0 dB)
     assert res["tf32x3"][-1, snr == 30.0].mean() < 0.5 * res["tf32x3"][-1, snr == 0.0].mean()
+
+
+@need
+def test_test_mmse_entry_point_small(tmp_path, monkeypatch):
+    """Approximate-MMSE drop-in (reference test_mmse.py): result-file keys / shapes, early stop, start points."""
+    monkeypatch.chdir(REPO)
+    from score_based_channels_b200 import test_mmse
+    hyper = os.path.join(str(tmp_path), "hyper.pt")
+    torch.save({"best_step_idx": np.full((1, 2), 3e-11), "best_noise_idx": np.full((1, 2), 0.01),
+                "best_stop_idx": np.array([[4, 100]])}, hyper)
+    for sp in ("Noise", "Adjoint", "LS"):
+        out = test_mmse.main(["--gpu", "0", "--ckpt", CKPT, "--hyper", hyper, "--out_dir", str(tmp_path), "--levels", "3",
+                              "--kept_samples", "4", "--mmse_avg", "3", "--snr_range", "0", "10", "--start_point", sp,
+                              "--dc_boost", "1.5", "--seed", "0"])
+        res = torch.load(os.path.join(str(tmp_path), "model_CDL-C_channel_CDL-C.pt"), weights_only=False)
+        assert set(res.keys()) == {"spacing_range", "pilot_alpha_range", "args", "config", "snr_range", "val_config",
+                                   "oracle_log", "oracle_H", "saved_H", "mmse_nmse"}          # test_mmse.py:278-288 (+1)
+        assert res["oracle_log"].shape == (1, 1, 2, 9, 4, 3) and res["saved_H"].shape == (1, 1, 2, 4, 3, 64, 16)
+        lg = res["oracle_log"][0, 0]
+        assert np.isfinite(lg[0, :5]).all() and np.isnan(lg[0, 5:]).all()     # SNR 0: stopped after step 4
+        assert np.isfinite(lg[1]).all()                                       # SNR 1: stop beyond the schedule
+        assert np.isfinite(res["mmse_nmse"]).all() and (res["mmse_nmse"] > 0).all()
+        assert res["oracle_H"].shape == (4, 64, 16)
+    # averaging posterior samples cannot be worse than the mean of the individual NMSEs (Jensen), SNR 1, last step
+    assert (out["mmse_nmse"][0, 0, 1] <= np.nanmean(out["oracle_log"][0, 0, 1, -1], axis=-1) * (1 + 1e-5)).all()

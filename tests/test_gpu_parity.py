@@ -44,7 +44,7 @@ def _rel(a, b):
 
 def test_native_library_is_the_one_running(dev):
     L = _lib.lib()
-    assert L.sbc_version() == 100
+    assert L.sbc_version() == 101
     sd, m = _model(8, 1, dev)
     info = m.packed(64, 16, dev).info()
     assert info.num_sms >= 100 and info.threads_per_cta == 512
@@ -313,3 +313,30 @@ def test_non_power_of_two_antenna_counts_match_oracle(dev, Nt, Nr):
     Xo, nlo = net.ald(P, Y, X0, H, **kw)
     assert np.abs(X.cpu().numpy() - Xo).max() < 2e-5 * np.abs(Xo).max()
     assert np.allclose(nlog.cpu().numpy(), nlo, rtol=1e-4)
+
+
+def test_dc_boost_and_early_stop_match_oracle(dev):
+    """The approximate-MMSE knobs of reference test_mmse.py (dc_boost :25,246; target_stop :173,260-263) as
+    kernel arguments: per-sample boost and per-sample last step, against the oracle; rows of the NMSE log after a
+    sample's stop stay NaN and its state is the one after the stop step."""
+    from oracle import oracle as orc
+    sd, m = _model(8, 1, dev)
+    B = 5
+    P, Y, X0, H, nv = _problem(B, snr=5.0, seed=3)
+    boost = np.array([1.0, 2.0, 0.5, 4.0, 1.0], np.float32)
+    stop = np.array([0, 2, 5, 4, 99], np.int32)                     # 6 steps in total: 99 = no early stop
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=SIGMA_END, level_begin=0, level_end=2, steps_each=3,
+              seed=21)
+    tt = lambda a: torch.from_numpy(a).to(dev)
+    X, nlog = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), dc_boost=tt(boost), stop_step=tt(stop), **kw)
+    Xo, nlo = orc.OracleNet(sd, 8, 64, 16).ald(P, Y, X0, H, dc_boost=boost, stop_step=stop, **kw)
+    assert np.abs(X.cpu().numpy() - Xo).max() < 2e-5 * np.abs(Xo).max()
+    ng = nlog.cpu().numpy()
+    for b in range(B):
+        k = min(int(stop[b]) + 1, 6)
+        assert np.allclose(ng[:k, b], nlo[:k, b], rtol=1e-4), b
+        assert np.isnan(ng[k:, b]).all(), b
+    # boost = 1 and no stop reproduce the plain path bit for bit
+    Xa, la = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), **kw)
+    Xb, lb = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), dc_boost=1.0, stop_step=1000, **kw)
+    assert torch.equal(Xa, Xb) and torch.equal(la, lb)
