@@ -60,6 +60,7 @@ typedef struct sbc_model_desc {
     const float* sigmas;    /* host, [n_sigmas] fp32 noise schedule (reference ncsnv2/models/__init__.py:4-8) */
     int32_t n_sigmas;
     int64_t conv_flops;     /* dense conv FLOP / forward / sample (reported by sbc_query) */
+    int32_t nthreads;       /* threads per CTA the program was planned for: must equal sbc_threads_per_cta() */
 } sbc_model_desc;
 
 typedef struct sbc_info {
@@ -101,6 +102,7 @@ typedef struct sbc_ald_args {
 } sbc_ald_args;
 
 int sbc_version(void);
+int sbc_threads_per_cta(void);   /* compile-time CTA size of the fused kernel (the host planner needs it) */
 const char* sbc_last_error(void);
 
 int sbc_model_create(const sbc_model_desc* desc, int device, void** handle_out);

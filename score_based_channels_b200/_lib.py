@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbc_b200.so")
 
-EXPORTS = ("sbc_version", "sbc_last_error", "sbc_model_create", "sbc_model_free", "sbc_query", "sbc_forward",
+EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_free", "sbc_query", "sbc_forward",
            "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host", "sbc_debug_arena", "sbc_set_profile_buffer")
 
 
@@ -18,7 +18,8 @@ class ModelDesc(C.Structure):
                 ("op_table", C.c_void_p), ("n_ops", C.c_int32), ("geo_table", C.c_void_p), ("n_geo", C.c_int32),
                 ("blob", C.c_void_p), ("blob_floats", C.c_int64),
                 ("arena_floats", C.c_int32), ("in_off", C.c_int32), ("out_off", C.c_int32), ("post_off", C.c_int32),
-                ("max_w_len", C.c_int32), ("sigmas", C.c_void_p), ("n_sigmas", C.c_int32), ("conv_flops", C.c_int64)]
+                ("max_w_len", C.c_int32), ("sigmas", C.c_void_p), ("n_sigmas", C.c_int32), ("conv_flops", C.c_int64),
+                ("nthreads", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -49,6 +50,7 @@ def lib():
                                "(there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         L.sbc_version.restype = C.c_int
+        L.sbc_threads_per_cta.restype = C.c_int
         L.sbc_last_error.restype = C.c_char_p
         L.sbc_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
         L.sbc_model_free.argtypes = [C.c_void_p]

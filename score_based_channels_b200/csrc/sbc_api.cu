@@ -48,6 +48,7 @@ struct SbcModel {
 };
 
 extern "C" int sbc_version(void) { return SBC_VERSION; }
+extern "C" int sbc_threads_per_cta(void) { return SBC_NTHREADS; }
 extern "C" const char* sbc_last_error(void) { return g_err; }
 
 static int env_int(const char* name, int dflt) {
@@ -64,6 +65,9 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         return sbc_fail(SBC_E_ARG, "sbc_model_create: Nt (%d) and Nr (%d) must be positive multiples of 8", desc->Nt,
                         desc->Nr);
     if (desc->channels != 2) return sbc_fail(SBC_E_ARG, "sbc_model_create: channels must be 2 (re, im)");
+    if (desc->nthreads != SBC_NTHREADS)
+        return sbc_fail(SBC_E_ARG, "sbc_model_create: program planned for %d threads per CTA, library built for %d",
+                        desc->nthreads, SBC_NTHREADS);
     if (desc->arena_floats % 4 || desc->max_w_len % 4)
         return sbc_fail(SBC_E_ARG, "sbc_model_create: arena_floats and max_w_len must be multiples of 4");
     int ndev = 0;

@@ -15,7 +15,11 @@
 #include "sbc_mma.h"
 #include "sbc_ops.h"
 
+#ifndef SBC_NTHREADS
 #define SBC_NTHREADS 512
+#endif
+// pixel tiles one warp accumulates per pass (register budget: 128 regs/thread at 512 threads, 64 at 1024)
+#define SBC_MAXNS (SBC_NTHREADS > 512 ? 2 : 4)
 
 struct SbcLaunch {
     // layer program
@@ -364,24 +368,35 @@ __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS
     sbc_epilogue_batch<NS, NN>(e, arena, wseg, pd, q0, nt0, lane, acc);
 }
 
-// ConvMeanPool: one output tile, the four pooling positions are the four slots
+// ConvMeanPool: one output tile, the four pooling positions are slots (SBC_MAXNS at a time)
 template <bool X3, bool SMEM, int NN>
 __device__ __forceinline__ void sbc_conv_pooled(const SbcOp& op, const SbcGeo& GS, const float* wseg,
                                                 const SbcALane<SMEM>& A, const float* bfrag, int bstride, int mt,
                                                 int s0, int s1, int lane, float (&c)[NN][4]) {
-    int po[4][2];
+    constexpr int QS = SBC_MAXNS < 4 ? SBC_MAXNS : 4;
 #pragma unroll
-    for (int j = 0; j < 4; j++) A.rows(op, GS, mt, j, lane, po[j]);
-    float acc[4][NN][4];
+    for (int n = 0; n < NN; n++) c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < 4; q0 += QS) {
+        int po[QS][2];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+        for (int j = 0; j < QS; j++) A.rows(op, GS, mt, q0 + j, lane, po[j]);
+        float acc[QS][NN][4];
 #pragma unroll
-        for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
-    sbc_mma_pass<X3, SMEM, 4, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, s0, s1, acc);
+        for (int j = 0; j < QS; j++)
 #pragma unroll
-    for (int n = 0; n < NN; n++)
+            for (int n = 0; n < NN; n++) acc[j][n][0] = acc[j][n][1] = acc[j][n][2] = acc[j][n][3] = 0.f;
+        sbc_mma_pass<X3, SMEM, QS, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, s0, s1, acc);
 #pragma unroll
-        for (int i = 0; i < 4; i++) c[n][i] = (acc[0][n][i] + acc[1][n][i]) + (acc[2][n][i] + acc[3][n][i]);
+        for (int n = 0; n < NN; n++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float t = acc[0][n][i];
+#pragma unroll
+                for (int j = 1; j < QS; j++) t += acc[j][n][i];
+                c[n][i] += t;
+            }
+    }
 }
 
 template <bool X3, bool SMEM>
@@ -459,23 +474,23 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
         return;
     }
 
-    // enough pixel tiles for every warp: warp w owns tiles w, w+NW, ... (up to 4 per pass); cout tiles are
-    // processed in pairs that share the gathered A fragments
-    for (int mt0 = warp; mt0 < MT; mt0 += 4 * NW) {
+    // enough pixel tiles for every warp: warp w owns tiles w, w+NW, ... (up to SBC_MAXNS per pass); cout tiles
+    // are processed in pairs that share the gathered A fragments
+    for (int mt0 = warp; mt0 < MT; mt0 += SBC_MAXNS * NW) {
         int ntile = (MT - mt0 + NW - 1) / NW;
-        if (ntile > 4) ntile = 4;
+        if (ntile > SBC_MAXNS) ntile = SBC_MAXNS;
         for (int nt0 = 0; nt0 < NT; nt0 += 2) {
             const float* bf = bf0 + nt0 * 32 * E;
             const bool two = NT - nt0 >= 2;
             if (ntile == 1) {
                 if (two) sbc_conv_tiles<X3, SMEM, 1, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
                 else sbc_conv_tiles<X3, SMEM, 1, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
-            } else if (ntile == 2) {
+            } else if (ntile == 2 || SBC_MAXNS == 2) {
                 if (two) sbc_conv_tiles<X3, SMEM, 2, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
                 else sbc_conv_tiles<X3, SMEM, 2, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             } else {
-                if (two) sbc_conv_tiles<X3, SMEM, 4, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
-                else sbc_conv_tiles<X3, SMEM, 4, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                if (two) sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             }
         }
     }

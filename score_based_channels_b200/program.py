@@ -418,9 +418,9 @@ class ProgramBuilder:
             MT = (oh * ow + 15) // 16
             units = MT * ntc
             ks = 1
-            while units * ks * 2 <= nwarps and ks * 2 <= S:
+            while units * ks * 2 <= min(nwarps, 16) and ks * 2 <= S:     # at most 16 warps take part in a K split
                 ks *= 2
-            scratch = self.tmp_raw(nwarps * 32 * 4, "ksp") if ks > 1 else None
+            scratch = self.tmp_raw(units * ks * 32 * 4, "ksp") if ks > 1 else None
             flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0)
             if compact:
                 assert nt_chunk == NT and cout == 2 and acc is None and edst is None
@@ -688,7 +688,7 @@ class ProgramBuilder:
         for op in self.ops:
             raw(op.wbuf, op.w_len)
             if op.kind == OP_CONV_MMA:
-                raw(op.scratch, nwarps * 32 * 4)
+                raw(op.scratch, op.MT * op.NT * op.ks * 32 * 4 if op.ks > 1 else 0)
                 if op.flags & F_COMPACT:
                     raw(op.dst, self.channels * op.oh * op.ow)
                 elif op.dst >= 0 and fresh(op.dst, op.dgeo, op.cout):
