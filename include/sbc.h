@@ -129,9 +129,10 @@ int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
 int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
 
 /* Profiling aid: subsequent launches of this handle make CTA 0 record clock64() at every op
- * boundary of its first sample / second step (first if there is only one) into dev_stamps (device int64 [5 * n_ops + 2]: op starts,
+ * boundary of its first sample / second step (first if there is only one) into dev_stamps (device int64 [6 * n_ops + 2]: op starts,
  * end of network, end of the Langevin update, then 4 intra-op stamps per op: conv = {prologue done, K loop
- * entered, K loop done, epilogue done}).  NULL switches it off. */
+ * entered, K loop done, epilogue done}, then per op the time at which its record and parameters were in hand).
+ * NULL switches it off. */
 int sbc_set_profile_buffer(void* handle, int64_t* dev_stamps);
 
 #ifdef __cplusplus

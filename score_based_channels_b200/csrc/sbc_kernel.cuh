@@ -733,13 +733,14 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     wseg = arena + op.wbuf;
                     wcount++;
                 }
+                const long long t_wait = (INSTR && do_prof) ? clock64() : 0;
                 const SbcGeo& GS = L.geo[op.sgeo];
                 const SbcGeo& GD = L.geo[op.dgeo];
                 long long* sub = nullptr;
                 int kind = op.kind, dbg = 0;
                 if (INSTR) {
                     sub = do_prof ? L.prof + L.n_ops + 2 + 4 * i : nullptr;   // intra-op stamps (thread 0)
-                    if (sub) sub[0] = sub[1] = sub[2] = sub[3] = 0;
+                    if (sub) { sub[0] = sub[1] = sub[2] = sub[3] = 0; L.prof[5 * L.n_ops + 2 + i] = t_wait; }
                     dbg = L.dbg;
                     if ((dbg & 16) || ((dbg & 4) && kind != SBC_OP_CONV_MMA)) kind = -1;   // timing experiments
                 }

@@ -31,7 +31,7 @@ e1.record()
 torch.cuda.synchronize()
 print("precision %s forward B=%d: %.3f ms per launch" % (PREC, B, e0.elapsed_time(e1) / 10))
 
-stamps = torch.zeros(5 * len(prog.ops) + 2, dtype=torch.int64, device=dev)
+stamps = torch.zeros(6 * len(prog.ops) + 2, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, stamps.data_ptr()), "prof")
 P = torch.from_numpy(synth.qpsk_pilots(B, 64, 38)).to(dev)
 H = torch.from_numpy(synth.cdl_like_channels(B)).to(dev)
@@ -42,7 +42,8 @@ torch.cuda.synchronize()
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, None), "prof")
 full = stamps.cpu().numpy()
 st = full[:len(prog.ops) + 2]
-sub = full[len(prog.ops) + 2:].reshape(len(prog.ops), 4)
+sub = full[len(prog.ops) + 2:5 * len(prog.ops) + 2].reshape(len(prog.ops), 4)
+tw = full[5 * len(prog.ops) + 2:]
 d = np.diff(st)
 tot = st[-1] - st[0]
 print("CTA0 second step (warm): %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
@@ -66,6 +67,8 @@ for i, op in enumerate(prog.ops):
         e = int(st[i + 1])
         phases = " | pro %d ent %d loop %d epi %d bar %d" % (ss[0] - st[i], max(ss[1] - ss[0], 0), max(ss[2] - ss[1], 0),
                                                           ss[3] - max(ss[2], ss[0]), e - ss[3])
+    if tw[i] > 0:
+        phases += " | fetch+wait %d" % (tw[i] - st[i])
     rows.append((i, op.name, key + phases, c))
 print("\n== by op class (cycles, count, cycles/op, share of network)")
 net = st[-2] - st[0]
