@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <memory>
 #include <vector>
 
 #include "../../include/sbc.h"
@@ -45,6 +46,9 @@ struct SbcModel {
     SbcGeo geo[SBC_MAX_GEO];
     int n_geo = 0;
     int halo_off[SBC_MAX_GEO] = {0};
+    ~SbcModel() {   // owns its device buffers: every early return of sbc_model_create releases them
+        cudaFree(d_ops); cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
+    }
 };
 
 extern "C" int sbc_version(void) { return SBC_VERSION; }
@@ -74,20 +78,21 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SBC_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return sbc_fail(SBC_E_ARG, "sbc_model_create: no CUDA device %d", device);
     SBC_CUDA(cudaSetDevice(device));
-    SbcModel* m = new SbcModel();
+    std::unique_ptr<SbcModel> mh(new SbcModel());
+    SbcModel* m = mh.get();
     m->device = device;
     m->d = *desc;
-    if (!desc->geo_table || desc->n_geo <= 0 || desc->n_geo > SBC_MAX_GEO) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: bad geometry table"); }
+    if (!desc->geo_table || desc->n_geo <= 0 || desc->n_geo > SBC_MAX_GEO) { return sbc_fail(SBC_E_ARG, "sbc_model_create: bad geometry table"); }
     memset(m->geo, 0, sizeof m->geo);
     memcpy(m->geo, desc->geo_table, sizeof(SbcGeo) * (size_t)desc->n_geo);
     m->n_geo = desc->n_geo;
     int halo_total = 0;   // uint16 entries of the per-geometry halo-pixel lists (shared misc region)
     for (int g = 0; g < desc->n_geo; g++) {
-        if (m->geo[g].pps > 65535) { delete m; return sbc_fail(SBC_E_UNSUPPORTED, "geometry %d: plane too large", g); }
+        if (m->geo[g].pps > 65535) { return sbc_fail(SBC_E_UNSUPPORTED, "geometry %d: plane too large", g); }
         m->halo_off[g] = halo_total;
         halo_total += m->geo[g].pps - m->geo[g].h * m->geo[g].w;
     }
-    if (m->geo[0].h != desc->Nt || m->geo[0].w != desc->Nr) { delete m; return sbc_fail(SBC_E_ARG, "sbc_model_create: geometry 0 must be Nt x Nr"); }
+    if (m->geo[0].h != desc->Nt || m->geo[0].w != desc->Nr) { return sbc_fail(SBC_E_ARG, "sbc_model_create: geometry 0 must be Nt x Nr"); }
     SBC_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
     SBC_CUDA(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 
@@ -99,9 +104,9 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         SbcOp& o = ops[i];
         o.next_w = next;
         if (o.w_len > 0) next = i;
-        if (o.kind < 0 || o.kind > SBC_OP_LAST) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
+        if (o.kind < 0 || o.kind > SBC_OP_LAST) { return sbc_fail(SBC_E_ARG, "op %d: bad kind %d", i, o.kind); }
         if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
-            o.w_len > desc->max_w_len) { delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
+            o.w_len > desc->max_w_len) { return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
         if (o.sgeo < 0 || o.sgeo >= SBC_MAX_GEO || o.dgeo < 0 || o.dgeo >= SBC_MAX_GEO) {
             delete m; return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
         }
@@ -115,13 +120,13 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
                             o.cout % 2 == 0 && o.MT == (o.oh * o.ow + 15) / 16 && o.NT == (o.cout + 7) / 8 &&
                             o.S >= 1 && o.frag_rel >= o.S && o.frag_rel % 4 == 0 &&
                             o.frag_rel + o.S * o.NT * 32 * E <= o.w_len;
-            if (!ok) { delete m; return sbc_fail(SBC_E_ARG, "op %d: unsupported tensor-core conv", i); }
+            if (!ok) { return sbc_fail(SBC_E_ARG, "op %d: unsupported tensor-core conv", i); }
             const bool ox3 = (o.flags & SBC_F_X3) != 0;
             if (nconv++ == 0) m->x3 = ox3;
-            else if (m->x3 != ox3) { delete m; return sbc_fail(SBC_E_ARG, "op %d: mixed conv precisions", i); }
+            else if (m->x3 != ox3) { return sbc_fail(SBC_E_ARG, "op %d: mixed conv precisions", i); }
         }
         if ((o.kind == SBC_OP_NORM_ELU || o.kind == SBC_OP_ELU || o.kind == SBC_OP_MAXPOOL5 || o.kind == SBC_OP_UPACC) &&
-            o.cin % 8) { delete m; return sbc_fail(SBC_E_ARG, "op %d: channel count must be a multiple of 8", i); }
+            o.cin % 8) { return sbc_fail(SBC_E_ARG, "op %d: channel count must be a multiple of 8", i); }
     }
     // parameter segment of the next parameterised op (the last one wraps to the first)
     for (int i = 0; i < desc->n_ops; i++) {
@@ -161,7 +166,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-    *handle_out = m;
+    *handle_out = mh.release();
     return SBC_OK;
 }
 
@@ -169,7 +174,6 @@ extern "C" int sbc_model_free(void* handle) {
     if (!handle) return SBC_OK;
     SbcModel* m = (SbcModel*)handle;
     cudaSetDevice(m->device);
-    cudaFree(m->d_ops); cudaFree(m->d_blob); cudaFree(m->d_sigmas); cudaFree(m->d_gws);
     delete m;
     return SBC_OK;
 }

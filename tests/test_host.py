@@ -156,3 +156,48 @@ def test_sharding_and_nmse_gather_world_size_2_gloo(tmp_path):
             spans = [sdist.shard_range(total, k, world) for k in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _gather_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sdist.init_from_env("gloo")
+    total = 7                                             # ragged: 4 + 3
+    lo, hi = sdist.shard_range(total, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
+    full = sdist.gather_rows(local, total)
+    expect = torch.arange(total, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
+    torch.save({"ok": torch.equal(full, expect)}, os.path.join(tmp, "g%d.pt" % rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_gather_rows_world_size_2_gloo(tmp_path):
+    """The final-estimate gather of the approximate-MMSE entry point (test_mmse.py), ragged shards."""
+    import torch.multiprocessing as mp
+    port = 29600 + os.getpid() % 200
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert torch.load(os.path.join(str(tmp_path), "g%d.pt" % r))["ok"]
+
+
+def test_oracle_dc_boost_and_early_stop_semantics():
+    """Oracle side of the approximate-MMSE knobs (reference test_mmse.py:25,246 and :173,260-263): boost 1 / no stop is
+    the plain loop; a stopped sample equals a run truncated after stop+1 steps; the boost scales the DC term."""
+    from oracle import oracle as orc
+    from score_based_channels_b200 import synth
+    sd = params.random_state(8, seed=1)
+    net = orc.OracleNet(sd, 8, 64, 16)
+    B = 2
+    P, H = synth.qpsk_pilots(B, 64, 38), synth.cdl_like_channels(B, 64, 16)
+    Y = synth.received_pilots(P, H, 1.0)
+    X0 = synth.cn01((B, 64, 16), np.random.default_rng(1))
+    kw = dict(noise_var=1.0, alpha_step=3e-11, beta=0.01, sigma_end=2.6e-4, level_begin=0, steps_each=3, seed=3)
+    Xa, la = net.ald(P, Y, X0, H, level_end=2, **kw)
+    Xb, lb = net.ald(P, Y, X0, H, level_end=2, dc_boost=1.0, stop_step=99, **kw)
+    assert np.array_equal(Xa, Xb) and np.array_equal(la, lb)
+    Xc, lc = net.ald(P, Y, X0, H, level_end=2, stop_step=np.array([2, 5], np.int32), **kw)     # sample 0: steps 0..2
+    Xd, ld = net.ald(P, Y, X0, H, level_end=1, **kw)                                            # one level = 3 steps
+    assert np.array_equal(Xc[0], Xd[0]) and np.array_equal(lc[:3, 0], ld[:, 0]) and np.all(lc[3:, 0] == 0)
+    assert np.array_equal(Xc[1], Xa[1])
+    Xe, _ = net.ald(P, Y, X0, H, level_end=2, dc_boost=4.0, **kw)
+    assert np.abs(Xe - Xa).max() > 1e-4 * np.abs(Xa).max()
