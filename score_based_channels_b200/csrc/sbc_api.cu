@@ -108,10 +108,10 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         if (o.w_len < 0 || o.w_len % 4 || o.w_off % 4 || (long long)o.w_off + o.w_len > desc->blob_floats ||
             o.w_len > desc->max_w_len) { return sbc_fail(SBC_E_ARG, "op %d: bad parameter segment", i); }
         if (o.sgeo < 0 || o.sgeo >= SBC_MAX_GEO || o.dgeo < 0 || o.dgeo >= SBC_MAX_GEO) {
-            delete m; return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
+            return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
         }
         if (o.w_len > 0 && (o.wbuf < 0 || o.wbuf % 4 || o.wbuf + o.w_len > desc->arena_floats)) {
-            delete m; return sbc_fail(SBC_E_ARG, "op %d: bad parameter staging buffer", i);
+            return sbc_fail(SBC_E_ARG, "op %d: bad parameter staging buffer", i);
         }
         if (o.kind == SBC_OP_CONV_MMA) {
             const int E = 2;
