@@ -117,6 +117,8 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
             const int E = 2;
             const bool ok = o.ks >= 1 && o.ks <= SBC_NTHREADS / 32 && (o.ks & (o.ks - 1)) == 0 &&
                             (o.ksize == 1 || o.ksize == 3) && o.tapmask != 0 && (o.ks == 1 || o.scratch >= 0) &&
+                            (o.ks == 1 || (o.flags & SBC_F_UNIT)) &&
+                            (!(o.flags & SBC_F_UNIT) || o.MT * o.NT * o.ks <= SBC_NTHREADS / 32) &&
                             o.cout % 2 == 0 && o.MT == (o.oh * o.ow + 15) / 16 && o.NT == (o.cout + 7) / 8 &&
                             o.S >= 1 && o.frag_rel >= o.S && o.frag_rel % 4 == 0 &&
                             o.frag_rel + o.S * o.NT * 32 * E <= o.w_len;

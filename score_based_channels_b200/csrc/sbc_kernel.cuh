@@ -416,9 +416,9 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
     const float* bf0 = wseg + op.frag_rel + lane * E;
     if (stamp) stamp[0] = clock64();
 
-    if (op.ks > 1) {
+    if (op.flags & SBC_F_UNIT) {
         // fewer (pixel tile, cout tile) units than warps: `ks` (a power of two) warps split the K steps of one
-        // unit and the partial accumulators are combined through shared memory
+        // unit and the partial accumulators are combined through shared memory (ks = 1: no split, no exchange)
         const int ks = op.ks, units = MT * NT;
         const int lks = 31 - __clz(ks);
         const int u = warp >> lks, kp = warp & (ks - 1);
@@ -436,8 +436,15 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
                 sbc_mma_pass<X3, SMEM, 1, 1>(A, po, reinterpret_cast<const int*>(wseg), bf0 + nt * 32 * E, bstride, s0, s1, acc);
                 c[0][0] = acc[0][0][0]; c[0][1] = acc[0][0][1]; c[0][2] = acc[0][0][2]; c[0][3] = acc[0][0][3];
             }
-            part[warp * 32 + lane] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+            if (ks == 1) {
+                int pd[2];
+                sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
+                sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0][0], c[0][1], c[0][2], c[0][3]);
+            } else {
+                part[warp * 32 + lane] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+            }
         }
+        if (ks == 1) return;
         __syncthreads();
         if (u < units && kp == 0) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};

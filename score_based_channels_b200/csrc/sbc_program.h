@@ -22,6 +22,8 @@ enum SbcOpFlags : int32_t {
     SBC_F_COMPACT = 4,    // conv epilogue writes couts 0,1 as interleaved (re, im) pairs [h*w] (the network output)
     SBC_F_ZH_DST = 8,     // the halo of the fresh tensor dst must be re-zeroed (decided offline by the planner:
     SBC_F_ZH_EDST = 16,   // program.py:_halo_analysis); same for edst
+    SBC_F_UNIT = 32,      // conv with fewer (pixel tile, cout tile) units than warps: unit u is owned by the `ks`
+                          // warps u*ks .. u*ks+ks-1 (ks = 1: one warp, no K split)
 };
 
 // Geometry of every tensor of one resolution: channel-interleaved by 8 (one pixel = 8 channels = 32 bytes

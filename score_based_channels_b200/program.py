@@ -31,6 +31,7 @@ test-suite to pin the schedule against the reference module before any CUDA code
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -53,6 +54,7 @@ PRECISIONS = ("tf32x3", "tf32")
 F_COMPACT = 4     # conv epilogue writes couts (0,1) as compact (re, im) pairs: the network output
 F_ZH_DST = 8      # the halo of the fresh tensor `dst` must be re-zeroed (set by ProgramBuilder._halo_analysis)
 F_ZH_EDST = 16    # same for `edst`
+F_UNIT = 32       # conv: unit (pixel tile, cout tile) u is owned by warps u*ks .. u*ks+ks-1 (ks = 1: no K split)
 
 OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout", "h", "w", "ksize", "dil",
              "w_off", "w_len", "b_rel", "sgeo", "dgeo", "ks", "scratch", "oh", "ow", "next_w", "tapmask",
@@ -417,11 +419,15 @@ class ProgramBuilder:
             w_off, w_len, rels = self._push(arrs)
             MT = (oh * ow + 15) // 16
             units = MT * ntc
-            ks = 1
-            while units * ks * 2 <= min(nwarps, 16) and ks * 2 <= S:     # at most 16 warps take part in a K split
-                ks *= 2
+            # fewer units than warps: `ks` warps split the K steps of a unit (measured: even in the 3xTF32 mode the
+            # serial K chain of a single warp costs more than the shared-memory exchange + barrier of the split:
+            # 36.3 est/s without, 40.5 with)
+            ks, unit = 1, units * 2 <= nwarps
+            if unit:
+                while units * ks * 2 <= min(nwarps, 16) and ks * 2 <= S:
+                    ks *= 2
             scratch = self.tmp_raw(units * ks * 32 * 4, "ksp") if ks > 1 else None
-            flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0)
+            flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0) | (F_UNIT if unit else 0)
             if compact:
                 assert nt_chunk == NT and cout == 2 and acc is None and edst is None
                 shift = lambda name: -1 if name is None else name
