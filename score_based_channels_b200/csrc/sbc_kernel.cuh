@@ -131,15 +131,17 @@ __device__ __forceinline__ void sbc_ldmatrix_x4(float (&a)[4], uint32_t saddr) {
 }
 
 // Per-lane A addressing of one warp for one conv op.
-//   SMEM: sbase = shared address of (src plane 0, channel half lane>>4); po[j][0] = byte offset of pixel row
-//         lane & 15 of slot j (ldmatrix row address)
+//   SMEM: sbase = shared address of src plane lane>>4 (of the chunk's two planes); po[j][0] = byte offset of
+//         pixel row lane & 15 of slot j (ldmatrix row address)
 //   else: gsrc = arena + op.src + t; po[j][0/1] = float offsets of pixel rows g / g + 8
 template <bool SMEM>
 struct SbcALane {
     uint32_t sbase;
     const float* gsrc;
-    __device__ __forceinline__ SbcALane(const SbcOp& op, float* arena, int lane) {
-        if (SMEM) { sbase = sbc_smem_u32(arena + op.src) + (uint32_t)(lane >> 4) * 16u; gsrc = nullptr; }
+    int pl4;   // floats per plane of the source geometry
+    __device__ __forceinline__ SbcALane(const SbcOp& op, const SbcGeo& GS, float* arena, int lane) {
+        pl4 = GS.pps * 4;
+        if (SMEM) { sbase = sbc_smem_u32(arena + op.src) + (uint32_t)(lane >> 4) * (uint32_t)(pl4 * 4); gsrc = nullptr; }
         else { sbase = 0; gsrc = arena + op.src + (lane & 3); }
     }
     __device__ __forceinline__ void rows(const SbcOp& op, const SbcGeo& GS, int mt, int quad, int lane, int (&po)[2]) const {
@@ -153,7 +155,7 @@ struct SbcALane {
     }
     __device__ __forceinline__ void frag(int off, const int (&po)[2], float (&a)[4]) const {
         if (SMEM) sbc_ldmatrix_x4(a, sbase + (uint32_t)(off * 4 + po[0]));
-        else sbc_mma_a_frag(gsrc, off, po[0], po[1], a);
+        else sbc_mma_a_frag(gsrc, off, po[0], po[1], pl4, a);
     }
 };
 
@@ -263,7 +265,7 @@ __device__ __forceinline__ void sbc_epilogue_batch(const SbcEpi& e, float* arena
     for (int n = 0; n < NN; n++) {
         const int co = (nt0 + n) * 8 + 2 * t;
         live[n] = co < e.cout;
-        cofs[n] = (co >> 3) * e.pps8 + (co & 7);
+        cofs[n] = (co >> 2) * e.pps4 + (co & 3);
         if (e.b_rel >= 0 && live[n]) {
             const float2 b = *reinterpret_cast<const float2*>(wseg + e.b_rel + co);   // co is even, b_rel % 4 == 0
 #pragma unroll
@@ -340,7 +342,7 @@ __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS
         // pixel offsets advance by a constant
         const int pstep = mstride * 16;
         if (op.low >= 0 && (pstep & (op.ow - 1)) == 0 && (mt0 + (NS - 1) * mstride) * 16 + 16 <= op.oh * op.ow) {
-            const int step = (pstep >> op.low) * GS.wp * (SMEM ? 32 : 8);
+            const int step = (pstep >> op.low) * GS.wp * (SMEM ? 16 : 4);
 #pragma unroll
             for (int j = 1; j < NS; j++) { po[j][0] = po[0][0] + j * step; po[j][1] = po[0][1] + j * step; }
         } else {
@@ -411,7 +413,7 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
     const bool pool = (op.flags & SBC_F_POOL) != 0;
 
     const int MT = op.MT, NT = op.NT, S = op.S;
-    const SbcALane<SMEM> A(op, arena, lane);
+    const SbcALane<SMEM> A(op, GS, arena, lane);
     const int bstride = NT * 32 * E;
     const float* bf0 = wseg + op.frag_rel + lane * E;
     if (stamp) stamp[0] = clock64();
@@ -568,12 +570,11 @@ __device__ __forceinline__ void sbc_norm_op(const SbcOp& op, const SbcGeo& G, fl
 // one float4 store per item, no index arithmetic.  hl = list of geometry g, nh = its length.
 __device__ __forceinline__ void sbc_zero_halo_list(float* t, const SbcGeo& G, const uint16_t* hl, int nh, int c,
                                                    int tid) {
-    const int np = (c + 7) >> 3;
+    const int np = (c + 3) >> 2;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int pl = 0; pl < np; pl++) {
-        float* base = t + (size_t)pl * G.pps * 8;
-        for (int k = tid; k < 2 * nh; k += SBC_NTHREADS)
-            *reinterpret_cast<float4*>(base + (int)hl[k >> 1] * 8 + (k & 1) * 4) = z;
+        float* base = t + (size_t)pl * G.pps * 4;
+        for (int k = tid; k < nh; k += SBC_NTHREADS) *reinterpret_cast<float4*>(base + (int)hl[k] * 4) = z;
     }
 }
 

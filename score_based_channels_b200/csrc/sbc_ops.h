@@ -3,8 +3,8 @@
 // intrinsics, so the same source is compiled by nvcc for the kernel (sbc_kernel.cuh) and by g++ for the
 // CPU thread-emulation harness (tests/emu/emu.cpp) that checks indexing before any GPU time is spent.
 //
-// Layout: see SbcGeo (sbc_program.h): channel-interleaved by 8 (one pixel of one plane = 8 channels = two
-// float4 "quads"), zero halo.  Every op body writes the interior only; because arena regions are recycled
+// Layout: see SbcGeo (sbc_program.h): channel-interleaved by 4 (one pixel of one plane = one float4 "quad" of
+// channels), zero halo.  Every op body writes the interior only; because arena regions are recycled
 // between tensors, the CALLER re-zeroes the halo of a fresh output (op.cout channels at op.dst / op.edst)
 // whenever the offline planner cannot prove that it is still zero (flags SBC_F_ZH_DST / SBC_F_ZH_EDST,
 // program.py:_halo_analysis): sbc_zero_halo here (CPU emulation, global-arena path), a list-driven version in
@@ -88,26 +88,26 @@ SBC_HD float sbc_rsqrt(float x) {
 }
 // float4 quad q (channels 4q .. 4q+3) of padded pixel p
 SBC_HD SbcF4* sbc_q4(float* base, const SbcGeo& G, int q, int p) {
-    return reinterpret_cast<SbcF4*>(base + ((size_t)((q >> 1) * G.pps + p) * 8 + (q & 1) * 4));
+    return reinterpret_cast<SbcF4*>(base + ((size_t)q * G.pps + p) * 4);
 }
 SBC_HD const SbcF4* sbc_q4(const float* base, const SbcGeo& G, int q, int p) {
-    return reinterpret_cast<const SbcF4*>(base + ((size_t)((q >> 1) * G.pps + p) * 8 + (q & 1) * 4));
+    return reinterpret_cast<const SbcF4*>(base + ((size_t)q * G.pps + p) * 4);
 }
 
 // zero the halo cells of a tensor with `c` channels: one item = one padded row of one plane.  Out of line
 // (scalar arguments, so that the caller's structs stay in registers).
 SBC_HD_OUTLINE void sbc_zero_halo_impl(float* t, int h, int w, int hy, int hx, int wp, int pps, int c, int tid,
                                        int nthr) {
-    const int np = (c + 7) >> 3;
+    const int np = (c + 3) >> 2;
     const int rows = h + 2 * hy;
     const SbcF4 z{0.f, 0.f, 0.f, 0.f};
     for (int i = tid; i < np * rows; i += nthr) {
         const int pl = i / rows, row = i - pl * rows;
-        SbcF4* r = reinterpret_cast<SbcF4*>(t + (size_t)(pl * pps + row * wp) * 8);
+        SbcF4* r = reinterpret_cast<SbcF4*>(t + (size_t)(pl * pps + row * wp) * 4);
         if (row < hy || row >= hy + h) {
-            for (int k = 0; k < 2 * wp; k++) r[k] = z;
+            for (int k = 0; k < wp; k++) r[k] = z;
         } else {
-            for (int k = 0; k < 2 * hx; k++) { r[k] = z; r[2 * (hx + w) + k] = z; }
+            for (int k = 0; k < hx; k++) { r[k] = z; r[hx + w + k] = z; }
         }
     }
 }
@@ -133,9 +133,9 @@ SBC_HD float sbc_bits_f(int32_t b) {
 }
 SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float* arena, int q, int s, int T) {
     SbcF4 a{0.f, 0.f, 0.f, 0.f};
-    const float* src = arena + op.src + (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    const float* src = arena + op.src + (size_t)q * G.pps * 4;
     sbc_for_pixels(G, s, T, [&](int p) {
-        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 8);
+        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 4);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     });
     return a;
@@ -143,9 +143,9 @@ SBC_HD SbcF4 sbc_norm_partial_sum(const SbcOp& op, const SbcGeo& G, const float*
 SBC_HD SbcF4 sbc_norm_partial_m2(const SbcOp& op, const SbcGeo& G, const float* arena, int q, int s, int T,
                                  SbcF4 mean) {
     SbcF4 a{0.f, 0.f, 0.f, 0.f};
-    const float* src = arena + op.src + (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    const float* src = arena + op.src + (size_t)q * G.pps * 4;
     sbc_for_pixels(G, s, T, [&](int p) {
-        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 8);
+        const SbcF4 v = *reinterpret_cast<const SbcF4*>(src + p * 4);
         const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
         a.x = fmaf(dx, dx, a.x); a.y = fmaf(dy, dy, a.y); a.z = fmaf(dz, dz, a.z); a.w = fmaf(dw, dw, a.w);
     });
@@ -178,17 +178,17 @@ SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const
     const float a2 = ga.z * sbc_rsqrt(m2_4.z * inv + 1e-5f), a3 = ga.w * sbc_rsqrt(m2_4.w * inv + 1e-5f);
     const float b0 = fmaf(ga.x, (mean4.x - m) * rv * al.x, be.x), b1 = fmaf(ga.y, (mean4.y - m) * rv * al.y, be.y);
     const float b2 = fmaf(ga.z, (mean4.z - m) * rv * al.z, be.z), b3 = fmaf(ga.w, (mean4.w - m) * rv * al.w, be.w);
-    const size_t qo = (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+    const size_t qo = (size_t)q * G.pps * 4;
     const float* src = arena + op.src + qo;
     float* dst = arena + op.dst + qo;
     sbc_for_pixels(G, s, T, [&](int p) {
-        const SbcF4 x = *reinterpret_cast<const SbcF4*>(src + p * 8);
+        const SbcF4 x = *reinterpret_cast<const SbcF4*>(src + p * 4);
         SbcF4 o;
         o.x = sbc_elu(fmaf(x.x - mean4.x, a0, b0));
         o.y = sbc_elu(fmaf(x.y - mean4.y, a1, b1));
         o.z = sbc_elu(fmaf(x.z - mean4.z, a2, b2));
         o.w = sbc_elu(fmaf(x.w - mean4.w, a3, b3));
-        *reinterpret_cast<SbcF4*>(dst + p * 8) = o;
+        *reinterpret_cast<SbcF4*>(dst + p * 4) = o;
     });
 }
 
@@ -198,11 +198,11 @@ SBC_HD void sbc_norm_apply(const SbcOp& op, const SbcGeo& G, float* arena, const
 SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {
     const int nq = op.cin >> 2, T = op.MT, lT = op.NT, gpp = nthr >> lT, s = tid & (T - 1);
     for (int q = tid >> lT; q < nq; q += gpp) {
-        const size_t qo = (size_t)(q >> 1) * G.pps * 8 + (q & 1) * 4;
+        const size_t qo = (size_t)q * G.pps * 4;
         const float* src = arena + op.src + qo;
         float* dst = arena + op.dst + qo;
         sbc_for_pixels(G, s, T, [&](int p) {
-            *reinterpret_cast<SbcF4*>(dst + p * 8) = sbc_elu4(*reinterpret_cast<const SbcF4*>(src + p * 8));
+            *reinterpret_cast<SbcF4*>(dst + p * 4) = sbc_elu4(*reinterpret_cast<const SbcF4*>(src + p * 4));
         });
     }
 }

@@ -26,9 +26,10 @@ enum SbcOpFlags : int32_t {
                           // warps u*ks .. u*ks+ks-1 (ks = 1: one warp, no K split)
 };
 
-// Geometry of every tensor of one resolution: channel-interleaved by 8 (one pixel = 8 channels = 32 bytes
-// = the K chunk of one m16n8k8 MMA), zero halo of (hy, hx) pixels.
-//   addr(c, y, x) = base + ((c >> 3) * pps + org + y * wp + x) * 8 + (c & 7)        [floats]
+// Geometry of every tensor of one resolution: channel-interleaved by 4 (one pixel of one plane = 4 channels
+// = 16 bytes = one ldmatrix row = one row of a no-swizzle K-major UMMA core matrix; two planes = the K chunk
+// of one m16n8k8 MMA), zero halo of (hy, hx) pixels.
+//   addr(c, y, x) = base + ((c >> 2) * pps + org + y * wp + x) * 4 + (c & 3)        [floats]
 struct SbcGeo {
     int32_t h, w;        // interior size
     int32_t hy, hx;      // halo (covers every live conv tap at this resolution)

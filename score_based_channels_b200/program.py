@@ -17,13 +17,14 @@ reference arithmetic):
 * ``ConvMeanPool`` = conv then 2x2 mean-pool: four accumulations (one per pooling position) summed in the
   epilogue, weights pre-scaled by 1/4 -- ``F_POOL``.
 
-Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by 8 with a zero halo,
-``addr(c, y, x) = base + ((c // 8) * pps + org + y * wp + x) * 8 + c % 8`` with ``wp = w + 2*hx``,
+Activation layout (``Geo``): a [C, h, w] tensor is stored channel-interleaved by 4 with a zero halo,
+``addr(c, y, x) = base + ((c // 4) * pps + org + y * wp + x) * 4 + c % 4`` with ``wp = w + 2*hx``,
 ``pps = (h + 2*hy) * wp``, ``org = hy * wp + hx``.  The halo (hy, hx) covers every live convolution tap
 at that resolution, so the implicit-im2col gather of a K step (tap, chunk of 8 input channels) is the
 *same* address pattern shifted by a constant -- tabulated per op at the head of its parameter segment --
-and needs no bounds checks; one pixel of one plane is exactly the K = 8 chunk of an m16n8k8 MMA = two
-16-byte ldmatrix rows, so one ldmatrix.x4 per lane loads a whole A fragment in register order.
+and needs no bounds checks; one pixel of one plane (4 channels, 16 bytes) is one ldmatrix row, 8 consecutive
+pixels are 128 contiguous bytes (conflict free), one ldmatrix.x4 per lane loads a whole m16n8k8 A fragment (two
+planes) in register order, and the same bytes are a no-swizzle K-major UMMA core matrix (tcgen05-ready).
 The sampler state ``x`` and the raw network output are *compact* (re, im) pair arrays [h*w].
 
 Nothing here touches a GPU; ``simulate`` is a torch (CPU) interpreter of the program used by the CPU
@@ -91,7 +92,7 @@ class Geo:
         return self.hy * self.wp + self.hx
 
     def floats(self, c: int) -> int:
-        return ((c + 7) // 8) * self.pps * 8
+        return ((c + 3) // 4) * self.pps * 4
 
     def words(self) -> List[int]:
         return [self.h, self.w, self.hy, self.hx, self.wp, self.pps, self.org, ilog2(self.w)]
@@ -174,7 +175,7 @@ class Program:
     def _index(self, off: int, c: int, h: int, w: int) -> np.ndarray:
         g = self.geo_of(h, w)
         cc, yy, xx = np.meshgrid(np.arange(c), np.arange(h), np.arange(w), indexing="ij")
-        return off + ((cc // 8) * g.pps + g.org + yy * g.wp + xx) * 8 + cc % 8
+        return off + ((cc // 4) * g.pps + g.org + yy * g.wp + xx) * 4 + cc % 4
 
     def read(self, arena, off: int, c: int, h: int, w: int):
         """[c,h,w] copy of the tensor stored at float offset ``off``."""
@@ -302,8 +303,8 @@ class ProgramBuilder:
             hy = max([d for d in dils if d < h] + [0])
             hx = max([d for d in dils if d < w] + [0])
             if w == 2:
-                # the 4 pixel rows of a quarter-warp A gather are (Y,0) (Y,1) (Y+1,0) (Y+1,1): with a row pitch
-                # of 6 pixels (192 B) they fall into disjoint shared-memory banks
+                # the 8 rows of one ldmatrix matrix are the pixels (Y,0) (Y,1) ... (Y+3,1), 16 B each: with a row
+                # pitch of 6 pixels (96 B) they fall into disjoint shared-memory banks
                 hx = max(hx, 2)
             self.geos.append(Geo(h, w, hy, hx))
 
@@ -359,7 +360,7 @@ class ProgramBuilder:
 
         v = conv(src) + bias;  dst <- v;  acc <- (v += acc);  edst <- ELU(v).
         Parameter segment: [S int32 A offsets | B fragments | bias].  ``aoff[s]`` is the float offset
-        (cin_chunk * pps + dy * wp + dx) * 8 that K step s adds to every gathered address.  The weights are in
+        (2 * cin_chunk * pps + dy * wp + dx) * 4 that K step s adds to every gathered address.  The weights are in
         mma.sync m16n8k8 B-fragment order (csrc/sbc_mma.h):
         frag[step][ntile][lane] = (w0, w1) where lane = 4*g + t holds W[cout g][cin t (+4)]: TF32-rounded (rna)
         in the "tf32" mode, plain fp32 in the 3xTF32 mode (the kernel splits w = hi + lo in registers)."""
@@ -402,7 +403,7 @@ class ProgramBuilder:
         for i, tap in enumerate(live):
             dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
             for kc in range(KC):
-                aoff[i * KC + kc] = (kc * sg.pps + dy * sg.wp + dx) * 8
+                aoff[i * KC + kc] = (2 * kc * sg.pps + dy * sg.wp + dx) * 4
         for nt0 in range(0, NT, nt_chunk):
             ntc = min(nt_chunk, NT - nt0)
             co0, co1 = nt0 * 8, min(cout, (nt0 + ntc) * 8)
@@ -432,7 +433,7 @@ class ProgramBuilder:
                 assert nt_chunk == NT and cout == 2 and acc is None and edst is None
                 shift = lambda name: -1 if name is None else name
             else:
-                shift = lambda name: -1 if name is None else (name, (co0 // 8) * dgeo.pps * 8)
+                shift = lambda name: -1 if name is None else (name, (co0 // 4) * dgeo.pps * 4)
             self.ops.append(Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin, co1 - co0, h, w, k,
                                dil, w_off, w_len, rels[2] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
                                ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask, MT=MT, NT=ntc,
@@ -602,7 +603,7 @@ class ProgramBuilder:
     # -- whole network ----------------------------------------------------
     def build(self) -> Program:
         ngf, H, W = self.ngf, self.H, self.W
-        assert ngf % 8 == 0, "ngf must be a multiple of 8 (channel planes hold 8 channels)"
+        assert ngf % 8 == 0, "ngf must be a multiple of 8 (one MMA K chunk = 8 input channels = two planes)"
         xin = self.new_raw("x_in", self.channels * H * W)       # compact (re, im) pairs
         a = self.tmp(8, H, W)                                   # begin_conv reads one chunk of 8 input channels
         self.affine(xin, a)
@@ -679,10 +680,10 @@ class ProgramBuilder:
         def fresh(off: int, gi: int, c: int) -> bool:
             g = self.geos[gi]
             need = False
-            for pl in range((c + 7) // 8):
-                a = off + pl * g.pps * 8
+            for pl in range((c + 3) // 4):
+                a = off + pl * g.pps * 4
                 key = (gi << 40) | a
-                seg = tags[a:a + g.pps * 8]
+                seg = tags[a:a + g.pps * 4]
                 if not bool((seg == key).all()):
                     need = True
                 seg[:] = key

@@ -32,7 +32,7 @@ static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float*
                         const int po0 = sbc_mma_row_off(op, GS, mt, quad, g);
                         const int po1 = sbc_mma_row_off(op, GS, mt, quad, g + 8);
                         float a[4];
-                        sbc_mma_a_frag(arena + op.src + t, steptab[s], po0, po1, a);
+                        sbc_mma_a_frag(arena + op.src + t, steptab[s], po0, po1, GS.pps * 4, a);
                         const int rr[4] = {g, g + 8, g, g + 8}, cc[4] = {t, t, t + 4, t + 4};
                         for (int i = 0; i < 4; i++) {
                             if (x3) {
