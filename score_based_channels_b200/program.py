@@ -129,6 +129,7 @@ class Op:
     frag_rel: int = 0   # conv: offset of the B fragments inside the segment
     low: int = -1       # log2(ow) or -1
     name: str = ""
+    branches: object = None   # conv, host side only: per summed conv {prefix, src, cin, k, dil, live, KC, step0}
 
     def words(self) -> List[int]:
         vals = [0 if f in DEVICE_FILLED else getattr(self, f) for f in OP_FIELDS]
@@ -353,7 +354,8 @@ class ProgramBuilder:
 
     # -- ops --------------------------------------------------------------
     def conv(self, prefix: str, src: str, dst: Optional[str] = None, acc: Optional[str] = None,
-             edst: Optional[str] = None, dil: int = 1, pool: bool = False, compact: bool = False) -> None:
+             edst: Optional[str] = None, dil: int = 1, pool: bool = False, compact: bool = False,
+             siblings=()) -> None:
         """One Conv2d (reference ``layers.py:28-60``) + fused epilogue, as an implicit GEMM on tensor cores:
 
             D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]   per K step (live tap, cin chunk)
@@ -363,59 +365,83 @@ class ProgramBuilder:
         (2 * cin_chunk * pps + dy * wp + dx) * 4 that K step s adds to every gathered address.  The weights are in
         mma.sync m16n8k8 B-fragment order (csrc/sbc_mma.h):
         frag[step][ntile][lane] = (w0, w1) where lane = 4*g + t holds W[cout g][cin t (+4)]: TF32-rounded (rna)
-        in the "tf32" mode, plain fp32 in the 3xTF32 mode (the kernel splits w = hi + lo in registers)."""
-        wt = self.sd[prefix + ".weight"]
-        bias = self.sd.get(prefix + ".bias")
-        cout, cin, k, k2 = wt.shape
-        assert k == k2 and k in (1, 3)
-        assert cout % 2 == 0, "the epilogue stores adjacent cout pairs"
-        c, h, w = self.shape[src]
-        assert c == cin or (c == 8 and cin < 8), (prefix, c, cin)      # begin_conv reads a zero-padded chunk
+        in the "tf32" mode, plain fp32 in the 3xTF32 mode (the kernel splits w = hi + lo in registers).
+
+        ``siblings``: further (prefix, src, dil) convs whose outputs are SUMMED with this one (the shortcut of a
+        'down' ResidualBlock, ``layers.py:416-420,455-456``; the second branch of a same-size MSFBlock,
+        ``layers.py:181-183``).  Because a K step is just an address offset, their K steps are appended to the table
+        with the distance between the two source tensors folded into the offsets (patched in once the arena plan
+        is known), their fragments to the fragment array, and their biases are added: one op, one pass."""
+        branches = [(prefix, src, dil)] + list(siblings)
+        x3 = self.precision == "tf32x3"
+        E = 2                                              # floats per lane per fragment
+        c0, h, w = self.shape[src]
+        sg = self.geos[self.gi(h, w)]
         oh, ow = (h // 2, w // 2) if pool else (h, w)
+        cout = self.sd[prefix + ".weight"].shape[0]
+        assert cout % 2 == 0, "the epilogue stores adjacent cout pairs"
         for t in (acc, edst) + (() if compact else (dst,)):
             if t is not None:
                 assert self.shape[t] == (cout, oh, ow), (prefix, t, self.shape[t], (cout, oh, ow))
-        self.flops += 2 * h * w * cin * k * k * cout       # dense count, reference convention
-        r = k // 2
-        x3 = self.precision == "tf32x3"
-        E = 2                                              # floats per lane per fragment
-        sg = self.geos[self.gi(h, w)]
-        live = []
-        for tap in range(k * k):
-            dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
-            if abs(dy) < h and abs(dx) < w:                # otherwise the tap only ever reads zero padding
-                assert abs(dy) <= sg.hy and abs(dx) <= sg.hx, "halo too small"
-                live.append(tap)
-        tapmask = sum(1 << t for t in live)
-        KC, NT = (cin + 7) // 8, (cout + 7) // 8
-        S = len(live) * KC
+        NT = (cout + 7) // 8
+        bias = None
+        meta, aoffs, wpads = [], [], []                    # per branch
+        for (bp, bsrc, bdil) in branches:
+            wt = self.sd[bp + ".weight"]
+            bco, cin, k, k2 = wt.shape
+            assert k == k2 and k in (1, 3) and bco == cout
+            c, bh, bw = self.shape[bsrc]
+            assert (bh, bw) == (h, w), "sibling convs must read tensors of the same geometry"
+            assert c == cin or (c == 8 and cin < 8), (bp, c, cin)   # begin_conv reads a zero-padded chunk
+            self.flops += 2 * h * w * cin * k * k * cout   # dense count, reference convention
+            r = k // 2
+            live = []
+            for tap in range(k * k):
+                dy, dx = (tap // k - r) * bdil, (tap % k - r) * bdil
+                if abs(dy) < h and abs(dx) < w:            # otherwise the tap only ever reads zero padding
+                    assert abs(dy) <= sg.hy and abs(dx) <= sg.hx, "halo too small"
+                    live.append(tap)
+            KC = (cin + 7) // 8
+            ao = np.zeros(len(live) * KC, np.int32)
+            for i, tap in enumerate(live):
+                dy, dx = (tap // k - r) * bdil, (tap % k - r) * bdil
+                for kc in range(KC):
+                    ao[i * KC + kc] = (2 * kc * sg.pps + dy * sg.wp + dx) * 4
+            wp_ = np.zeros((NT * 8, KC * 8, k * k), np.float32)
+            wp_[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
+            b = self.sd.get(bp + ".bias")
+            if b is not None:
+                bias = b.astype(np.float32) if bias is None else (bias + b).astype(np.float32)
+            meta.append(dict(prefix=bp, src=bsrc, cin=cin, k=k, dil=bdil, live=live, KC=KC, step0=sum(len(a_) for a_ in aoffs)))
+            aoffs.append(ao)
+            wpads.append(wp_)
+        S = sum(len(a_) for a_ in aoffs)
         S4 = (S + 3) // 4 * 4
+        aoff = np.zeros(S4, np.int32)
+        aoff[:S] = np.concatenate(aoffs)
         per_nt = S * 32 * E
         nt_chunk = NT
         while nt_chunk > 1 and S4 + per_nt * nt_chunk + 8 * nt_chunk > self.SLOT_FLOATS:
             nt_chunk //= 2
-        wpad = np.zeros((NT * 8, KC * 8, k * k), np.float32)
-        wpad[:cout, :cin] = wt.reshape(cout, cin, k * k) * (np.float32(0.25) if pool else np.float32(1.0))
         g, t = np.arange(32) >> 2, np.arange(32) & 3
         nwarps = self.nthreads // 32
         dgeo = self.geos[self.gi(oh, ow)]
-        aoff = np.zeros(S4, np.int32)
-        for i, tap in enumerate(live):
-            dy, dx = (tap // k - r) * dil, (tap % k - r) * dil
-            for kc in range(KC):
-                aoff[i * KC + kc] = (2 * kc * sg.pps + dy * sg.wp + dx) * 4
+        k0, cin0 = meta[0]["k"], meta[0]["cin"]
+        tapmask = sum(1 << tp for tp in meta[0]["live"])
         for nt0 in range(0, NT, nt_chunk):
             ntc = min(nt_chunk, NT - nt0)
             co0, co1 = nt0 * 8, min(cout, (nt0 + ntc) * 8)
-            frag = np.zeros((len(live), KC, ntc, 32, E), np.float32)
-            for i, tap in enumerate(live):
-                for kc in range(KC):
-                    for nt in range(ntc):
-                        w0 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t, tap]
-                        w1 = wpad[(nt0 + nt) * 8 + g, kc * 8 + t + 4, tap]
-                        if not x3:
-                            w0, w1 = tf32_rna(w0), tf32_rna(w1)
-                        frag[i, kc, nt, :, 0], frag[i, kc, nt, :, 1] = w0, w1
+            frag = np.zeros((S, ntc, 32, E), np.float32)
+            for m, wp_ in zip(meta, wpads):
+                for i, tap in enumerate(m["live"]):
+                    for kc in range(m["KC"]):
+                        for nt in range(ntc):
+                            w0 = wp_[(nt0 + nt) * 8 + g, kc * 8 + t, tap]
+                            w1 = wp_[(nt0 + nt) * 8 + g, kc * 8 + t + 4, tap]
+                            if not x3:
+                                w0, w1 = tf32_rna(w0), tf32_rna(w1)
+                            st = m["step0"] + i * m["KC"] + kc
+                            frag[st, nt, :, 0], frag[st, nt, :, 1] = w0, w1
             arrs = [aoff.view(np.float32), frag] + ([bias[co0:co1]] if bias is not None else [])
             w_off, w_len, rels = self._push(arrs)
             MT = (oh * ow + 15) // 16
@@ -434,11 +460,13 @@ class ProgramBuilder:
                 shift = lambda name: -1 if name is None else name
             else:
                 shift = lambda name: -1 if name is None else (name, (co0 // 4) * dgeo.pps * 4)
-            self.ops.append(Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin, co1 - co0, h, w, k,
-                               dil, w_off, w_len, rels[2] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
-                               ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask, MT=MT, NT=ntc,
-                               S=S, frag_rel=rels[1], low=ilog2(ow),
-                               name=prefix + ("" if nt_chunk == NT else "[co%d:%d]" % (co0, co1))))
+            op = Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin0, co1 - co0, h, w, k0,
+                    dil, w_off, w_len, rels[2] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
+                    ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask, MT=MT, NT=ntc,
+                    S=S, frag_rel=rels[1], low=ilog2(ow),
+                    name="+".join(m["prefix"] for m in meta) + ("" if nt_chunk == NT else "[co%d:%d]" % (co0, co1)))
+            op.branches = [dict(m) for m in meta]          # host-side only (simulator, offset fix-ups)
+            self.ops.append(op)
             if scratch is not None:
                 self.free(scratch)
 
@@ -497,8 +525,9 @@ class ProgramBuilder:
                            sgeo=self.gi(h, w), dgeo=self.gi(oh, ow), oh=oh, ow=ow, name="upacc"))
 
     # -- blocks -----------------------------------------------------------
-    def residual(self, p: str, x: str, cout: int, down: bool, dil: Optional[int]) -> str:
-        """ResidualBlock.forward (``layers.py:443-456``). Consumes ``x``; returns the output tensor."""
+    def residual(self, p: str, x: str, cout: int, down: bool, dil: Optional[int], elu_out: Optional[str] = None) -> str:
+        """ResidualBlock.forward (``layers.py:443-456``). Consumes ``x``; returns the output tensor.  ``elu_out``
+        (same-shape blocks only): tensor that additionally receives ELU(output) from the last conv's epilogue."""
         cin, h, w = self.shape[x]
         d = dil or 1
         t = self.tmp(cin, h, w)
@@ -511,19 +540,18 @@ class ProgramBuilder:
         self.norm_elu(p + ".normalize2", t2, t3)
         self.free(t2)
         if cout == cin and not down:
-            self.conv(p + ".conv2", t3, acc=x, dil=d)           # shortcut = x
+            self.conv(p + ".conv2", t3, acc=x, edst=elu_out, dil=d)   # shortcut = x
             self.free(t3)
             return x
+        assert elu_out is None
         if down and dil is None:
             out = self.tmp(cout, h // 2, w // 2, "o")
-            self.conv(p + ".conv2.conv", t3, dst=out, pool=True)  # ConvMeanPool 3x3
-            self.free(t3)
-            self.conv(p + ".shortcut.conv", x, acc=out, pool=True)  # ConvMeanPool 1x1
+            # ConvMeanPool 3x3 + ConvMeanPool 1x1 shortcut, one op
+            self.conv(p + ".conv2.conv", t3, dst=out, pool=True, siblings=[(p + ".shortcut.conv", x, 1)])
         else:
             out = self.tmp(cout, h, w, "o")
-            self.conv(p + ".conv2", t3, dst=out, dil=d)
-            self.free(t3)
-            self.conv(p + ".shortcut", x, acc=out, dil=d)
+            self.conv(p + ".conv2", t3, dst=out, dil=d, siblings=[(p + ".shortcut", x, d)])
+        self.free(t3)
         self.free(x)
         return out
 
@@ -572,21 +600,23 @@ class ProgramBuilder:
         """RefineBlock.forward (``layers.py:234-249``).  ``es[i]`` optionally holds ELU(xs[i]).
 
         Returns (h, ELU(h)) (ELU(h) is None for the last block)."""
-        hs = []
+        hs, e_single = [], None
         for i, x in enumerate(xs):
-            h_, _ = self.rcu("%s.adapt_convs.%d" % (p, i), x, 2, e_in=es[i])
+            # a single-input block applies ELU to the adapted tensor right away (CRP): take it from the epilogue
+            h_, e_single = self.rcu("%s.adapt_convs.%d" % (p, i), x, 2, e_in=es[i], want_elu_out=(len(xs) == 1))
             hs.append(h_)
         c0, oh, ow = self.shape[hs[0]]
         if len(hs) > 1:
             s = self.tmp(features, oh, ow, "s")
             e = self.tmp(features, oh, ow, "e")
             same = self.shape[hs[1]][1:] == (oh, ow)
-            self.conv(p + ".msf.convs.0", hs[0], dst=s)
-            self.free(hs[0])
-            if same:   # bilinear to the same size with align_corners=True is the identity
-                self.conv(p + ".msf.convs.1", hs[1], acc=s, edst=e)
+            if same:   # bilinear to the same size with align_corners=True is the identity: one summed conv
+                self.conv(p + ".msf.convs.0", hs[0], dst=s, edst=e, siblings=[(p + ".msf.convs.1", hs[1], 1)])
+                self.free(hs[0])
                 self.free(hs[1])
             else:
+                self.conv(p + ".msf.convs.0", hs[0], dst=s)
+                self.free(hs[0])
                 _, lh, lw = self.shape[hs[1]]
                 lo = self.tmp(features, lh, lw, "lo")
                 self.conv(p + ".msf.convs.1", hs[1], dst=lo)
@@ -594,9 +624,7 @@ class ProgramBuilder:
                 self.upacc(lo, s, edst=e)
                 self.free(lo)
         else:
-            s = hs[0]
-            e = self.tmp(c0, oh, ow, "e")
-            self.elu(s, e)
+            s, e = hs[0], e_single
         h_, eh = self.crp(p + ".crp", s, e)
         return self.rcu(p + ".output_convs", h_, 3 if end else 1, e_in=eh, want_elu_out=not end)
 
@@ -611,15 +639,18 @@ class ProgramBuilder:
         self.conv("begin_conv", a, dst=o)
         self.free(a)
         l1 = self.residual("res1.1", self.residual("res1.0", o, ngf, False, None), ngf, False, None)
-        l2 = self._stage("res2", l1, 2 * ngf, None)
-        l3 = self._stage("res3", l2, 2 * ngf, None)
-        l31 = self._stage("res31", l3, 2 * ngf, None)
-        l4 = self._stage("res4", l31, 4 * ngf, 2)
-        l5 = self._stage("res5", l4, 4 * ngf, 4)
-        r1, e1 = self.refine("refine1", [l5], [None], 4 * ngf)
-        r2, e2 = self.refine("refine2", [l4, r1], [None, e1], 2 * ngf)
-        r31, e31 = self.refine("refine31", [l31, r2], [None, e2], 2 * ngf)
-        r3, e3 = self.refine("refine3", [l3, r31], [None, e31], 2 * ngf)
+        # l4 and l5 also emit ELU(skip) from the epilogue of their last conv (the first thing their RefineBlock does
+        # with them); for the others a stand-alone ELU op later is cheaper than arena held across the phase where
+        # the two largest parameter staging buffers are live (it would push the plan past the 227 KB of one SM)
+        l2, _ = self._stage("res2", l1, 2 * ngf, None)
+        l3, el3 = self._stage("res3", l2, 2 * ngf, None)
+        l31, el31 = self._stage("res31", l3, 2 * ngf, None)
+        l4, el4 = self._stage("res4", l31, 4 * ngf, 2, want_elu=True)
+        l5, el5 = self._stage("res5", l4, 4 * ngf, 4, want_elu=True)
+        r1, e1 = self.refine("refine1", [l5], [el5], 4 * ngf)
+        r2, e2 = self.refine("refine2", [l4, r1], [el4, e1], 2 * ngf)
+        r31, e31 = self.refine("refine31", [l31, r2], [el31, e2], 2 * ngf)
+        r3, e3 = self.refine("refine3", [l3, r31], [el3, e31], 2 * ngf)
         r4, e4 = self.refine("refine4", [l2, r3], [None, e3], ngf)
         r5, _ = self.refine("refine5", [l1, r4], [None, e4], ngf, end=True)
         t = self.tmp(ngf, H, W)
@@ -650,6 +681,13 @@ class ProgramBuilder:
         # ---- solve the arena plan and resolve tensor names to float offsets ----
         self.ar.solve(end)
         for op in self.ops:
+            if op.branches:   # sibling convs: fold the distance between the source tensors into their K-step offsets
+                base = self.ar.offs[op.branches[0]["src"]]
+                tab = blob[op.w_off:op.w_off + op.S].view(np.int32)
+                for m in op.branches:
+                    m["src_off"] = self.ar.offs[m["src"]]
+                    n = len(m["live"]) * m["KC"]
+                    tab[m["step0"]:m["step0"] + n] += m["src_off"] - base
             for f in ("src", "dst", "acc", "edst", "scratch", "wbuf"):
                 v = getattr(op, f)
                 if isinstance(v, tuple):
@@ -718,8 +756,9 @@ class ProgramBuilder:
             else:
                 raise ValueError(op.kind)
 
-    def _stage(self, p: str, skip: str, cout: int, dil: Optional[int]) -> str:
-        """Two ResidualBlocks, the first 'down'; ``skip`` must survive (it feeds a RefineBlock later)."""
+    def _stage(self, p: str, skip: str, cout: int, dil: Optional[int], want_elu: bool = False):
+        """Two ResidualBlocks, the first 'down'; ``skip`` must survive (it feeds a RefineBlock later).
+        Returns (output, ELU(output) or None)."""
         cin, h, w = self.shape[skip]
         d = dil or 1
         t = self.tmp(cin, h, w)
@@ -732,15 +771,16 @@ class ProgramBuilder:
         self.free(t2)
         if dil is None:
             out = self.tmp(cout, h // 2, w // 2, "o")
-            self.conv(p + ".0.conv2.conv", t3, dst=out, pool=True)
-            self.free(t3)
-            self.conv(p + ".0.shortcut.conv", skip, acc=out, pool=True)
+            self.conv(p + ".0.conv2.conv", t3, dst=out, pool=True, siblings=[(p + ".0.shortcut.conv", skip, 1)])
         else:
             out = self.tmp(cout, h, w, "o")
-            self.conv(p + ".0.conv2", t3, dst=out, dil=d)
-            self.free(t3)
-            self.conv(p + ".0.shortcut", skip, acc=out, dil=d)
-        return self.residual(p + ".1", out, cout, False, dil)
+            self.conv(p + ".0.conv2", t3, dst=out, dil=d, siblings=[(p + ".0.shortcut", skip, d)])
+        self.free(t3)
+        e = None
+        if want_elu:
+            c, h2, w2 = self.shape[out]
+            e = self.tmp(c, h2, w2, "e")
+        return self.residual(p + ".1", out, cout, False, dil, elu_out=e), e
 
 
 def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channels: int = 2,
@@ -751,17 +791,16 @@ def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channe
 # ---------------------------------------------------------------------------
 # torch (CPU) interpreter of a Program -- host-side check of the schedule only
 # ---------------------------------------------------------------------------
-def conv_weights(prog: Program, op: Op):
-    """Decode (weight [cout,cin,k,k], bias or None) of a conv op back from the packed blob."""
+def conv_weights(prog: Program, op: Op, branch: int = 0):
+    """Decode (weight [cout,cin,k,k], bias or None) of (one summed branch of) a conv op back from the packed blob;
+    the bias (already summed over the branches) is returned with branch 0 only."""
     import torch
     blob = torch.from_numpy(prog.blob)
-    k = op.ksize
-    live = [t for t in range(k * k) if (op.tapmask >> t) & 1]
-    KC, NT = (op.cin + 7) // 8, op.NT
-    assert op.S == len(live) * KC
+    m = op.branches[branch]
+    k, live, KC, NT = m["k"], m["live"], m["KC"], op.NT
     E = 2
+    f0 = op.w_off + op.frag_rel + m["step0"] * NT * 32 * E
     n = len(live) * KC * NT * 32 * E
-    f0 = op.w_off + op.frag_rel
     frag = blob[f0:f0 + n].view(len(live), KC, NT, 32, E)
     full = torch.zeros(NT * 8, KC * 8, k * k)
     g, t = torch.arange(32) >> 2, torch.arange(32) & 3
@@ -770,8 +809,8 @@ def conv_weights(prog: Program, op: Op):
             for nt in range(NT):
                 full[nt * 8 + g, kc * 8 + t, tap] = frag[i, kc, nt, :, 0]
                 full[nt * 8 + g, kc * 8 + t + 4, tap] = frag[i, kc, nt, :, 1]
-    wt = full[:op.cout, :op.cin].reshape(op.cout, op.cin, k, k).contiguous()
-    bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if op.b_rel >= 0 else None
+    wt = full[:op.cout, :m["cin"]].reshape(op.cout, m["cin"], k, k).contiguous()
+    bias = blob[op.w_off + op.b_rel:op.w_off + op.b_rel + op.cout] if (op.b_rel >= 0 and branch == 0) else None
     return wt, bias
 
 
@@ -815,17 +854,17 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
             if op.edst >= 0:
                 prog.write(arena, op.edst, F.elu(a))
         elif op.kind == OP_CONV_MMA:
-            k = op.ksize
-            wt, bias = conv_weights(prog, op)
-            s = rd(op.src, op.cin, op.h, op.w)[None]       # begin_conv: the real channels of the padded chunk
-            if op.flags & F_POOL:
-                # packed weights already carry the 1/4; conv at full res then 2x2 SUM
-                v = F.conv2d(s, wt, None, 1, op.dil * (k // 2), op.dil)
-                v = F.avg_pool2d(v, 2) * 4.0
+            v = None
+            for bi, m in enumerate(op.branches):
+                k = m["k"]
+                wt, bias = conv_weights(prog, op, bi)
+                s = rd(m["src_off"], m["cin"], op.h, op.w)[None]     # begin_conv: the real channels of the padded chunk
+                vb = F.conv2d(s, wt, None, 1, m["dil"] * (k // 2), m["dil"])
+                if op.flags & F_POOL:                                # packed weights already carry the 1/4: 2x2 SUM
+                    vb = F.avg_pool2d(vb, 2) * 4.0
                 if bias is not None:
-                    v = v + bias[None, :, None, None]
-            else:
-                v = F.conv2d(s, wt, bias, 1, op.dil * (k // 2), op.dil)
+                    vb = vb + bias[None, :, None, None]
+                v = vb if v is None else v + vb
             v = v[0]
             if op.flags & F_COMPACT:
                 arena[op.dst:op.dst + op.cout * op.oh * op.ow] = v.permute(1, 2, 0).reshape(-1)
