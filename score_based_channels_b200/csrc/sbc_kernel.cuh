@@ -535,6 +535,20 @@ __device__ __forceinline__ void sbc_norm_op(const SbcOp& op, const SbcGeo& G, fl
     const int s = tid & (T - 1), w0 = (tid >> lT) * wpg;
     const SbcF4 z{0.f, 0.f, 0.f, 0.f};
     SbcF4 mean = z, m2 = z;
+    if (wpg == 1 && npass == 1) {
+        // one warp per quad (small maps): both statistics come straight out of the shuffle reductions; the only
+        // exchange is the per-channel means every thread needs for the cross-channel term
+        const int q = tid >> 5;
+        const bool active = q < nq;
+        SbcF4 sum = active ? sbc_norm_partial_sum(op, G, arena, q, lane, 32) : z;
+        sum = sbc_warp_sum4(sum);
+        mean.x = sum.x * inv; mean.y = sum.y * inv; mean.z = sum.z * inv; mean.w = sum.w * inv;
+        m2 = sbc_warp_sum4(active ? sbc_norm_partial_m2(op, G, arena, q, lane, 32, mean) : z);
+        if (active && lane == 0) mu4[q] = mean;
+        __syncthreads();
+        if (active) sbc_norm_apply(op, G, arena, wseg, reinterpret_cast<const float*>(mu4), q, lane, 32, mean, m2);
+        return;
+    }
     for (int pass = 0; pass < npass; pass++) {
         const int q = pass * gpp + (tid >> lT);
         const bool active = q < nq;

@@ -480,19 +480,20 @@ class ProgramBuilder:
         # scratch: per-warp partial sums of the two statistics passes (4 channels each) + per-channel (mean, M2)
         nwarps = self.nthreads // 32
         scratch = self.tmp_raw(2 * nwarps * 4 + 2 * c, "nsc")
-        T, lT, npass = self._quad_threads(c)
+        T, lT, npass = self._quad_threads(c, h * w)
         fb = lambda v: int(np.float32(v).view(np.int32))
         self.ops.append(Op(OP_NORM_ELU, 0, src, dst, cin=c, cout=c, h=h, w=w, w_off=w_off, w_len=w_len,
                            sgeo=self.gi(h, w), dgeo=self.gi(h, w), scratch=scratch, oh=h, ow=w, MT=T, NT=lT, S=npass,
                            frag_rel=fb(1.0 / (h * w)), low=fb(1.0 / c), tapmask=fb(1.0 / (c - 1)), name=prefix))
         self.free(scratch)
 
-    def _quad_threads(self, c: int) -> Tuple[int, int, int]:
-        """(T, log2 T, passes): T = threads per channel quad = largest power of two <= nthreads / (c/4), >= 32."""
+    def _quad_threads(self, c: int, hw: int = 1 << 30) -> Tuple[int, int, int]:
+        """(T, log2 T, passes): T = threads per channel quad = largest power of two <= nthreads / (c/4), >= 32.
+        Small maps (<= 64 pixels) get one warp per quad: the statistics then need no cross-warp exchange."""
         assert c % 8 == 0
         nq = c // 4
         T = 32
-        while T * 2 <= self.nthreads // nq:
+        while T * 2 <= self.nthreads // nq and hw > 64:
             T *= 2
         gpp = self.nthreads // T
         return T, T.bit_length() - 1, (nq + gpp - 1) // gpp
