@@ -179,10 +179,11 @@ __device__ __forceinline__ void sbc_mma_pass(const SbcALane<SMEM>& A, const int 
 #pragma unroll
                 for (int n = 0; n < NN; n++) accx[c][j][n][0] = accx[c][j][n][1] = accx[c][j][n][2] = accx[c][j][n][3] = 0.f;
     }
+    const int* tp = steptab + s0;                 // running pointers: no per-step 64-bit address arithmetic
+    const float* bp = bfrag + (size_t)s0 * bstride;
 #pragma unroll 1
-    for (int s = s0; s < s1; s++) {
-        const int off = steptab[s];
-        const float* bp = bfrag + s * bstride;
+    for (int s = s0; s < s1; s++, tp++, bp += bstride) {
+        const int off = *tp;
         float bh[NN][2], bl[NN][2];
 #pragma unroll
         for (int n = 0; n < NN; n++) {
