@@ -254,10 +254,11 @@ def main():
     kern_s = ms_res * 1e-3 / args.steps                                    # one launch per step dominates the step
     achieved = flops_per_launch / kern_s / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    # context for the fraction: this kernel's MMAs are mma.sync TF32 (ncu: 1024 FLOP/clk/SM = ~298 TFLOP/s per
-    # B200), and the fp32-equivalent mode issues 3 of them per algorithmic MMA
+    # context for the fraction: this kernel's MMAs are mma.sync TF32, measured at one m16n8k8 per ~12 clk per SM
+    # sub-partition (~683 FLOP/clk/SM, ~199 TFLOP/s per B200), and the fp32-equivalent mode
+    # issues 3 of them per algorithmic MMA
     sm_clk_ghz = 1.965
-    mma_sync_tf32_peak = 1024 * 148 * sm_clk_ghz / 1e3
+    mma_sync_tf32_peak = (2 * 1024 * 4 / 12.0) * 148 * sm_clk_ghz / 1e3
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": 11.9e6 if levels == 16 else None,
                 "traffic_note": "ncu dram__bytes_read+write = 11.9 MB for the 16-level launch at B=256 captured in "
