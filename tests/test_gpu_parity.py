@@ -340,3 +340,28 @@ def test_dc_boost_and_early_stop_match_oracle(dev):
     Xa, la = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), **kw)
     Xb, lb = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), dc_boost=1.0, stop_step=1000, **kw)
     assert torch.equal(Xa, Xb) and torch.equal(la, lb)
+
+
+def test_ngf32_train_default_width_matches_oracle(dev):
+    """ngf = 32 is the default of reference train_score.py:43 (the shipped checkpoint has 8): 16x the conv work and a
+    ~1.4 MB arena, so the fused kernel runs it from the L2-resident global arena; forward and one ALD step vs the
+    oracle."""
+    from oracle import oracle as orc
+    sd, m = _model(32, 9, dev)
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((2, 2, 64, 16)) * 2).astype(np.float32)
+    y = np.array([10, 2000])
+    out = m(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)).cpu().numpy()
+    assert m.packed(64, 16, dev).info().arena_in_smem == 0
+    net = orc.OracleNet(sd, 32, 64, 16)
+    ref = net.forward(x, y)
+    for b in range(2):
+        assert _rel(out[b], ref[b]) < 2e-5, (b, _rel(out[b], ref[b]))
+    P, Y, X0, H, nv = _problem(2, snr=10.0, seed=4)
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=SIGMA_END, level_begin=0, level_end=1, steps_each=2,
+              seed=3)
+    tt = lambda a: torch.from_numpy(a).to(dev)
+    X, nlog = sampler.ald_run(m, tt(P), tt(Y), tt(X0), tt(H), **kw)
+    Xo, nlo = net.ald(P, Y, X0, H, **kw)
+    assert np.abs(X.cpu().numpy() - Xo).max() < 2e-5 * np.abs(Xo).max()
+    assert np.allclose(nlog.cpu().numpy(), nlo, rtol=1e-4)
