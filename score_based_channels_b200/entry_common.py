@@ -47,6 +47,17 @@ def pick_device(gpu: int) -> Tuple[torch.device, int, int]:
     return dev, rank, ws
 
 
+def common_seed(seed: Optional[int], dev: torch.device, ws: int) -> int:
+    """Seed of the sampler's Philox stream and of the measurement-noise generator: ``--seed`` when given (the
+    reference seeds nothing), else a fresh draw -- rank 0's, so that every rank of a sharded run uses the same one."""
+    s = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+    if ws > 1:
+        t = torch.tensor([s], dtype=torch.int64, device=dev)
+        torch.distributed.broadcast(t, src=0)
+        s = int(t.item())
+    return s
+
+
 def finalize() -> None:
     """Tear down torch.distributed at the end of an entry point started under torchrun."""
     if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -61,7 +61,7 @@ def main(argv=None):
     if args.seed is not None:
         torch.manual_seed(args.seed)
         np.random.seed(args.seed)
-    sampler_seed = args.seed if args.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+    sampler_seed = ec.common_seed(args.seed, dev, ws)
 
     contents = ec.load_checkpoint(args.ckpt or './models/score/%s/final_model.pt' % args.model)
     config = contents['config']

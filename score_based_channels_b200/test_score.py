@@ -45,7 +45,7 @@ def main(argv=None):
     if args.seed is not None:
         torch.manual_seed(args.seed)
         np.random.seed(args.seed)
-    sampler_seed = args.seed if args.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+    sampler_seed = ec.common_seed(args.seed, dev, ws)
 
     # Target file (test_score.py:32-36)
     target_dir = './models/score/%s' % args.train
@@ -96,10 +96,9 @@ def main(argv=None):
         if ws > 1:   # every rank must hold the same inputs: rank 0's draw is broadcast
             for t in (val_P, val_H, init_val_H):
                 torch.distributed.broadcast(torch.view_as_real(t), src=0)
-        gen = None
-        if ws > 1:
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(sampler_seed + 17 * meta_idx)
+        # measurement noise from a dedicated generator: the same draw whatever the number of ranks
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(sampler_seed + 17 * meta_idx)
         nm = ec.ald_over_snr(diffuser, val_P, val_H, init_val_H, noise_range, alpha_step, beta_noise,
                              float(val_config.model.sigma_end), num_levels, steps_each,
                              seed=sampler_seed + meta_idx, generator=gen)

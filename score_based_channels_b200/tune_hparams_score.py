@@ -41,7 +41,7 @@ def main(argv=None):
     if args.seed is not None:
         torch.manual_seed(args.seed)
         np.random.seed(args.seed)
-    sampler_seed = args.seed if args.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+    sampler_seed = ec.common_seed(args.seed, dev, ws)
 
     target_dir = './models/score/%s' % args.channel
     target_file = args.ckpt or os.path.join(target_dir, 'final_model.pt')
@@ -83,12 +83,12 @@ def main(argv=None):
         val_H_herm = torch.from_numpy(np.stack([it['H_herm'] for it in items])).to(dev)
         val_H = (val_H_herm[:, 0] + 1j * val_H_herm[:, 1]).contiguous()
         init_val_H = torch.randn_like(val_H)
-        gen = None
         if ws > 1:
             for t in (val_P, val_H, init_val_H):
                 torch.distributed.broadcast(torch.view_as_real(t), src=0)
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(sampler_seed + 17 * meta_idx)
+        # measurement noise from a dedicated generator: the same draw whatever the number of ranks
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(sampler_seed + 17 * meta_idx)
         nm = ec.ald_over_snr(diffuser, val_P, val_H, init_val_H, noise_range, float(alpha_step), float(beta_noise),
                              float(val_config.model.sigma_end), num_levels, steps_each,
                              seed=sampler_seed + meta_idx, id_base=meta_idx * len(snr_range) * n, generator=gen)
