@@ -1,5 +1,5 @@
 // sbc_kernel.cuh -- persistent fused kernel: one CTA owns one channel realisation at a time and
-// runs, entirely out of shared memory, the whole NCSNv2Deepest forward (161-op layer program,
+// runs, entirely out of shared memory, the whole NCSNv2Deepest forward (152-op layer program,
 // reference ncsnv2/models/ncsnv2.py:269-300) followed by the data-consistency gradient, the
 // Langevin update, the Philox noise draw and the per-step NMSE (reference test_score.py:135-171)
 // for every (sigma level, inner step) of the requested range.  Nothing returns to the host inside
