@@ -43,65 +43,61 @@ def find_data_file(channel: str, spacing: float, seed: int, allow_other_seed: bo
     raise FileNotFoundError("./data/%s (also searched $SBC_DATA_DIR, ./fixtures_local, ./sample_data)" % names[0])
 
 
+def _herm(a: np.ndarray) -> np.ndarray:
+    return np.conj(a.T)
+
+
+def _planes(a: np.ndarray) -> np.ndarray:
+    """complex [r, c] -> float32 [2, r, c] (re, im): the network's channel layout."""
+    return np.stack((a.real, a.imag), axis=0).astype(np.float32)
+
+
 class Channels(Dataset):
-    """MIMO Channels"""
+    """Validation / training channel set with the interface of the reference ``Channels`` (``loaders.py:8-107``).
+
+    Behavioural contract kept from the reference (restated, not copied):
+    * one ``.mat`` per antenna spacing in ``config.data.spacing_list``; of every realisation only the first
+      subcarrier/symbol slice ``output_h[:, 0]`` ([Nr, Nt]) is used (``loaders.py:30-33``);
+    * ``norm``: ``[mean, std]`` list = use as given; ``'global'`` = mean 0, std of all entries; ``'entrywise'`` =
+      per-entry statistics (``loaders.py:39-49``);
+    * QPSK pilots ``(+-1 +-1j)/sqrt(2)`` of shape [N, Nt, num_pilots], real parts drawn before imaginary parts from
+      numpy's global RNG (``loaders.py:52-55``), per-item measurement noise likewise (``:79-82``)."""
+
+    _ITEM_KEYS = ("H", "H_herm", "H_herm_cplx", "P", "P_herm", "Y", "Y_herm", "eig1", "sigma_n", "idx")
 
     def __init__(self, seed, config, norm=None):
-        target_spacings = config.data.spacing_list
-        target_channel = config.data.channel
-        self.channels = []
-        self.spacings = np.copy(target_spacings)
-        self.filenames = []
-        for spacing in target_spacings:
-            filename = find_data_file(target_channel, spacing, seed)
-            self.filenames.append(filename)
-            contents = loadmat_v73(filename)
-            channels = np.asarray(contents["output_h"], dtype=np.complex64)
-            self.channels.append(channels[:, 0])            # first subcarrier of each symbol (loaders.py:33)
-        self.channels = np.asarray(self.channels)
-        self.channels = np.reshape(self.channels, (-1, self.channels.shape[-2], self.channels.shape[-1]))
+        data = config.data
+        self.spacings = np.array(data.spacing_list, copy=True)
+        self.filenames = [find_data_file(data.channel, sp, seed) for sp in data.spacing_list]
+        per_file = [np.asarray(loadmat_v73(f)["output_h"], dtype=np.complex64)[:, 0] for f in self.filenames]
+        stacked = np.asarray(per_file)
+        self.channels = stacked.reshape((-1,) + stacked.shape[-2:])
 
-        if type(norm) == list:
-            self.mean, self.std = norm[0], norm[1]
-        elif norm == "entrywise":
-            self.mean = np.mean(self.channels, axis=0)
-            self.std = np.std(self.channels, axis=0)
+        if isinstance(norm, list):
+            self.mean, self.std = norm
         elif norm == "global":
-            self.mean = 0.
-            self.std = np.std(self.channels)
+            self.mean, self.std = 0., np.std(self.channels)
+        elif norm == "entrywise":
+            self.mean, self.std = np.mean(self.channels, axis=0), np.std(self.channels, axis=0)
 
-        # random QPSK pilots (loaders.py:52-55)
-        shape = (self.channels.shape[0], config.data.image_size[1], config.data.num_pilots)
-        self.pilots = 1 / np.sqrt(2) * (2 * np.random.binomial(1, 0.5, size=shape) - 1 +
-                                        1j * (2 * np.random.binomial(1, 0.5, size=shape) - 1))
-        self.noise_power = 1 / np.sqrt(2) * config.data.noise_std
+        n_tx = data.image_size[1]
+        bits = [np.random.binomial(1, 0.5, size=(len(self.channels), n_tx, data.num_pilots)) for _ in range(2)]
+        self.pilots = ((2 * bits[0] - 1) + 1j * (2 * bits[1] - 1)) / np.sqrt(2)
+        self.noise_power = data.noise_std / np.sqrt(2)
 
     def __len__(self):
-        return len(self.channels)
+        return self.channels.shape[0]
 
     def __getitem__(self, idx):
-        if torch.is_tensor(idx):
-            idx = idx.tolist()
-        H_cplx = self.channels[idx]
-        H_cplx_norm = (H_cplx - self.mean) / self.std
-        H_real_norm = np.stack((np.real(H_cplx_norm), np.imag(H_cplx_norm)), axis=0)
-        P = self.pilots[idx]
-        Y = np.matmul(H_cplx, P)
-        N = self.noise_power * (np.random.normal(size=Y.shape) + 1j * np.random.normal(size=Y.shape))
-        Y = Y + N
-        eigvals = np.real(np.linalg.eigvals(np.matmul(P, np.conj(P.T))))
-        H_herm = np.conj(np.transpose(H_cplx))
-        H_herm_norm = np.conj(np.transpose(H_cplx_norm))
-        H_real_herm_norm = np.stack((np.real(H_herm_norm), np.imag(H_herm_norm)), axis=0)
-        P_herm = np.conj(np.transpose(P))
-        Y_herm = np.conj(np.transpose(Y))
-        return {"H": H_real_norm.astype(np.float32),
-                "H_herm": H_real_herm_norm.astype(np.float32),
-                "H_herm_cplx": H_herm.astype(np.complex64),
-                "P": self.pilots[idx].astype(np.complex64),
-                "P_herm": P_herm.astype(np.complex64),
-                "Y": Y.astype(np.complex64),
-                "Y_herm": Y_herm.astype(np.complex64),
-                "eig1": eigvals[0].astype(np.float32),
-                "sigma_n": np.float32(self.noise_power),
-                "idx": int(idx)}
+        idx = idx.tolist() if torch.is_tensor(idx) else idx
+        h = self.channels[idx]                              # [Nr, Nt]
+        hn = (h - self.mean) / self.std
+        p = self.pilots[idx]                                # [Nt, Np]
+        y = h @ p
+        noise = [np.random.normal(size=y.shape) for _ in range(2)]
+        y = y + self.noise_power * (noise[0] + 1j * noise[1])
+        gram_eig = np.linalg.eigvals(p @ _herm(p)).real
+        values = (_planes(hn), _planes(_herm(hn)), _herm(h).astype(np.complex64), p.astype(np.complex64),
+                  _herm(p).astype(np.complex64), y.astype(np.complex64), _herm(y).astype(np.complex64),
+                  gram_eig[0].astype(np.float32), np.float32(self.noise_power), int(idx))
+        return dict(zip(self._ITEM_KEYS, values))
