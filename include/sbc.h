@@ -48,7 +48,7 @@ typedef struct sbc_model_desc {
     int32_t ngf;            /* config.model.ngf */
     int32_t Nt, Nr;         /* network input is [B, channels, Nt, Nr] (reference test_score.py:149) */
     int32_t channels;       /* 2 (re, im) */
-    const int32_t* op_table;/* host, [n_ops][24] int32 (csrc/sbc_program.h: SbcOp) */
+    const int32_t* op_table;/* host, [n_ops][32] int32 (csrc/sbc_program.h: SbcOp) */
     int32_t n_ops;
     const int32_t* geo_table;/* host, [n_geo][8] int32 (csrc/sbc_program.h: SbcGeo), entry 0 = Nt x Nr */
     int32_t n_geo;

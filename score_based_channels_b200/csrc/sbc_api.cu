@@ -110,6 +110,18 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         if (o.sgeo < 0 || o.sgeo >= SBC_MAX_GEO || o.dgeo < 0 || o.dgeo >= SBC_MAX_GEO) {
             return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
         }
+        {   // every arena offset an op touches must lie inside the arena (a malformed table must not write out of bounds)
+            const int offs[5] = {o.src, o.dst, o.acc, o.edst, o.scratch};
+            for (int k = 0; k < 5; k++)
+                if (offs[k] < -1 || offs[k] >= desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: arena offset out of range", i); }
+            const SbcGeo& gs = m->geo[o.sgeo]; const SbcGeo& gd = m->geo[o.dgeo];
+            const long long in_ext = (long long)((o.cin + 3) / 4) * gs.pps * 4, out_ext = (long long)((o.cout + 3) / 4) * gd.pps * 4;
+            const bool compact_in = o.kind == SBC_OP_AFFINE, compact_out = (o.kind == SBC_OP_CONV_MMA) && (o.flags & SBC_F_COMPACT);
+            if (o.src >= 0 && !compact_in && o.src + in_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: input tensor exceeds the arena", i); }
+            if (o.dst >= 0 && !compact_out && o.dst + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: output tensor exceeds the arena", i); }
+            if (o.acc >= 0 && o.acc + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: accumulator tensor exceeds the arena", i); }
+            if (o.edst >= 0 && o.edst + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: ELU output tensor exceeds the arena", i); }
+        }
         if (o.w_len > 0 && (o.wbuf < 0 || o.wbuf % 4 || o.wbuf + o.w_len > desc->arena_floats)) {
             return sbc_fail(SBC_E_ARG, "op %d: bad parameter staging buffer", i);
         }

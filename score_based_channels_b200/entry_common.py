@@ -12,13 +12,19 @@ from . import dotmap_shim, sampler
 from .ncsnv2 import NCSNv2Deepest
 
 
-def load_checkpoint(target_file: str):
+def load_checkpoint(target_file: str, model_name: Optional[str] = None):
     """``contents = torch.load(target_file)`` of reference test_score.py:33-36.  The file is a pickle that
-    embeds a ``dotmap.DotMap`` config; the bundled shim stands in for the (absent) dotmap package."""
+    embeds a ``dotmap.DotMap`` config; the bundled shim stands in for the (absent) dotmap package.
+
+    When ``target_file`` is missing the reference raises.  Two substitutions are allowed here, both announced:
+    an explicit ``$SBC_CKPT`` override, and -- only when the requested model IS the shipped one (``model_name``
+    'CDL-C') -- the shipped ``score-deepest-cdl-c.pt`` fixture.  Anything else raises FileNotFoundError, so results
+    are never written under another model's name."""
     dotmap_shim.install()
     if not os.path.exists(target_file):
-        alt = [os.environ.get("SBC_CKPT", ""), "./fixtures_local/score-deepest-cdl-c.pt",
-               "./pretrained_models/score-deepest-cdl-c.pt"]
+        alt = [os.environ.get("SBC_CKPT", "")]
+        if model_name == "CDL-C":
+            alt += ["./fixtures_local/score-deepest-cdl-c.pt", "./pretrained_models/score-deepest-cdl-c.pt"]
         for a in alt:
             if a and os.path.exists(a):
                 print("checkpoint %s not found; using %s" % (target_file, a))

@@ -65,10 +65,10 @@ class Channels(Dataset):
 
     _ITEM_KEYS = ("H", "H_herm", "H_herm_cplx", "P", "P_herm", "Y", "Y_herm", "eig1", "sigma_n", "idx")
 
-    def __init__(self, seed, config, norm=None):
+    def __init__(self, seed, config, norm=None, allow_other_seed=True):
         data = config.data
         self.spacings = np.array(data.spacing_list, copy=True)
-        self.filenames = [find_data_file(data.channel, sp, seed) for sp in data.spacing_list]
+        self.filenames = [find_data_file(data.channel, sp, seed, allow_other_seed) for sp in data.spacing_list]
         per_file = [np.asarray(loadmat_v73(f)["output_h"], dtype=np.complex64)[:, 0] for f in self.filenames]
         stacked = np.asarray(per_file)
         self.channels = stacked.reshape((-1,) + stacked.shape[-2:])

@@ -48,12 +48,14 @@ def ald_run(model: NCSNv2Deepest, P: torch.Tensor, Y: torch.Tensor, X0: torch.Te
     Nr = Y.shape[2]
     if X0.shape != (B, Nt, Nr) or Y.shape != (B, Np, Nr):
         raise ValueError("inconsistent shapes P %s Y %s X %s" % (tuple(P.shape), tuple(Y.shape), tuple(X0.shape)))
-    P = P.to(torch.complex64).contiguous()
-    Y = Y.to(torch.complex64).contiguous()
-    X = X0.to(torch.complex64).contiguous()
+    # torch's lazy conj / neg bits do not change data_ptr(): materialise them before handing raw pointers over
+    _mat = lambda t: t.to(torch.complex64).resolve_conj().resolve_neg().contiguous()
+    P = _mat(P)
+    Y = _mat(Y)
+    X = _mat(X0)
     if not inplace and X.data_ptr() == X0.data_ptr():
         X = X.clone()
-    Hc = H.to(torch.complex64).contiguous() if H is not None else None
+    Hc = _mat(H) if H is not None else None
     if level_end is None:
         level_end = model.num_classes
     if sigma_end is None:
@@ -76,7 +78,7 @@ def ald_run(model: NCSNv2Deepest, P: torch.Tensor, Y: torch.Tensor, X0: torch.Te
     ids = sample_ids.to(device=dev, dtype=torch.int64).contiguous() if sample_ids is not None else None
     en = None
     if ext_noise is not None:
-        en = ext_noise.to(device=dev, dtype=torch.complex64).contiguous()
+        en = _mat(ext_noise.to(device=dev))
         if en.shape != (nsteps, B, Nt, Nr):
             raise ValueError("ext_noise must be [steps,B,Nt,Nr]")
     pm = model.packed(Nt, Nr, dev)

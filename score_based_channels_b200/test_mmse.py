@@ -63,7 +63,7 @@ def main(argv=None):
         np.random.seed(args.seed)
     sampler_seed = ec.common_seed(args.seed, dev, ws)
 
-    contents = ec.load_checkpoint(args.ckpt or './models/score/%s/final_model.pt' % args.model)
+    contents = ec.load_checkpoint(args.ckpt or './models/score/%s/final_model.pt' % args.model, args.model)
     config = contents['config']
     config.sampling.sigma = 0.
     config.purpose = 'train'
@@ -115,7 +115,7 @@ def main(argv=None):
         val_config.data.channel = args.channel
         val_config.data.spacing_list = [spacing]
         val_config.data.num_pilots = int(np.floor(config.data.num_pilots * pilot_alpha))
-        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std])
+        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std], allow_other_seed=False)
         print('There are %d validation channels!' % len(val_dataset))
         n = min(kept, len(val_dataset))
         items = [val_dataset[i] for i in range(n)]
@@ -133,7 +133,9 @@ def main(argv=None):
             noise_boost = float(best_noise[pilot_alpha_idx, snr_idx])
             target_stop = int(best_stop[pilot_alpha_idx, snr_idx])
             local_Y = torch.matmul(val_P, val_H)
-            local_Y = local_Y + float(np.sqrt(local_noise)) * torch.randn_like(local_Y)
+            local_Y = (local_Y + float(np.sqrt(local_noise)) * torch.randn_like(local_Y)).contiguous()
+            if ws > 1:   # rank 0's measurement noise is THE draw: broadcast before anything is derived from it
+                torch.distributed.broadcast(torch.view_as_real(local_Y), src=0)
             # every channel is replicated mmse_avg times: same pilots / measurements, independent chains (:180-187)
             gP = val_P.repeat_interleave(navg, dim=0)
             gY = local_Y.repeat_interleave(navg, dim=0)
@@ -144,9 +146,9 @@ def main(argv=None):
                 current = torch.matmul(torch.conj(torch.transpose(gP, -1, -2)), gY)
             else:   # 'LS' (:199-201): minimum-norm least squares of P x = y on the host
                 current = torch.linalg.lstsq(gP.cpu(), gY.cpu(), driver='gelsd').solution.to(dev)
+            current = current.contiguous()     # lstsq returns a column-major solution
             if ws > 1:
-                for t in (gY, current):
-                    torch.distributed.broadcast(torch.view_as_real(t.contiguous()), src=0)
+                torch.distributed.broadcast(torch.view_as_real(current), src=0)
             total = n * navg
             lo, hi = sdist.shard_range(total, rank, ws)
             ids = torch.arange(lo, hi, dtype=torch.int64, device=dev) + (meta_idx * len(snr_range) + snr_idx) * total

@@ -50,7 +50,7 @@ def main(argv=None):
     # Target file (test_score.py:32-36)
     target_dir = './models/score/%s' % args.train
     target_file = args.ckpt or os.path.join(target_dir, 'final_model.pt')
-    contents = ec.load_checkpoint(target_file)
+    contents = ec.load_checkpoint(target_file, args.train)
     config = contents['config']
 
     # Default hyper-parameters for pilot_alpha = 0.6, all SNR points (test_score.py:38-54)
@@ -84,9 +84,12 @@ def main(argv=None):
         val_config.data.channel = args.test
         val_config.data.spacing_list = [spacing]
         val_config.data.num_pilots = int(np.floor(config.data.image_size[1] * pilot_alpha))
-        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std])
+        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std], allow_other_seed=False)
         print('There are %d validation channels' % len(val_dataset))
-        n = min(num_channels, len(val_dataset))
+        if len(val_dataset) < num_channels:   # the reference's DataLoader(batch_size=num_channels, drop_last=True) yields nothing
+            raise ValueError('validation set holds %d channels, fewer than --num_channels %d: averages over the '
+                             'missing columns would be diluted' % (len(val_dataset), num_channels))
+        n = num_channels
         items = [val_dataset[i] for i in range(n)]
         val_P = torch.from_numpy(np.stack([it['P'] for it in items])).to(dev)
         val_P = torch.conj(torch.transpose(val_P, -1, -2)).contiguous()      # Hermitian pilots (:110)

@@ -45,7 +45,7 @@ def main(argv=None):
 
     target_dir = './models/score/%s' % args.channel
     target_file = args.ckpt or os.path.join(target_dir, 'final_model.pt')
-    contents = ec.load_checkpoint(target_file)
+    contents = ec.load_checkpoint(target_file, args.channel)
     config = contents['config']
     diffuser = ec.build_model(config, contents['model_state'], dev, args.precision)
 
@@ -74,9 +74,12 @@ def main(argv=None):
         val_config.data.channel = args.channel
         val_config.data.spacing_list = [args.spacing]
         val_config.data.num_pilots = int(np.floor(config.data.image_size[1] * args.pilot_alpha))
-        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std])
+        val_dataset = Channels(val_seed, val_config, norm=[dataset.mean, dataset.std], allow_other_seed=False)
         print('There are %d validation channels' % len(val_dataset))
-        n = min(nch, len(val_dataset))
+        if len(val_dataset) < nch:   # the reference's DataLoader(batch_size=num_channels, drop_last=True) yields nothing
+            raise ValueError('validation set holds %d channels, fewer than --num_channels %d: averages over the '
+                             'missing columns would be diluted' % (len(val_dataset), nch))
+        n = nch
         items = [val_dataset[i] for i in range(n)]
         val_P = torch.from_numpy(np.stack([it['P'] for it in items])).to(dev)
         val_P = torch.conj(torch.transpose(val_P, -1, -2)).contiguous()
