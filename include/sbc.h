@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define SBC_VERSION 101   /* 0.1.1: sbc_ald_args gained dc_boost / stop_step (appended) */
+#define SBC_VERSION 200   /* 0.2.0: engine 2 (tcgen05): sbc_model_create_from_state, sbc_info gained engine / ctas_per_sm /
+                           * group_size / n_ops (appended), debug views sbc_debug_plan / sbc_debug_run */
 
 enum {
     SBC_OK = 0,
@@ -74,7 +75,29 @@ typedef struct sbc_info {
     int64_t arena_bytes;
     int64_t conv_flops_per_forward;
     int64_t kernel_launches;    /* launches issued through this handle so far */
+    int32_t engine;             /* 1: fused shared-memory arena on mma.sync; 2: tcgen05 / TMEM, L2-resident arena */
+    int32_t ctas_per_sm;        /* resident CTAs per SM (engine 2: 2) */
+    int32_t group_size;         /* engine 2: samples per CTA group (S) of the last launch */
+    int32_t n_ops;              /* ops of the layer program */
 } sbc_info;
+
+/* One tensor of a reference state dict (same key names as NCSNv2Deepest.state_dict(), reference
+ * ncsnv2/models/ncsnv2.py:198-262; 'sigmas' carries the noise schedule).  fp32, C-contiguous, host memory. */
+typedef struct sbc_state_entry {
+    const char* name;
+    const float* data;
+    const int64_t* shape;
+    int32_t ndim;
+} sbc_state_entry;
+
+/* Debug view of one activation tensor of an engine-2 plan (sbc_debug_plan). */
+typedef struct sbc_tensor_info {
+    char name[48];
+    int32_t fmt;                /* 0: F32 [C/4][npx][4], 1: SP16 [C/8][hi,lo][npx][8 halfs], 2: raw */
+    int32_t level, C;
+    int64_t off, bytes;         /* inside the group arena */
+    int32_t born, died;         /* live range in op indices */
+} sbc_tensor_info;
 
 /* One annealed-Langevin run over levels [level_begin, level_end) x steps_each for B independent
  * channel realisations.  Replaces the loop body reference test_score.py:135-171 (duplicated at
@@ -106,6 +129,12 @@ int sbc_threads_per_cta(void);   /* compile-time CTA size of the fused kernel (t
 const char* sbc_last_error(void);
 
 int sbc_model_create(const sbc_model_desc* desc, int device, void** handle_out);
+/* Engine 2 (tcgen05): builds the layer program, plans the activation arena and packs the parameters inside the
+ * library from a plain state dict -- no Python planner involved.  Replaces `NCSNv2Deepest(config)` +
+ * `load_state_dict` + `.cuda()` (reference test_score.py:59-63).  Conv arithmetic: fp16 hi/lo split operands
+ * ("fp16x2", 22 significant bits, fp32 accumulate in TMEM): fp32-equivalent. */
+int sbc_model_create_from_state(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt, int32_t Nr,
+                                int32_t channels, int device, void** handle_out);
 int sbc_model_free(void* handle);
 int sbc_query(void* handle, sbc_info* out);
 
@@ -127,6 +156,17 @@ int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
  * excluding op `stop_op` (n_ops = all) and copy the whole arena to arena_out (device,
  * arena_floats). */
 int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
+
+/* Engine-2 debug views.  sbc_debug_plan: tensor table (up to `cap` entries), arena size and the four level
+ * geometries ([4][12] int32: h, w, hy, hx, wp, rps, pps, lead, npx, T, slot, hw) of the plan for group size S
+ * (reuse = 0: every tensor gets its own region, so a whole forward can be inspected afterwards).
+ * sbc_debug_run: one forward of S samples x (device fp32 [S,channels,Nt,Nr] contiguous) as ONE group, then the
+ * group arena is copied to arena_out (device).  sbc_op_name / sbc_op_kind: the layer program. */
+int sbc_debug_plan(void* handle, int32_t S, int32_t reuse, sbc_tensor_info* out, int32_t cap, int32_t* n_out,
+                   int64_t* arena_bytes, int32_t* geo_out);
+int sbc_debug_run(void* handle, const float* x, int32_t S, int32_t reuse, void* arena_out, void* stream);
+const char* sbc_op_name(void* handle, int32_t i);
+int sbc_op_kind(void* handle, int32_t i);
 
 /* Profiling aid: subsequent launches of this handle make CTA 0 record clock64() at every op
  * boundary of its first sample / second step (first if there is only one) into dev_stamps (device int64 [6 * n_ops + 2]: op starts,

@@ -9,8 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbc_b200.so")
 
-EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_free", "sbc_query", "sbc_forward",
-           "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host", "sbc_debug_arena", "sbc_set_profile_buffer")
+EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_create_from_state",
+           "sbc_model_free", "sbc_query", "sbc_forward", "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host",
+           "sbc_debug_arena", "sbc_set_profile_buffer", "sbc_debug_plan", "sbc_debug_run", "sbc_op_name", "sbc_op_kind")
 
 
 class ModelDesc(C.Structure):
@@ -25,7 +26,17 @@ class ModelDesc(C.Structure):
 class Info(C.Structure):
     _fields_ = [("version", C.c_int32), ("device", C.c_int32), ("num_sms", C.c_int32), ("threads_per_cta", C.c_int32),
                 ("arena_in_smem", C.c_int32), ("weights_staged", C.c_int32), ("smem_bytes_per_cta", C.c_int64),
-                ("arena_bytes", C.c_int64), ("conv_flops_per_forward", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("arena_bytes", C.c_int64), ("conv_flops_per_forward", C.c_int64), ("kernel_launches", C.c_int64),
+                ("engine", C.c_int32), ("ctas_per_sm", C.c_int32), ("group_size", C.c_int32), ("n_ops", C.c_int32)]
+
+
+class StateEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("shape", C.c_void_p), ("ndim", C.c_int32)]
+
+
+class TensorInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("fmt", C.c_int32), ("level", C.c_int32), ("C", C.c_int32),
+                ("off", C.c_int64), ("bytes", C.c_int64), ("born", C.c_int32), ("died", C.c_int32)]
 
 
 class AldArgs(C.Structure):
@@ -62,6 +73,14 @@ def lib():
         L.sbc_ald_run_host.argtypes = [C.c_void_p, C.POINTER(AldArgs)]
         L.sbc_debug_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.sbc_set_profile_buffer.argtypes = [C.c_void_p, C.c_void_p]
+        L.sbc_model_create_from_state.argtypes = [C.POINTER(StateEntry), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                  C.c_int32, C.c_int, C.POINTER(C.c_void_p)]
+        L.sbc_debug_plan.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
+        L.sbc_debug_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.sbc_op_name.restype = C.c_char_p
+        L.sbc_op_name.argtypes = [C.c_void_p, C.c_int32]
+        L.sbc_op_kind.argtypes = [C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 

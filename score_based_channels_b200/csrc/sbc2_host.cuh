@@ -1,0 +1,162 @@
+// sbc2_host.cuh -- host side of engine 2 (tcgen05): model object, per-group-size plan cache, launch.
+// Included by sbc_api.cu, which exposes it through the C ABI of include/sbc.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "sbc2_kernel.cuh"
+#include "sbc2_plan.h"
+
+struct Sbc2PlanDev {
+    sbc2::Plan plan;
+    sbc2::Op* d_ops = nullptr;
+    int32_t* d_pix[sbc2::MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    ~Sbc2PlanDev() {
+        cudaFree(d_ops);
+        for (auto p : d_pix) cudaFree(p);
+    }
+};
+
+struct Sbc2Model {
+    int device = 0, num_sms = 0, smem_optin = 0;
+    int ngf = 0, Nt = 0, Nr = 0, channels = 2;
+    std::unique_ptr<sbc2::Builder> builder;
+    // the builder keeps a reference to the state dict: own copies of the tensors
+    sbc2::StateDict sd;
+    std::vector<std::vector<float>> storage;
+    uint8_t* d_blob = nullptr;
+    float* d_sigmas = nullptr;
+    int n_sigmas = 0;
+    std::map<std::pair<int, int>, std::unique_ptr<Sbc2PlanDev>> plans;   // (S, reuse) -> device plan
+    uint8_t* d_gws = nullptr;
+    size_t gws_bytes = 0;
+    long long* d_prof = nullptr;
+    long long launches = 0;
+    int wmax = 0, stage_bytes = 0;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 2;
+    int last_S = 0, last_grid = 0;
+    ~Sbc2Model() {
+        cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
+    }
+};
+
+static const int SBC2_STAGE_CAP = 32 * 1024;
+
+// returns an error string ("" = ok)
+static std::string sbc2_create(Sbc2Model* m, const sbc2::StateDict& sd_in, int ngf, int Nt, int Nr, int channels, int device) {
+    m->device = device; m->ngf = ngf; m->Nt = Nt; m->Nr = Nr; m->channels = channels;
+    for (auto& kv : sd_in) {
+        int64_t n = 1;
+        for (auto d : kv.second.shape) n *= d;
+        m->storage.emplace_back(kv.second.data, kv.second.data + n);
+        m->sd[kv.first] = sbc2::TensorArg{m->storage.back().data(), kv.second.shape};
+    }
+    auto it = m->sd.find("sigmas");
+    if (it == m->sd.end()) return "state dict has no 'sigmas' entry";
+    m->n_sigmas = (int)it->second.shape[0];
+    try {
+        m->builder.reset(new sbc2::Builder(m->sd, ngf, Nt, Nr, channels, SBC2_STAGE_CAP));
+    } catch (const std::exception& e) {
+        return std::string("planner: ") + e.what();
+    }
+    if (cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return "cudaDeviceGetAttribute failed";
+    cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const sbc2::Builder& b = *m->builder;
+    m->wmax = (b.max_seg + 127) / 128 * 128;
+    m->stage_bytes = (std::max(b.max_stage, 1024) + 127) / 128 * 128;
+    m->smem_bytes = 2 * (size_t)m->wmax + (size_t)m->stage_bytes + SBC2_NBARS * 8 + SBC2_PART_FLOATS * 4;
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, sbc2_ald_kernel) != cudaSuccess) return std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError());
+    if (m->smem_bytes + fa.sharedSizeBytes > (size_t)m->smem_optin)
+        return "model needs " + std::to_string(m->smem_bytes) + " bytes of shared memory per CTA (weights of the widest conv twice + staging): too wide for engine 2";
+    if (cudaFuncSetAttribute(sbc2_ald_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes) != cudaSuccess)
+        return std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(cudaGetLastError());
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sbc2_ald_kernel, SBC2_NTHR, m->smem_bytes);
+    m->ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);     // TMEM: 256 columns per CTA -> at most 2
+    if (cudaMalloc(&m->d_blob, b.blob.size() ? b.blob.size() : 16) != cudaSuccess) return "cudaMalloc(blob) failed";
+    cudaMemcpy(m->d_blob, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&m->d_sigmas, sizeof(float) * (size_t)m->n_sigmas) != cudaSuccess) return "cudaMalloc(sigmas) failed";
+    cudaMemcpy(m->d_sigmas, it->second.data, sizeof(float) * (size_t)m->n_sigmas, cudaMemcpyHostToDevice);
+    return "";
+}
+
+static Sbc2PlanDev* sbc2_plan(Sbc2Model* m, int S, bool reuse, std::string& err) {
+    auto key = std::make_pair(S, reuse ? 1 : 0);
+    auto it = m->plans.find(key);
+    if (it != m->plans.end()) return it->second.get();
+    std::unique_ptr<Sbc2PlanDev> pd(new Sbc2PlanDev());
+    try {
+        pd->plan = m->builder->layout(S, reuse);
+    } catch (const std::exception& e) {
+        err = std::string("planner: ") + e.what();
+        return nullptr;
+    }
+    const auto& ops = pd->plan.ops;
+    if (cudaMalloc(&pd->d_ops, sizeof(sbc2::Op) * ops.size()) != cudaSuccess) { err = "cudaMalloc(ops) failed"; return nullptr; }
+    cudaMemcpy(pd->d_ops, ops.data(), sizeof(sbc2::Op) * ops.size(), cudaMemcpyHostToDevice);
+    for (int l = 0; l < sbc2::MAX_LEVELS; l++) {
+        const auto& pm = pd->plan.pix[l];
+        if (cudaMalloc(&pd->d_pix[l], pm.size() * 4) != cudaSuccess) { err = "cudaMalloc(pix) failed"; return nullptr; }
+        cudaMemcpy(pd->d_pix[l], pm.data(), pm.size() * 4, cudaMemcpyHostToDevice);
+    }
+    Sbc2PlanDev* r = pd.get();
+    m->plans[key] = std::move(pd);
+    return r;
+}
+
+static int sbc2_env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+// group size for a batch: one sample per CTA slot while the batch fits in one wave, then grow the groups
+static int sbc2_pick_S(const Sbc2Model* m, int B) {
+    const int forced = sbc2_env_int("SBC2_S", 0);
+    if (forced > 0) return forced > SBC2_MAXS ? SBC2_MAXS : forced;
+    const int slots = m->num_sms * m->ctas_per_sm;
+    int S = (B + slots - 1) / slots;
+    if (S < 1) S = 1;
+    if (S > SBC2_MAXS) S = SBC2_MAXS;
+    return S;
+}
+
+// fills the common part of the launch record and makes sure the workspace is large enough
+static std::string sbc2_prepare(Sbc2Model* m, int B, int S, bool reuse, Sbc2Launch& L, int& grid) {
+    std::string err;
+    Sbc2PlanDev* pd = sbc2_plan(m, S, reuse, err);
+    if (!pd) return err;
+    const int n_groups = (B + S - 1) / S;
+    const int slots = m->num_sms * m->ctas_per_sm;
+    grid = n_groups < slots ? n_groups : slots;
+    const size_t need = (size_t)grid * (size_t)pd->plan.arena_bytes;
+    if (need > m->gws_bytes) {
+        cudaFree(m->d_gws);
+        m->d_gws = nullptr; m->gws_bytes = 0;
+        if (cudaMalloc(&m->d_gws, need) != cudaSuccess) return "cudaMalloc(workspace, " + std::to_string(need) + " bytes) failed";
+        m->gws_bytes = need;
+    }
+    memset(&L, 0, sizeof L);
+    L.ops = pd->d_ops; L.n_ops = (int)pd->plan.ops.size(); L.blob = m->d_blob;
+    for (int l = 0; l < sbc2::MAX_LEVELS; l++) { L.geo[l] = pd->plan.geo[l]; L.pix[l] = pd->d_pix[l]; }
+    L.gws = m->d_gws; L.arena_bytes = pd->plan.arena_bytes;
+    L.S = S; L.B = B;
+    L.x_off = pd->plan.x_off; L.out_off = pd->plan.out_off; L.post_off = pd->plan.post_off;
+    L.wmax = m->wmax; L.stage_bytes = m->stage_bytes;
+    L.Nt = m->Nt; L.Nr = m->Nr; L.channels = m->channels;
+    L.sigmas = m->d_sigmas; L.n_sigmas = m->n_sigmas;
+    L.prof = m->d_prof;
+    m->last_S = S; m->last_grid = grid;
+    return "";
+}
+
+static cudaError_t sbc2_launch(Sbc2Model* m, const Sbc2Launch& L, int grid, cudaStream_t st) {
+    sbc2_ald_kernel<<<grid, SBC2_NTHR, m->smem_bytes, st>>>(L);
+    m->launches++;
+    return cudaGetLastError();
+}

@@ -1,0 +1,799 @@
+// sbc2_kernel.cuh -- engine 2: persistent annealed-Langevin kernel with the conv contractions on tcgen05 / TMEM.
+//
+// One CTA (192 threads, two CTAs per SM) owns a GROUP of S channel realisations and walks them in lock-step through
+// the layer program of NCSNv2Deepest.forward (reference ncsnv2/models/ncsnv2.py:269-300) and then through the
+// data-consistency gradient, Langevin update, Philox noise and NMSE of reference test_score.py:157-170, for every
+// (sigma level, inner step) of the requested range.  Activations live in a per-CTA arena in global memory that stays
+// L2 resident (layouts: sbc2_plan.h); they are never touched by another SM and never returned to the host.
+//
+// A conv op is a warp-specialised pipeline over 128-pixel M tiles of the S stacked images:
+//   warp 4 (one lane): cp.async.bulk (TMA bulk copy) of the tile's input window, every 16-byte sub-plane, global ->
+//                      shared staging ring, completion on an mbarrier; also prefetches the NEXT conv's parameter
+//                      segment (UMMA list | bias | B tiles) into the other weight buffer
+//   warp 5 (one lane): tcgen05.mma kind::f16 (M128 x N x K16, fp32 accumulate in TMEM) per (tap, channel chunk) straight
+//                      off the staged window -- a tap is a start-address shift of the no-swizzle K-major descriptor --
+//                      then tcgen05.commit to free the stage and to publish the accumulator slot
+//   warps 0-3        : epilogue: tcgen05.ld of the accumulator (lane = pixel), hi + lo column groups summed, bias,
+//                      residual accumulate, ELU, fp16 hi/lo split, coalesced 16-byte stores
+// TMEM: 256 columns per CTA = 4 accumulator slots of 64 columns, so the MMAs of up to 4 tiles run ahead of the epilogue.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sbc2_plan.h"
+#include "sbc_ops.h"
+
+#define SBC2_NTHR 192
+#define SBC2_NACC 4
+#define SBC2_TMEM_COLS 256
+#define SBC2_MAXS 8
+#define SBC2_NBARS 24
+#define SBC2_PART_FLOATS 1024      // shared scratch of the norm statistics: 2 x 64 units x 8 channels
+
+struct Sbc2Launch {
+    const sbc2::Op* ops;
+    int n_ops;
+    const uint8_t* blob;
+    sbc2::Geo geo[sbc2::MAX_LEVELS];
+    const int32_t* pix[sbc2::MAX_LEVELS];
+    uint8_t* gws;                 // [gridDim.x] group arenas
+    long long arena_bytes;
+    int S, B;
+    int x_off, out_off, post_off;
+    int first_w_off, first_w_len;
+    int wmax, stage_bytes;        // shared-memory carve-up (bytes): two weight buffers of wmax, one staging ring
+    int Nt, Nr, channels;
+    int mode;                     // 0 = forward, 1 = annealed Langevin
+    // forward mode
+    const float* fx;
+    long long fxs[4];
+    const long long* labels;
+    float* fout;
+    const float* sigmas;
+    int n_sigmas;
+    // ALD mode (same meaning as engine 1 / include/sbc.h)
+    int Np, level_begin, level_end, steps_each;
+    const float* P;
+    const float* Y;
+    float* X;
+    const float* Hor;
+    const float* noise_var;
+    const float* alpha_step;
+    const float* beta;
+    double sigma_end;
+    float* nmse_log;
+    unsigned long long seed;
+    const unsigned long long* sample_ids;
+    const float* ext_noise;
+    const float* dc_boost;
+    const int* stop_step;
+    long long* prof;              // optional [n_ops + 2] clock64 stamps of CTA 0, first group, second step
+    int* status;                  // optional: device-side error flag (mbarrier timeout)
+};
+
+namespace sbc2k {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a CUDA error (trap), never as a hung GPU.  try_wait suspends the
+// thread in hardware for a bounded time per call, so the limit below is tens of seconds.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100).  Core matrix = 8 rows x 16 bytes
+// (128 contiguous bytes); SBO = byte distance between 8-row groups (M / N direction), LBO = between the two
+// 16-byte K halves of a K = 16 (fp16) slice.  Validated on hardware by tools/tcgen05_probe.cu.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ELU (layers.py:13): expm1 by an 8-term Horner polynomial for small |v| (no cancellation), MUFU.EX2 otherwise
+__device__ __forceinline__ float elu(float v) {
+    float p = 2.4801587e-5f;            // 1/8!
+    p = fmaf(p, v, 1.9841270e-4f);
+    p = fmaf(p, v, 1.3888889e-3f);
+    p = fmaf(p, v, 8.3333333e-3f);
+    p = fmaf(p, v, 4.1666667e-2f);
+    p = fmaf(p, v, 1.6666667e-1f);
+    p = fmaf(p, v, 0.5f);
+    p = fmaf(p, v, 1.0f);
+    const float small = p * v, big = __expf(v) - 1.f;
+    return v > 0.f ? v : (v > -0.35f ? small : big);
+}
+
+struct alignas(16) H8 { __half2 a, b, c, d; };
+// v[0..7] -> fp16 hi / lo pair (hi = rn(v), lo = rn(v - hi)); |v| is clamped below the fp16 overflow threshold
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float x0 = fminf(fmaxf(v[2 * i], -65000.f), 65000.f), x1 = fminf(fmaxf(v[2 * i + 1], -65000.f), 65000.f);
+        const __half2 hh = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void store_sp16(uint8_t* base, int slot, int oct, int q, const float (&v)[8]) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* p = base + (size_t)(2 * oct) * slot + (size_t)q * 16;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + slot) = lo;
+}
+__device__ __forceinline__ void load_f32x8(const uint8_t* base, int slot, int oct, int q, float (&v)[8]) {
+    const uint8_t* p = base + (size_t)(2 * oct) * slot + (size_t)q * 16;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + slot);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store_f32x8(uint8_t* base, int slot, int oct, int q, const float (&v)[8]) {
+    uint8_t* p = base + (size_t)(2 * oct) * slot + (size_t)q * 16;
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + slot) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// (sample, y, x) decomposition of a flat interior-pixel index; shifts when the sizes are powers of two
+struct Dec {
+    int w, hw, lw, lhw;
+    __device__ __forceinline__ Dec(const sbc2::Geo& G) : w(G.w), hw(G.hw) {
+        lw = (w & (w - 1)) ? -1 : (31 - __clz(w));
+        lhw = (hw & (hw - 1)) ? -1 : (31 - __clz(hw));
+    }
+    __device__ __forceinline__ void yx(int e, int& y, int& x) const {
+        y = lw >= 0 ? (e >> lw) : (e / w);
+        x = e - y * w;
+    }
+    __device__ __forceinline__ void sex(int i, int& s, int& e) const {
+        s = lhw >= 0 ? (i >> lhw) : (i / hw);
+        e = i - s * hw;
+    }
+};
+__device__ __forceinline__ int qof(const sbc2::Geo& G, int s, int y, int x) { return G.lead + s * G.pps + y * G.wp + x; }
+
+// sum over the warp of 8 per-lane values; every lane gets all 8 totals
+__device__ __forceinline__ void warp_sum8(float (&v)[8]) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// non-conv ops: all 192 threads, items = (sample, channel octet, pixel), pixel fastest (coalesced 16-byte accesses)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void op_affine(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = L.geo[0];
+    const Dec D(G);
+    const float2* xin = reinterpret_cast<const float2*>(arena + op.src0);
+    const int n = L.S * G.hw;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        int s, e, y, x;
+        D.sex(i, s, e);
+        D.yx(e, y, x);
+        const float2 c = xin[i];
+        float v[8] = {2.f * c.x - 1.f, 2.f * c.y - 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // ncsnv2.py:270-271
+        store_sp16(arena + op.raw16, G.slot, 0, qof(G, s, y, x), v);
+    }
+}
+
+__device__ __forceinline__ void op_elu(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = L.geo[op.gs];
+    const Dec D(G);
+    const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const int oct = i / per, r = i - oct * per;
+        int s, e, y, x;
+        D.sex(r, s, e);
+        D.yx(e, y, x);
+        const int q = qof(G, s, y, x);
+        float v[8];
+        load_f32x8(arena + op.src0, G.slot, oct, q, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
+        store_sp16(arena + op.elu16, G.slot, oct, q, v);
+    }
+}
+
+// MaxPool2d(5, 1, 2) with -inf padding (layers.py:70): F32 in, SP16 out
+__device__ __forceinline__ void op_maxpool5(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = L.geo[op.gs];
+    const Dec D(G);
+    const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const int oct = i / per, r = i - oct * per;
+        int s, e, y, x;
+        D.sex(r, s, e);
+        D.yx(e, y, x);
+        const int y0 = max(y - 2, 0), y1 = min(y + 2, G.h - 1), x0 = max(x - 2, 0), x1 = min(x + 2, G.w - 1);
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[k] = -INFINITY;
+        for (int yy = y0; yy <= y1; yy++)
+            for (int xx = x0; xx <= x1; xx++) {
+                float v[8];
+                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, yy, xx), v);
+#pragma unroll
+                for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
+            }
+        store_sp16(arena + op.raw16, G.slot, oct, qof(G, s, y, x), m);
+    }
+}
+
+// acc += bilinear(src, align_corners=True) (layers.py:182-183); optional elu32 = ELU(acc)
+__device__ __forceinline__ void op_upacc(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
+    const sbc2::Geo& GS = L.geo[op.gs];
+    const sbc2::Geo& GD = L.geo[op.gd];
+    const Dec D(GD);
+    const int H = GS.h, W = GS.w, OH = GD.h, OW = GD.w;
+    const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+    const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const int oct = i / per, r = i - oct * per;
+        int s, e, y, x;
+        D.sex(r, s, e);
+        D.yx(e, y, x);
+        const float fy = sy * (float)y, fx = sx * (float)x;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        float p00[8], p01[8], p10[8], p11[8], a[8];
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y0, x0), p00);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y0, x1), p01);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y1, x0), p10);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y1, x1), p11);
+        const int q = qof(GD, s, y, x);
+        load_f32x8(arena + op.acc32, GD.slot, oct, q, a);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] += hy * (hx * p00[k] + lx * p01[k]) + ly * (hx * p10[k] + lx * p11[k]);
+        store_f32x8(arena + op.acc32, GD.slot, oct, q, a);
+        if (op.elu32 >= 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = elu(a[k]);
+            store_f32x8(arena + op.elu32, GD.slot, oct, q, a);
+        }
+    }
+}
+
+// 2x2 mean-pool of ConvMeanPool (layers.py:309-313): F32 level g -> F32 level g+1 (+ optional raw SP16)
+__device__ __forceinline__ void op_pool2(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
+    const sbc2::Geo& GS = L.geo[op.gs];
+    const sbc2::Geo& GD = L.geo[op.gd];
+    const Dec D(GD);
+    const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const int oct = i / per, r = i - oct * per;
+        int s, e, y, x;
+        D.sex(r, s, e);
+        D.yx(e, y, x);
+        float a[8], b[8], c[8], d[8], v[8];
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y, 2 * x), a);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y + 1, 2 * x), b);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y, 2 * x + 1), c);
+        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y + 1, 2 * x + 1), d);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (a[k] + b[k] + c[k] + d[k]) * 0.25f;   // same order as layers.py:311-312
+        const int q = qof(GD, s, y, x);
+        store_f32x8(arena + op.dst32, GD.slot, oct, q, v);
+        if (op.raw16 >= 0) store_sp16(arena + op.raw16, GD.slot, oct, q, v);
+    }
+}
+
+// InstanceNorm2dPlus + ELU (normalization.py:163-176): F32 in, SP16 out.  Work unit = (sample, octet, pixel chunk),
+// one warp per unit; two-pass statistics, partial sums exchanged through shared memory.
+__device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, float* spart, int tid) {
+    const sbc2::Geo& G = L.geo[op.gs];
+    const Dec D(G);
+    const int C = op.cin, noct = C >> 3, S = L.S, hw = G.hw;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = SBC2_NTHR / 32;
+    const float* wseg = reinterpret_cast<const float*>(L.blob + op.w_off);
+    float* stats = reinterpret_cast<float*>(arena + op.scratch);       // [S][C][2] = (mean, M2)
+    float* coef = stats + (size_t)S * C * 2;                            // [S][C][2] = (scale, shift)
+    const int n_items = S * noct;
+    int nchunk = 1;
+    while (nchunk * 2 * n_items <= NW && nchunk * 2 * 32 <= hw) nchunk *= 2;
+    const int lchunk = 31 - __clz(nchunk);
+    const int batch_items = min(n_items, 64 >> lchunk);
+    const float inv_hw = 1.f / (float)hw;
+    float* part1 = spart;                 // [64 units][8]
+    float* part2 = spart + 512;
+    for (int it0 = 0; it0 < n_items; it0 += batch_items) {
+        const int nit = min(batch_items, n_items - it0), nunits = nit << lchunk;
+        // pass 1: sums
+        for (int u = warp; u < nunits; u += NW) {
+            const int item = it0 + (u >> lchunk), ch = u & (nchunk - 1);
+            const int s = item / noct, oct = item - s * noct;
+            const int e0 = (hw * ch) >> lchunk, e1 = (hw * (ch + 1)) >> lchunk;
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int e = e0 + lane; e < e1; e += 32) {
+                int y, x;
+                D.yx(e, y, x);
+                float v[8];
+                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, y, x), v);
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k] += v[k];
+            }
+            warp_sum8(a);
+            if (lane < 8) part1[u * 8 + lane] = a[lane];
+        }
+        __syncthreads();
+        // pass 2: centred sums of squares
+        for (int u = warp; u < nunits; u += NW) {
+            const int item = it0 + (u >> lchunk), ch = u & (nchunk - 1);
+            const int s = item / noct, oct = item - s * noct;
+            const int e0 = (hw * ch) >> lchunk, e1 = (hw * (ch + 1)) >> lchunk;
+            float mean[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float t = 0.f;
+                for (int c2 = 0; c2 < nchunk; c2++) t += part1[(((u >> lchunk) << lchunk) + c2) * 8 + k];
+                mean[k] = t * inv_hw;
+            }
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int e = e0 + lane; e < e1; e += 32) {
+                int y, x;
+                D.yx(e, y, x);
+                float v[8];
+                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, y, x), v);
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const float d = v[k] - mean[k]; a[k] = fmaf(d, d, a[k]); }
+            }
+            warp_sum8(a);
+            if (lane < 8) part2[u * 8 + lane] = a[lane];
+        }
+        __syncthreads();
+        // per (item, channel): stats[s][c] = (mean, M2)
+        for (int i = tid; i < nit * 8; i += SBC2_NTHR) {
+            const int li = i >> 3, k = i & 7, item = it0 + li;
+            const int s = item / noct, oct = item - s * noct;
+            float t1 = 0.f, t2 = 0.f;
+            for (int c2 = 0; c2 < nchunk; c2++) { t1 += part1[((li << lchunk) + c2) * 8 + k]; t2 += part2[((li << lchunk) + c2) * 8 + k]; }
+            stats[(s * C + oct * 8 + k) * 2] = t1 * inv_hw;
+            stats[(s * C + oct * 8 + k) * 2 + 1] = t2;
+        }
+        __syncthreads();
+    }
+    // cross-channel statistics of the per-channel means (torch.mean / unbiased torch.var over C) and the affine:
+    // out = ELU(x * cs + csh)
+    for (int j = tid; j < S * C; j += SBC2_NTHR) {
+        const int s = j / C, c = j - s * C;
+        float m = 0.f;
+        for (int k = 0; k < C; k++) m += stats[(s * C + k) * 2];
+        m /= (float)C;
+        float v = 0.f;
+        for (int k = 0; k < C; k++) { const float d = stats[(s * C + k) * 2] - m; v = fmaf(d, d, v); }
+        v /= (float)(C - 1);
+        const float mean = stats[j * 2], m2 = stats[j * 2 + 1];
+        const float al = wseg[c], ga = wseg[C + c], be = wseg[2 * C + c];
+        const float cs = ga * rsqrtf(m2 * inv_hw + 1e-5f);
+        const float csh = fmaf(ga, (mean - m) * rsqrtf(v + 1e-5f) * al, be);
+        coef[j * 2] = cs;
+        coef[j * 2 + 1] = fmaf(-mean, cs, csh);
+    }
+    __syncthreads();
+    const int per = S * hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const int oct = i / per, r = i - oct * per;
+        int s, e, y, x;
+        D.sex(r, s, e);
+        D.yx(e, y, x);
+        const int q = qof(G, s, y, x);
+        float v[8];
+        load_f32x8(arena + op.src0, G.slot, oct, q, v);
+        const float4* cf = reinterpret_cast<const float4*>(coef + (s * C + oct * 8) * 2);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) {
+            const float4 c4 = cf[k2];
+            v[2 * k2] = elu(fmaf(v[2 * k2], c4.x, c4.y));
+            v[2 * k2 + 1] = elu(fmaf(v[2 * k2 + 1], c4.z, c4.w));
+        }
+        store_sp16(arena + op.elu16, G.slot, oct, q, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv op (warp-specialised; see the header comment)
+// ---------------------------------------------------------------------------------------------------------
+struct Pipe {
+    uint32_t sfull_k, sempty_k;     // next parity per staging barrier (bit b)
+    uint32_t acc_n;                 // accumulator slots handed out so far (all roles count alike)
+    uint32_t conv_n;                // convs executed so far (weight buffer = conv_n & 1)
+};
+
+__device__ __forceinline__ void op_conv(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, uint8_t* smem,
+                                        uint64_t* bars, uint32_t tmem, Pipe& P, int tid, bool prefetch_next) {
+    uint64_t* sfull = bars;            // [4]
+    uint64_t* sempty = bars + 4;       // [4]
+    uint64_t* tfull = bars + 8;        // [4]
+    uint64_t* tempty = bars + 12;      // [4]
+    uint64_t* wfull = bars + 16;       // [2]
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t wslot = P.conv_n & 1u, wpar = (P.conv_n >> 1) & 1u;
+    uint8_t* wb = smem + (size_t)wslot * L.wmax;
+    uint8_t* stage = smem + 2 * (size_t)L.wmax;
+    const sbc2::Geo& G = L.geo[op.gs];
+    const int T = op.T, ns = op.nstage, nsub = op.nsub0 + op.nsub1;
+    const uint32_t stage_bytes = (uint32_t)nsub * (uint32_t)op.sps;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            if (prefetch_next) {   // the other buffer held the previous conv's segment: that conv is complete
+                uint64_t* wn = &wfull[wslot ^ 1u];
+                mbar_expect_tx(wn, (uint32_t)op.nw_len);
+                bulk_g2s(smem + (size_t)(wslot ^ 1u) * L.wmax, L.blob + op.nw_off, (uint32_t)op.nw_len, wn);
+            }
+            for (int t = 0; t < T; t++) {
+                const int b = t & (ns - 1);
+                mbar_wait(&sempty[b], (P.sempty_k >> b) & 1u);
+                P.sempty_k ^= 1u << b;
+                mbar_expect_tx(&sfull[b], stage_bytes);
+                uint8_t* sb = stage + (size_t)b * stage_bytes;
+                const size_t goff = (size_t)(G.lead + t * sbc2::TILE_M - op.halo) * 16;
+                const uint8_t* g0 = arena + op.src0 + goff;
+                for (int j = 0; j < op.nsub0; j++) bulk_g2s(sb + (size_t)j * op.sps, g0 + (size_t)j * G.slot, (uint32_t)op.sps, &sfull[b]);
+                if (op.nsub1 > 0) {
+                    const uint8_t* g1 = arena + op.src1 + goff;
+                    for (int j = 0; j < op.nsub1; j++)
+                        bulk_g2s(sb + (size_t)(op.nsub0 + j) * op.sps, g1 + (size_t)j * G.slot, (uint32_t)op.sps, &sfull[b]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            mbar_wait(&wfull[wslot], wpar);
+            const uint4* list = reinterpret_cast<const uint4*>(wb + op.mma_rel);
+            const uint32_t wb_s = smem_u32(wb), nlbo = (uint32_t)op.N * 16u;
+            for (int t = 0; t < T; t++) {
+                const int b = t & (ns - 1);
+                const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
+                mbar_wait(&sfull[b], (P.sfull_k >> b) & 1u);
+                P.sfull_k ^= 1u << b;
+                mbar_wait(&tempty[a], ((n / SBC2_NACC) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t sb_s = smem_u32(stage + (size_t)b * stage_bytes);
+                const uint32_t td = tmem + a * 64u;
+                for (int i = 0; i < op.n_mma; i++) {
+                    const uint4 e = list[i];
+                    umma_f16(td, make_desc(sb_s + e.x, e.y, 128u), make_desc(wb_s + e.z, nlbo, 128u), (uint32_t)op.idesc, i > 0 ? 1u : 0u);
+                }
+                umma_commit(&sempty[b]);     // the stage may be refilled once these MMAs have read it
+                umma_commit(&tfull[a]);      // accumulator complete
+            }
+        }
+    } else {
+        // ---------------- epilogue: warp w owns TMEM lanes 32w .. 32w+31 = pixels m0 + 32w + lane ----------------
+        mbar_wait(&wfull[wslot], wpar);
+        const float* bias = op.bias_rel >= 0 ? reinterpret_cast<const float*>(wb + op.bias_rel) : nullptr;
+        const int32_t* pix = L.pix[op.gd];
+        const int slot = G.slot, nchunk = op.cout8 >> 3;
+        const float us = op.unscale;
+        for (int t = 0; t < T; t++) {
+            const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
+            const int q = G.lead + t * sbc2::TILE_M + warp * 32 + lane;
+            const int px = pix[q];
+            mbar_wait(&tfull[a], (n / SBC2_NACC) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem + a * 64u + ((uint32_t)(warp * 32) << 16);
+            for (int c = 0; c < nchunk; c++) {
+                float hi[8], lo[8], v[8];
+                tmem_ld8(taddr + (uint32_t)(c * 8), hi);
+                tmem_ld8(taddr + (uint32_t)(op.cout8 + c * 8), lo);
+                tmem_ld_wait();
+                if (c == nchunk - 1) {     // every column of this slot is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[a]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    v[k] = (hi[k] + lo[k]) * us;
+                    if (bias) v[k] += bias[c * 8 + k];
+                }
+                if (op.flags & sbc2::F_COMPACT) {     // network output: couts (0,1) = (re, im) of element px
+                    if (px >= 0) reinterpret_cast<float2*>(arena + op.dst32)[px] = make_float2(v[0], v[1]);
+                    continue;
+                }
+                if (px < 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = 0.f;      // pads of every output stay zero
+                }
+                if (op.dst32 >= 0) store_f32x8(arena + op.dst32, slot, c, q, v);     // the raw conv result
+                if (op.acc32 >= 0) {
+                    if (px >= 0) {
+                        float o[8];
+                        load_f32x8(arena + op.acc32, slot, c, q, o);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) v[k] += o[k];
+                    }
+                    store_f32x8(arena + op.acc32, slot, c, q, v);
+                }
+                if (op.raw16 >= 0) store_sp16(arena + op.raw16, slot, c, q, v);
+                if (op.elu16 >= 0 || op.elu32 >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
+                    if (op.elu16 >= 0) store_sp16(arena + op.elu16, slot, c, q, v);
+                    if (op.elu32 >= 0) store_f32x8(arena + op.elu32, slot, c, q, v);
+                }
+            }
+        }
+    }
+    P.acc_n += (uint32_t)T;
+    P.conv_n++;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();                      // protects `red` against the previous use
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < SBC2_NTHR / 32; i++) s += red[i];
+    return s;
+}
+
+}  // namespace sbc2k
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_constant__ Sbc2Launch L) {
+    using namespace sbc2k;
+    extern __shared__ __align__(128) uint8_t sbc2_smem[];
+    uint8_t* smem = sbc2_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)L.wmax + (size_t)L.stage_bytes);
+    float* spart = reinterpret_cast<float*>(bars + SBC2_NBARS);
+    __shared__ uint32_t s_tmem;
+    __shared__ SbcStepScalars s_sc[SBC2_MAXS];
+    __shared__ float s_hnorm[SBC2_MAXS];
+    __shared__ float s_red[SBC2_NTHR / 32];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int S = L.S;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; i++) { mbar_init(&bars[i], 1); mbar_init(&bars[4 + i], 1); mbar_init(&bars[8 + i], 1); mbar_init(&bars[12 + i], 4); }
+        mbar_init(&bars[16], 1);
+        mbar_init(&bars[17], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(SBC2_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    uint8_t* arena = L.gws + (size_t)blockIdx.x * (size_t)L.arena_bytes;
+    {   // the arena starts out all zero: SP16 pads and guards are never written with anything else
+        uint4* a4 = reinterpret_cast<uint4*>(arena);
+        const size_t n16 = (size_t)L.arena_bytes / 16;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (size_t i = tid; i < n16; i += SBC2_NTHR) a4[i] = z;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    Pipe P;
+    P.sfull_k = 0u; P.sempty_k = 0xFu; P.acc_n = 0u; P.conv_n = 0u;
+    bool w_pending = false;   // a parameter-segment prefetch is in flight (or landed) for conv number P.conv_n
+    const int n_groups = (L.B + S - 1) / S;
+    const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
+    const int nsteps = (L.mode == 1) ? (L.level_end - L.level_begin) * L.steps_each : 1;
+    int last_conv = -1;
+    for (int i = 0; i < L.n_ops; i++)
+        if (L.ops[i].kind == sbc2::K_CONV) last_conv = i;
+
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const bool last_group = (g + (int)gridDim.x >= n_groups);
+        const int b0 = g * S;
+        // ---------------- load the group's state ----------------
+        for (int s = 0; s < S; s++) {
+            const int b = b0 + s;
+            float2* ax = reinterpret_cast<float2*>(arena + L.x_off) + (size_t)s * ne;
+            if (b >= L.B) {
+                for (int e = tid; e < ne; e += SBC2_NTHR) ax[e] = make_float2(0.f, 0.f);
+                continue;
+            }
+            if (L.mode == 1) {
+                const float2* X = reinterpret_cast<const float2*>(L.X) + (size_t)b * ne;
+                for (int e = tid; e < ne; e += SBC2_NTHR) ax[e] = X[e];
+                if (L.Hor) {   // ||H||_F^2 once per sample (test_score.py:169)
+                    const float2* Hc = reinterpret_cast<const float2*>(L.Hor) + (size_t)b * ne;
+                    float part = 0.f;
+                    for (int e = tid; e < ne; e += SBC2_NTHR) { const float2 v = Hc[e]; part += v.x * v.x + v.y * v.y; }
+                    const float tot = block_sum(part, s_red, tid);
+                    if (tid == 0) s_hnorm[s] = tot;
+                }
+            } else {
+                const float* fx = L.fx + (size_t)b * L.fxs[0];
+                for (int e = tid; e < ne; e += SBC2_NTHR) {
+                    const int t = e / Nr, r = e - t * Nr;
+                    const float* qp = fx + t * L.fxs[2] + r * L.fxs[3];
+                    ax[e] = make_float2(qp[0], qp[L.fxs[1]]);
+                }
+            }
+        }
+        // steps this group runs = the longest of its samples (early stop, test_mmse.py:260-263)
+        int nsteps_g = nsteps;
+        if (L.mode == 1 && L.stop_step) {
+            int mx = 1;
+            for (int s = 0; s < S && b0 + s < L.B; s++) {
+                const int st = L.stop_step[b0 + s] + 1;
+                mx = max(mx, min(max(st, 1), nsteps));
+            }
+            nsteps_g = mx;
+        }
+        __syncthreads();
+
+        for (int gs = 0; gs < nsteps_g; gs++) {
+            const bool last_step = (gs + 1 == nsteps_g);
+            int lvl = 0;
+            if (L.mode == 1) {
+                lvl = L.level_begin + gs / L.steps_each;
+                if (tid < S && b0 + tid < L.B && (gs % L.steps_each) == 0) {   // per-level scalars, in double like the reference
+                    const int b = b0 + tid;
+                    const double sigma = (double)L.sigmas[lvl];
+                    const double ratio = sigma / L.sigma_end;
+                    const double alpha = (double)L.alpha_step[b] * ratio * ratio;
+                    s_sc[tid].sigma = L.sigmas[lvl];
+                    s_sc[tid].alpha = (float)alpha;
+                    s_sc[tid].den = (float)((double)L.noise_var[b] / 2. + sigma * sigma) / (L.dc_boost ? L.dc_boost[b] : 1.f);
+                    s_sc[tid].nscale = (float)sqrt(2. * alpha * (double)L.beta[b]);
+                }
+            }
+            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && g == 0 && gs == (nsteps > 1 ? 1 : 0) && tid == 0;
+
+            // ---------------- the network ----------------
+            for (int i = 0; i < L.n_ops; i++) {
+                if (do_prof) L.prof[i] = clock64();
+                const sbc2::Op op = L.ops[i];
+                if (op.kind == sbc2::K_CONV) {
+                    if (!w_pending) {      // very first conv of the launch: nobody prefetched its segment
+                        if (tid == 4 * 32) {
+                            mbar_expect_tx(&bars[16 + (P.conv_n & 1u)], (uint32_t)op.w_len);
+                            bulk_g2s(smem + (size_t)(P.conv_n & 1u) * L.wmax, L.blob + op.w_off, (uint32_t)op.w_len, &bars[16 + (P.conv_n & 1u)]);
+                        }
+                    }
+                    // the last conv of the launch must not leave a copy in flight
+                    const bool pf = !(i == last_conv && last_step && last_group);
+                    op_conv(op, L, arena, smem, bars, tmem, P, tid, pf);
+                    w_pending = pf;
+                } else if (op.kind == sbc2::K_NORM_ELU) {
+                    op_norm_elu(op, L, arena, spart, tid);
+                } else if (op.kind == sbc2::K_MAXPOOL5) {
+                    op_maxpool5(op, L, arena, tid);
+                } else if (op.kind == sbc2::K_ELU) {
+                    op_elu(op, L, arena, tid);
+                } else if (op.kind == sbc2::K_UPACC) {
+                    op_upacc(op, L, arena, tid);
+                } else if (op.kind == sbc2::K_POOL2) {
+                    op_pool2(op, L, arena, tid);
+                } else if (op.kind == sbc2::K_AFFINE) {
+                    op_affine(op, L, arena, tid);
+                }
+                fence_proxy_async();      // generic-proxy stores -> visible to the next op's bulk copies
+                __syncthreads();
+            }
+            if (do_prof) L.prof[L.n_ops] = clock64();
+
+            // ---------------- after the network ----------------
+            if (L.mode == 0) {
+                for (int s = 0; s < S && b0 + s < L.B; s++) {   // score = net / sigmas[y]   (ncsnv2.py:295-298)
+                    const int b = b0 + s;
+                    long long lab = L.labels ? L.labels[b] : 0;
+                    if (lab < 0) lab = 0;
+                    if (lab >= L.n_sigmas) lab = L.n_sigmas - 1;
+                    const float sg = L.sigmas[lab];
+                    const float2* net = reinterpret_cast<const float2*>(arena + L.out_off) + (size_t)s * ne;
+                    float* o = L.fout + (size_t)b * L.channels * ne;
+                    for (int e = tid; e < ne; e += SBC2_NTHR) {
+                        const float2 v = net[e];
+                        o[e] = v.x / sg;
+                        o[ne + e] = v.y / sg;
+                    }
+                }
+            } else {
+                // data-consistency residual P x - y for every sample, then gradient + Langevin update + NMSE
+                for (int s = 0; s < S && b0 + s < L.B; s++) {
+                    const int b = b0 + s;
+                    const float* ax = reinterpret_cast<const float*>(arena + L.x_off) + (size_t)s * ne * 2;
+                    float* res = reinterpret_cast<float*>(arena + L.post_off) + (size_t)s * ne * 2;
+                    sbc_dc_residual(ax, res, L.P + (size_t)b * L.Np * Nt * 2, L.Y + (size_t)b * L.Np * Nr * 2, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                }
+                __syncthreads();
+                for (int s = 0; s < S && b0 + s < L.B; s++) {
+                    const int b = b0 + s;
+                    int st_last = nsteps - 1;
+                    if (L.stop_step) { const int st = L.stop_step[b]; st_last = min(max(st, 0), nsteps - 1); }
+                    if (gs > st_last) continue;                        // this sample stopped early
+                    float* ax = reinterpret_cast<float*>(arena + L.x_off) + (size_t)s * ne * 2;
+                    const float* net = reinterpret_cast<const float*>(arena + L.out_off) + (size_t)s * ne * 2;
+                    const float* res = reinterpret_cast<const float*>(arena + L.post_off) + (size_t)s * ne * 2;
+                    const float* Pm = L.P + (size_t)b * L.Np * Nt * 2;
+                    const float* Hc = L.Hor ? L.Hor + (size_t)b * ne * 2 : nullptr;
+                    const float* en = L.ext_noise ? L.ext_noise + ((size_t)gs * L.B + b) * ne * 2 : nullptr;
+                    const unsigned long long sid = L.sample_ids ? L.sample_ids[b] : (unsigned long long)b;
+                    const uint32_t gstep = (uint32_t)(lvl * L.steps_each + gs % L.steps_each);
+                    const float part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                    if (L.nmse_log && Hc) {
+                        const float tot = block_sum(part, s_red, tid);
+                        if (tid == 0) L.nmse_log[(size_t)gs * L.B + b] = tot / s_hnorm[s];
+                    }
+                }
+            }
+            __syncthreads();
+            if (do_prof) L.prof[L.n_ops + 1] = clock64();
+        }
+
+        if (L.mode == 1) {   // write the final estimates back (interleaved complex64)
+            for (int s = 0; s < S && b0 + s < L.B; s++) {
+                float2* X = reinterpret_cast<float2*>(L.X) + (size_t)(b0 + s) * ne;
+                const float2* ax = reinterpret_cast<const float2*>(arena + L.x_off) + (size_t)s * ne;
+                for (int e = tid; e < ne; e += SBC2_NTHR) X[e] = ax[e];
+            }
+        }
+        __syncthreads();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SBC2_TMEM_COLS));
+}

@@ -10,6 +10,7 @@
 
 #include "../../include/sbc.h"
 #include "sbc_kernel.cuh"
+#include "sbc2_host.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -28,6 +29,8 @@ static int sbc_fail(int code, const char* fmt, ...) {
     } while (0)
 
 struct SbcModel {
+    int engine = 1;                // 1: fused shared-memory arena, mma.sync (sbc_kernel.cuh); 2: tcgen05 (sbc2_kernel.cuh)
+    Sbc2Model* e2 = nullptr;
     int device = 0;
     int num_sms = 0;
     int smem_optin = 0;
@@ -48,6 +51,7 @@ struct SbcModel {
     int halo_off[SBC_MAX_GEO] = {0};
     ~SbcModel() {   // owns its device buffers: every early return of sbc_model_create releases them
         cudaFree(d_ops); cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
+        delete e2;
     }
 };
 
@@ -187,7 +191,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
 extern "C" int sbc_model_free(void* handle) {
     if (!handle) return SBC_OK;
     SbcModel* m = (SbcModel*)handle;
-    cudaSetDevice(m->device);
+    cudaSetDevice(m->engine == 2 ? m->e2->device : m->device);
     delete m;
     return SBC_OK;
 }
@@ -195,6 +199,17 @@ extern "C" int sbc_model_free(void* handle) {
 extern "C" int sbc_query(void* handle, sbc_info* out) {
     if (!handle || !out) return sbc_fail(SBC_E_ARG, "sbc_query: null argument");
     SbcModel* m = (SbcModel*)handle;
+    if (m->engine == 2) {
+        const Sbc2Model* e = m->e2;
+        memset(out, 0, sizeof *out);
+        out->version = SBC_VERSION; out->device = e->device; out->num_sms = e->num_sms; out->threads_per_cta = SBC2_NTHR;
+        out->arena_in_smem = 0; out->weights_staged = 1; out->smem_bytes_per_cta = (int64_t)e->smem_bytes;
+        out->arena_bytes = e->last_grid > 0 ? (int64_t)(e->gws_bytes / (size_t)e->last_grid) : 0;
+        out->conv_flops_per_forward = e->builder->conv_flops; out->kernel_launches = e->launches;
+        out->engine = 2; out->ctas_per_sm = e->ctas_per_sm; out->group_size = e->last_S; out->n_ops = e->builder->n_ops();
+        return SBC_OK;
+    }
+    out->engine = 1; out->ctas_per_sm = 1; out->group_size = 1; out->n_ops = m->d.n_ops;
     out->version = SBC_VERSION;
     out->device = m->device;
     out->num_sms = m->num_sms;
@@ -248,6 +263,17 @@ extern "C" int sbc_forward(void* handle, const float* x, const int64_t x_strides
     if (B < 0) return sbc_fail(SBC_E_ARG, "sbc_forward: negative batch");
     if (B == 0) return SBC_OK;
     SbcModel* m = (SbcModel*)handle;
+    if (m->engine == 2) {
+        SBC_CUDA(cudaSetDevice(m->e2->device));
+        Sbc2Launch L2;
+        int grid = 0;
+        const std::string err = sbc2_prepare(m->e2, B, sbc2_pick_S(m->e2, B), true, L2, grid);
+        if (!err.empty()) return sbc_fail(SBC_E_CUDA, "sbc_forward: %s", err.c_str());
+        L2.mode = 0; L2.fx = x; L2.labels = (const long long*)labels; L2.fout = out;
+        for (int i = 0; i < 4; i++) L2.fxs[i] = x_strides[i];
+        SBC_CUDA(sbc2_launch(m->e2, L2, grid, (cudaStream_t)stream));
+        return SBC_OK;
+    }
     SbcLaunch L;
     fill_common(m, L);
     L.mode = 0; L.B = B; L.fx = x; L.labels = (const long long*)labels; L.fout = out;
@@ -258,12 +284,13 @@ extern "C" int sbc_forward(void* handle, const float* x, const int64_t x_strides
 static int check_ald(const SbcModel* m, const sbc_ald_args* a) {
     if (!a) return sbc_fail(SBC_E_ARG, "sbc_ald_run: null args");
     if (a->B < 0) return sbc_fail(SBC_E_ARG, "sbc_ald_run: negative batch");
-    if (a->Nt != m->d.Nt || a->Nr != m->d.Nr)
-        return sbc_fail(SBC_E_ARG, "sbc_ald_run: model packed for %dx%d, got Nt=%d Nr=%d", m->d.Nt, m->d.Nr, a->Nt, a->Nr);
+    const int mNt = m->engine == 2 ? m->e2->Nt : m->d.Nt, mNr = m->engine == 2 ? m->e2->Nr : m->d.Nr;
+    const int mns = m->engine == 2 ? m->e2->n_sigmas : m->d.n_sigmas;
+    if (a->Nt != mNt || a->Nr != mNr)
+        return sbc_fail(SBC_E_ARG, "sbc_ald_run: model packed for %dx%d, got Nt=%d Nr=%d", mNt, mNr, a->Nt, a->Nr);
     if (a->Np <= 0 || a->Np > a->Nt) return sbc_fail(SBC_E_ARG, "sbc_ald_run: need 0 < Np <= Nt (Np=%d)", a->Np);
-    if (a->level_begin < 0 || a->level_end > m->d.n_sigmas || a->level_begin > a->level_end)
-        return sbc_fail(SBC_E_ARG, "sbc_ald_run: level range [%d,%d) outside [0,%d]", a->level_begin, a->level_end,
-                        m->d.n_sigmas);
+    if (a->level_begin < 0 || a->level_end > mns || a->level_begin > a->level_end)
+        return sbc_fail(SBC_E_ARG, "sbc_ald_run: level range [%d,%d) outside [0,%d]", a->level_begin, a->level_end, mns);
     if (a->steps_each <= 0) return sbc_fail(SBC_E_ARG, "sbc_ald_run: steps_each must be positive");
     if (a->B > 0 && (!a->P || !a->Y || !a->X || !a->noise_var || !a->alpha_step || !a->beta))
         return sbc_fail(SBC_E_ARG, "sbc_ald_run: null array");
@@ -287,6 +314,21 @@ extern "C" int sbc_ald_run(void* handle, const sbc_ald_args* a, void* stream) {
     int rc = check_ald(m, a);
     if (rc) return rc;
     if (a->B == 0 || a->level_begin == a->level_end) return SBC_OK;
+    if (m->engine == 2) {
+        SBC_CUDA(cudaSetDevice(m->e2->device));
+        Sbc2Launch L2;
+        int grid = 0;
+        const std::string err = sbc2_prepare(m->e2, a->B, sbc2_pick_S(m->e2, a->B), true, L2, grid);
+        if (!err.empty()) return sbc_fail(SBC_E_CUDA, "sbc_ald_run: %s", err.c_str());
+        L2.mode = 1; L2.Np = a->Np;
+        L2.level_begin = a->level_begin; L2.level_end = a->level_end; L2.steps_each = a->steps_each;
+        L2.P = (const float*)a->P; L2.Y = (const float*)a->Y; L2.X = (float*)a->X; L2.Hor = (const float*)a->H_oracle;
+        L2.noise_var = a->noise_var; L2.alpha_step = a->alpha_step; L2.beta = a->beta; L2.sigma_end = a->sigma_end;
+        L2.nmse_log = a->nmse_log; L2.seed = a->seed; L2.sample_ids = (const unsigned long long*)a->sample_ids;
+        L2.ext_noise = (const float*)a->ext_noise; L2.dc_boost = a->dc_boost; L2.stop_step = a->stop_step;
+        SBC_CUDA(sbc2_launch(m->e2, L2, grid, (cudaStream_t)stream));
+        return SBC_OK;
+    }
     SbcLaunch L;
     fill_common(m, L);
     fill_ald(L, a);
@@ -304,6 +346,7 @@ extern "C" int sbc_forward_host(void* handle, const float* x, const int64_t* lab
     if (!handle || !x || !labels || !out) return sbc_fail(SBC_E_ARG, "sbc_forward_host: null argument");
     if (B <= 0) return B == 0 ? SBC_OK : sbc_fail(SBC_E_ARG, "sbc_forward_host: negative batch");
     SbcModel* m = (SbcModel*)handle;
+    if (m->engine == 2) { m->d.channels = m->e2->channels; m->d.Nt = m->e2->Nt; m->d.Nr = m->e2->Nr; m->device = m->e2->device; }
     SBC_CUDA(cudaSetDevice(m->device));
     const size_t n = (size_t)B * m->d.channels * m->d.Nt * m->d.Nr;
     DevBuf dx, dl, dout;
@@ -323,7 +366,7 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
     int rc = check_ald(m, a);
     if (rc) return rc;
     if (a->B == 0 || a->level_begin == a->level_end) return SBC_OK;
-    SBC_CUDA(cudaSetDevice(m->device));
+    SBC_CUDA(cudaSetDevice(m->engine == 2 ? m->e2->device : m->device));
     const size_t B = a->B, ne = (size_t)a->Nt * a->Nr, steps = (size_t)(a->level_end - a->level_begin) * a->steps_each;
     const size_t nP = B * a->Np * a->Nt * 8, nY = B * a->Np * a->Nr * 8, nX = B * ne * 8;
     DevBuf dP, dY, dX, dH, dnv, dal, dbe, dlog, dids, dn, ddb, dst;
@@ -379,12 +422,14 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
 extern "C" int sbc_set_profile_buffer(void* handle, int64_t* dev_stamps) {
     if (!handle) return sbc_fail(SBC_E_ARG, "sbc_set_profile_buffer: null handle");
     ((SbcModel*)handle)->d_prof = (long long*)dev_stamps;
+    if (((SbcModel*)handle)->engine == 2) ((SbcModel*)handle)->e2->d_prof = (long long*)dev_stamps;
     return SBC_OK;
 }
 
 extern "C" int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream) {
     if (!handle || !x || !arena_out) return sbc_fail(SBC_E_ARG, "sbc_debug_arena: null argument");
     SbcModel* m = (SbcModel*)handle;
+    if (m->engine == 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_arena: engine 2 models use sbc_debug_run");
     if (stop_op < 0 || stop_op > m->d.n_ops) return sbc_fail(SBC_E_ARG, "sbc_debug_arena: stop_op out of range");
     static const long long zero_label = 0;
     (void)zero_label;
@@ -395,4 +440,90 @@ extern "C" int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, fl
     L.fxs[2] = m->d.Nr; L.fxs[3] = 1;
     L.debug_stop = stop_op; L.debug_out = arena_out;
     return launch(m, L, (cudaStream_t)stream);
+}
+
+
+// ---- engine 2: self-contained model creation from a plain state dict + debug views ---------------------------
+extern "C" int sbc_model_create_from_state(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt,
+                                           int32_t Nr, int32_t channels, int device, void** handle_out) {
+    if (!entries || n_entries <= 0 || !handle_out) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state: null / empty argument");
+    int ndev = 0;
+    SBC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state: no CUDA device %d", device);
+    SBC_CUDA(cudaSetDevice(device));
+    sbc2::StateDict sd;
+    for (int i = 0; i < n_entries; i++) {
+        const sbc_state_entry& e = entries[i];
+        if (!e.name || !e.data || e.ndim < 0 || e.ndim > 8 || (e.ndim > 0 && !e.shape))
+            return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state: bad entry %d", i);
+        sbc2::TensorArg t;
+        t.data = e.data;
+        for (int k = 0; k < e.ndim; k++) t.shape.push_back(e.shape[k]);
+        sd[e.name] = t;
+    }
+    std::unique_ptr<SbcModel> mh(new SbcModel());
+    mh->engine = 2;
+    mh->e2 = new Sbc2Model();
+    mh->device = device;
+    const std::string err = sbc2_create(mh->e2, sd, ngf, Nt, Nr, channels, device);
+    if (!err.empty()) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state: %s", err.c_str());
+    *handle_out = mh.release();
+    return SBC_OK;
+}
+
+extern "C" int sbc_debug_plan(void* handle, int32_t S, int32_t reuse, sbc_tensor_info* out, int32_t cap, int32_t* n_out,
+                              int64_t* arena_bytes, int32_t* geo_out /* [4][12] */) {
+    if (!handle) return sbc_fail(SBC_E_ARG, "sbc_debug_plan: null handle");
+    SbcModel* m = (SbcModel*)handle;
+    if (m->engine != 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_plan: engine 2 only");
+    SBC_CUDA(cudaSetDevice(m->e2->device));
+    std::string err;
+    Sbc2PlanDev* pd = sbc2_plan(m->e2, S, reuse != 0, err);
+    if (!pd) return sbc_fail(SBC_E_CUDA, "sbc_debug_plan: %s", err.c_str());
+    static_assert(sizeof(sbc_tensor_info) == sizeof(sbc2::TensorInfo), "tensor info layout");
+    const int n = (int)pd->plan.tensors.size();
+    if (n_out) *n_out = n;
+    if (out) memcpy(out, pd->plan.tensors.data(), sizeof(sbc2::TensorInfo) * (size_t)(n < cap ? n : cap));
+    if (arena_bytes) *arena_bytes = pd->plan.arena_bytes;
+    if (geo_out) memcpy(geo_out, pd->plan.geo, sizeof(sbc2::Geo) * sbc2::MAX_LEVELS);
+    return SBC_OK;
+}
+
+extern "C" int sbc_debug_run(void* handle, const float* x, int32_t S, int32_t reuse, void* arena_out, void* stream) {
+    if (!handle || !x) return sbc_fail(SBC_E_ARG, "sbc_debug_run: null argument");
+    SbcModel* m = (SbcModel*)handle;
+    if (m->engine != 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_run: engine 2 only");
+    Sbc2Model* e = m->e2;
+    SBC_CUDA(cudaSetDevice(e->device));
+    Sbc2Launch L2;
+    int grid = 0;
+    const std::string err = sbc2_prepare(e, S, S, reuse != 0, L2, grid);     // one group of S samples
+    if (!err.empty()) return sbc_fail(SBC_E_CUDA, "sbc_debug_run: %s", err.c_str());
+    L2.mode = 0; L2.fx = x; L2.labels = nullptr; L2.fout = nullptr;
+    L2.fxs[0] = (long long)e->channels * e->Nt * e->Nr; L2.fxs[1] = (long long)e->Nt * e->Nr; L2.fxs[2] = e->Nr; L2.fxs[3] = 1;
+    float* scratch = nullptr;
+    SBC_CUDA(cudaMalloc(&scratch, sizeof(float) * (size_t)S * e->channels * e->Nt * e->Nr));
+    L2.fout = scratch;
+    cudaError_t ce = sbc2_launch(e, L2, grid, (cudaStream_t)stream);
+    if (ce == cudaSuccess && arena_out) ce = cudaMemcpyAsync(arena_out, e->d_gws, (size_t)L2.arena_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(scratch);
+    if (ce != cudaSuccess) return sbc_fail(SBC_E_CUDA, "sbc_debug_run: %s", cudaGetErrorString(ce));
+    return SBC_OK;
+}
+
+extern "C" const char* sbc_op_name(void* handle, int32_t i) {
+    if (!handle) return "";
+    SbcModel* m = (SbcModel*)handle;
+    if (m->engine != 2 || i < 0 || i >= m->e2->builder->n_ops()) return "";
+    return m->e2->builder->op_names()[(size_t)i].c_str();
+}
+
+extern "C" int sbc_op_kind(void* handle, int32_t i) {
+    if (!handle) return -1;
+    SbcModel* m = (SbcModel*)handle;
+    if (m->engine != 2 || i < 0 || i >= m->e2->builder->n_ops()) return -1;
+    std::string err;
+    Sbc2PlanDev* pd = sbc2_plan(m->e2, 1, true, err);
+    return pd ? pd->plan.ops[(size_t)i].kind : -1;
 }

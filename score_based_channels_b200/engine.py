@@ -9,12 +9,33 @@ import numpy as np
 from . import _lib, program
 
 
+ENGINE2_PRECISIONS = ("fp16x2",)      # tcgen05 engine: fp16 hi/lo split operands, fp32 accumulate (fp32-equivalent)
+ALL_PRECISIONS = ENGINE2_PRECISIONS + tuple(program.PRECISIONS)
+
+
 class PackedModel:
     """Owns one ``sbc_model_create`` handle for a (state_dict, ngf, Nt, Nr) on one CUDA device."""
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, Nt: int, Nr: int, device: int = 0,
                  channels: int = 2, precision: str = "tf32x3"):
         self.precision = precision
+        self.ngf, self.Nt, self.Nr, self.channels, self.device = ngf, Nt, Nr, channels, device
+        self.sigmas = np.ascontiguousarray(state["sigmas"], dtype=np.float32)
+        self.prog = None
+        if precision in ENGINE2_PRECISIONS:
+            # engine 2 (tcgen05): the library plans and packs from the plain state dict (sbc_model_create_from_state)
+            keep, ents = [], (_lib.StateEntry * len(state))()
+            for i, (k, v) in enumerate(state.items()):
+                a = np.ascontiguousarray(v, dtype=np.float32)
+                shp = np.asarray(a.shape if a.ndim else (1,), dtype=np.int64)
+                keep += [a, shp]
+                ents[i] = _lib.StateEntry(k.encode(), a.ctypes.data, shp.ctypes.data, len(shp))
+            h = C.c_void_p()
+            _lib.check(_lib.lib().sbc_model_create_from_state(ents, len(state), ngf, Nt, Nr, channels, device,
+                                                              C.byref(h)), "sbc_model_create_from_state")
+            self.handle = h
+            self.conv_flops = int(self.info().conv_flops_per_forward)
+            return
         nthreads = int(_lib.lib().sbc_threads_per_cta())
         self.prog = program.build_program(state, ngf, Nt, Nr, channels, nthreads=nthreads, precision=precision)
         self.sigmas = np.ascontiguousarray(state["sigmas"], dtype=np.float32)
@@ -29,11 +50,26 @@ class PackedModel:
         h = C.c_void_p()
         _lib.check(_lib.lib().sbc_model_create(C.byref(d), device, C.byref(h)), "sbc_model_create")
         self.handle = h
+        self.conv_flops = int(p.conv_flops)
 
     def info(self) -> _lib.Info:
         out = _lib.Info()
         _lib.check(_lib.lib().sbc_query(self.handle, C.byref(out)), "sbc_query")
         return out
+
+    # ---- engine-2 debug views (tests / tools) ----
+    def debug_plan(self, S: int, reuse: bool = True):
+        """(arena_bytes, [TensorInfo], geo[4][12]) of the engine-2 plan for group size S."""
+        n, ab = C.c_int32(), C.c_int64()
+        info = (_lib.TensorInfo * 2048)()
+        geo = np.zeros((4, 12), np.int32)
+        _lib.check(_lib.lib().sbc_debug_plan(self.handle, S, int(reuse), info, 2048, C.byref(n), C.byref(ab),
+                                             geo.ctypes.data), "sbc_debug_plan")
+        return int(ab.value), list(info)[:n.value], geo
+
+    def op_names(self):
+        L = _lib.lib()
+        return [L.sbc_op_name(self.handle, i).decode() for i in range(self.info().n_ops)]
 
     def close(self) -> None:
         if getattr(self, "handle", None):

@@ -38,7 +38,9 @@ def _cfg_get(node, key, default=None):
 class NCSNv2Deepest(nn.Module):
     """``precision`` selects the arithmetic of the 113 convolutions (everything else is fp32):
 
-    * ``"tf32x3"`` (default): tensor cores, 3xTF32 error-compensated products -- fp32-equivalent
+    * ``"fp16x2"``: engine 2 -- tcgen05 tensor cores with TMEM accumulators; every operand is an fp16 hi/lo pair
+      (22 significant bits), fp32 accumulate: fp32-equivalent results;
+    * ``"tf32x3"``: engine 1 -- mma.sync tensor cores, 3xTF32 error-compensated products -- fp32-equivalent
       results (the reference disables TF32, ``test_score.py:24-26``);
     * ``"tf32"``: tensor cores, plain TF32 operands (round to nearest), fp32 accumulate (fastest).
     The environment variable ``SBC_PRECISION`` overrides the default."""

@@ -101,7 +101,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     L.sbc_version.restype = C.c_int
-    assert L.sbc_version() == 101
+    assert L.sbc_version() == 200
     L.sbc_model_create.restype = C.c_int
     h = C.c_void_p()
     assert L.sbc_model_create(None, 0, C.byref(h)) == -1        # SBC_E_ARG, never a crash
