@@ -158,7 +158,7 @@ int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
 int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
 
 /* Engine-2 debug views.  sbc_debug_plan: tensor table (up to `cap` entries), arena size and the four level
- * geometries ([4][12] int32: h, w, hy, hx, wp, rps, pps, lead, npx, T, slot, hw) of the plan for group size S
+ * geometries ([4][14] int32: h, w, hy, hx, wp, rps, pps, lead, npx, T, slot, hw, 2 magic words) of the plan for group size S
  * (reuse = 0: every tensor gets its own region, so a whole forward can be inspected afterwards).
  * sbc_debug_run: one forward of S samples x (device fp32 [S,channels,Nt,Nr] contiguous) as ONE group, then the
  * group arena is copied to arena_out (device).  sbc_op_name / sbc_op_kind: the layer program. */

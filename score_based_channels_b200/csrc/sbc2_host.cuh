@@ -39,13 +39,18 @@ struct Sbc2Model {
     int wmax = 0, stage_bytes = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 2;
-    int last_S = 0, last_grid = 0;
+    int last_S = 0, last_grid = 0, last_reuse = 1;
     ~Sbc2Model() {
         cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
     }
 };
 
 static const int SBC2_STAGE_CAP = 32 * 1024;
+
+static int sbc2_env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
 
 // returns an error string ("" = ok)
 static std::string sbc2_create(Sbc2Model* m, const sbc2::StateDict& sd_in, int ngf, int Nt, int Nr, int channels, int device) {
@@ -67,8 +72,9 @@ static std::string sbc2_create(Sbc2Model* m, const sbc2::StateDict& sd_in, int n
     if (cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return "cudaDeviceGetAttribute failed";
     cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const sbc2::Builder& b = *m->builder;
+    if (b.max_stage > SBC2_STAGE_CAP) return "a conv input is too wide for the staging ring of engine 2 (" + std::to_string(b.max_stage) + " bytes per tile)";
     m->wmax = (b.max_seg + 127) / 128 * 128;
-    m->stage_bytes = (std::max(b.max_stage, 1024) + 127) / 128 * 128;
+    m->stage_bytes = SBC2_STAGE_CAP;      // the ring the planner sized every op's stage count against (Op::nstage)
     m->smem_bytes = 2 * (size_t)m->wmax + (size_t)m->stage_bytes + SBC2_NBARS * 8 + SBC2_PART_FLOATS * 4;
     cudaFuncAttributes fa{};
     if (cudaFuncGetAttributes(&fa, sbc2_ald_kernel) != cudaSuccess) return std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError());
@@ -76,9 +82,24 @@ static std::string sbc2_create(Sbc2Model* m, const sbc2::StateDict& sd_in, int n
         return "model needs " + std::to_string(m->smem_bytes) + " bytes of shared memory per CTA (weights of the widest conv twice + staging): too wide for engine 2";
     if (cudaFuncSetAttribute(sbc2_ald_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes) != cudaSuccess)
         return std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(cudaGetLastError());
-    int occ = 0;
+    cudaFuncSetAttribute(sbc2_ald_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // Resident CTAs per SM.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for ANY kernel that contains a
+    // tcgen05.alloc, yet the hardware co-schedules two such CTAs when each allocates <= 256 TMEM columns (measured with
+    // tools/occ_probe.cu: 296 CTAs of 192 threads run in one wave).  So: shared memory and registers decide, capped at 2.
+    int occ = 0, smpm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sbc2_ald_kernel, SBC2_NTHR, m->smem_bytes);
-    m->ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);     // TMEM: 256 columns per CTA -> at most 2
+    cudaDeviceGetAttribute(&smpm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    cudaFuncGetAttributes(&fa, sbc2_ald_kernel);
+    const size_t per_cta_smem = m->smem_bytes + fa.sharedSizeBytes + 1024;
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 32 * (SBC2_NTHR / 32);
+    const int by_smem = (int)((size_t)smpm / per_cta_smem), by_regs = 65536 / regs_per_cta;
+    int mine = by_smem < by_regs ? by_smem : by_regs;
+    mine = mine < 1 ? 1 : (mine > 2 ? 2 : mine);
+    m->ctas_per_sm = mine;
+    if (sbc2_env_int("SBC2_VERBOSE", 0))
+        fprintf(stderr, "[sbc2] regs %d static smem %zu dyn smem %zu (wmax %d stage %d) smem/SM %d: occupancy API %d, used %d\n",
+                fa.numRegs, fa.sharedSizeBytes, m->smem_bytes, m->wmax, m->stage_bytes, smpm, occ, mine);
+    if (sbc2_env_int("SBC2_CTAS", 0) > 0) m->ctas_per_sm = sbc2_env_int("SBC2_CTAS", 0);
     if (cudaMalloc(&m->d_blob, b.blob.size() ? b.blob.size() : 16) != cudaSuccess) return "cudaMalloc(blob) failed";
     cudaMemcpy(m->d_blob, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice);
     if (cudaMalloc(&m->d_sigmas, sizeof(float) * (size_t)m->n_sigmas) != cudaSuccess) return "cudaMalloc(sigmas) failed";
@@ -108,11 +129,6 @@ static Sbc2PlanDev* sbc2_plan(Sbc2Model* m, int S, bool reuse, std::string& err)
     Sbc2PlanDev* r = pd.get();
     m->plans[key] = std::move(pd);
     return r;
-}
-
-static int sbc2_env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return s ? atoi(s) : dflt;
 }
 
 // group size for a batch: one sample per CTA slot while the batch fits in one wave, then grow the groups
@@ -151,11 +167,32 @@ static std::string sbc2_prepare(Sbc2Model* m, int B, int S, bool reuse, Sbc2Laun
     L.Nt = m->Nt; L.Nr = m->Nr; L.channels = m->channels;
     L.sigmas = m->d_sigmas; L.n_sigmas = m->n_sigmas;
     L.prof = m->d_prof;
-    m->last_S = S; m->last_grid = grid;
+    L.dbg = sbc2_env_int("SBC2_DBG", 0);
+    L.trace_op = sbc2_env_int("SBC2_TRACE_OP", -1);
+    m->last_S = S; m->last_grid = grid; m->last_reuse = reuse ? 1 : 0;
+    if ((int)pd->plan.ops.size() > SBC2_MAX_OPS) return "layer program too long for the constant-memory op table";
     return "";
 }
 
 static cudaError_t sbc2_launch(Sbc2Model* m, const Sbc2Launch& L, int grid, cudaStream_t st) {
+    // the layer program travels through constant memory: stream-ordered upload in front of every launch (tens of KB,
+    // negligible against a launch that runs the whole schedule).  Launches of engine-2 models on DIFFERENT streams of
+    // one device must therefore not overlap.
+    Sbc2PlanDev* pd = m->plans[std::make_pair(L.S, m->last_reuse)].get();
+    const auto& ops = pd->plan.ops;
+    std::vector<int4> cc(ops.size());
+    const bool in_const = m->builder->all_mma.size() <= (size_t)SBC2_MAX_MMA;
+    for (size_t i = 0; i < ops.size(); i++) {
+        const sbc2::Op& o = ops[i];
+        cc[i] = o.kind == sbc2::K_CONV ? make_int4(in_const ? o.mma_idx : -1, o.n_mma, o.idesc, o.nstage) : make_int4(-1, 0, 0, 1);
+    }
+    cudaError_t ce = cudaMemcpyToSymbolAsync(sbc2_c_conv, cc.data(), sizeof(int4) * cc.size(), 0, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) return ce;
+    if (in_const) {
+        ce = cudaMemcpyToSymbolAsync(sbc2_c_mma, m->builder->all_mma.data(), sizeof(sbc2::MmaEntry) * m->builder->all_mma.size(), 0,
+                                     cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) return ce;
+    }
     sbc2_ald_kernel<<<grid, SBC2_NTHR, m->smem_bytes, st>>>(L);
     m->launches++;
     return cudaGetLastError();

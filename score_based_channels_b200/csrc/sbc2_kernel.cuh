@@ -31,8 +31,17 @@
 #define SBC2_NBARS 24
 #define SBC2_PART_FLOATS 1024      // shared scratch of the norm statistics: 2 x 64 units x 8 channels
 
+#define SBC2_MAX_OPS 320
+#define SBC2_MAX_MMA 4096
+// Per-op constants of the conv pipeline and every conv's UMMA descriptor list, in constant memory (uploaded by
+// sbc2_launch): indexed by warp-uniform values only, so the MMA issue loop runs on the uniform datapath (ULDC -> UIADD ->
+// UTCHMMA) without vector -> uniform register moves.  x = first list entry (-1: the list is read from the parameter
+// segment in shared memory instead), y = entries, z = instruction descriptor, w = staging ring depth.
+__constant__ int4 sbc2_c_conv[SBC2_MAX_OPS];
+__constant__ uint2 sbc2_c_mma[SBC2_MAX_MMA];
+
 struct Sbc2Launch {
-    const sbc2::Op* ops;
+    const sbc2::Op* ops;          // device copy of the layer program (records are prefetched into shared memory)
     int n_ops;
     const uint8_t* blob;
     sbc2::Geo geo[sbc2::MAX_LEVELS];
@@ -68,8 +77,11 @@ struct Sbc2Launch {
     const float* ext_noise;
     const float* dc_boost;
     const int* stop_step;
-    long long* prof;              // optional [n_ops + 2] clock64 stamps of CTA 0, first group, second step
-    int* status;                  // optional: device-side error flag (mbarrier timeout)
+    long long* prof;              // optional [n_ops + 2] clock64 stamps of CTA 0, first group, second step; when trace_op >= 0
+                                  // it is followed by [3 roles][64 tiles][4] intra-conv stamps of that op
+    int trace_op;
+    int dbg;                      // timing experiments only (env SBC2_DBG; results are garbage): 1 no MMAs, 2 no bulk
+                                  // copies, 4 no epilogue loads / stores, 8 no non-conv op bodies
 };
 
 namespace sbc2k {
@@ -104,6 +116,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// one lane of a converged warp (the pattern the compiler needs to keep descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -214,21 +234,52 @@ __device__ __forceinline__ void warp_sum8(float (&v)[8]) {
         for (int i = 0; i < 8; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
 }
 
+// interior-pixel number s*hw + y*w + x of padded pixel q, or -1 for pads (exact magic-number divisions)
+__device__ __forceinline__ int pix_of(const sbc2::Geo& G, int S, int q) {
+    const uint32_t n = (uint32_t)(q - G.lead);
+    const uint32_t s = __umulhi(n, G.mg_pps), r = n - s * (uint32_t)G.pps;
+    const uint32_t y = __umulhi(r, G.mg_wp), x = r - y * (uint32_t)G.wp;
+    return (q >= G.lead && s < (uint32_t)S && y < (uint32_t)G.h && x < (uint32_t)G.w) ? (int)(s * G.hw + y * G.w + x) : -1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// non-conv ops: all 192 threads, items = (sample, channel octet, pixel), pixel fastest (coalesced 16-byte accesses)
+// non-conv ops: all 192 threads, items = (sample, channel octet, pixel), pixel fastest (coalesced 16-byte accesses).
+// Activations come from L2 (~700 clk): every loop first issues the loads of U items, then computes and stores.
 // ---------------------------------------------------------------------------------------------------------
+struct Item { int oct, s, y, x, q; bool ok; };
+__device__ __forceinline__ Item item_of(const sbc2::Geo& G, const Dec& D, int i, int n, int per) {
+    Item it;
+    it.ok = i < n;
+    const int ii = it.ok ? i : 0;
+    it.oct = ii / per;
+    const int r = ii - it.oct * per;
+    int e;
+    D.sex(r, it.s, e);
+    D.yx(e, it.y, it.x);
+    it.q = qof(G, it.s, it.y, it.x);
+    return it;
+}
+
 __device__ __forceinline__ void op_affine(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
     const sbc2::Geo& G = L.geo[0];
     const Dec D(G);
     const float2* xin = reinterpret_cast<const float2*>(arena + op.src0);
     const int n = L.S * G.hw;
-    for (int i = tid; i < n; i += SBC2_NTHR) {
-        int s, e, y, x;
-        D.sex(i, s, e);
-        D.yx(e, y, x);
-        const float2 c = xin[i];
-        float v[8] = {2.f * c.x - 1.f, 2.f * c.y - 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // ncsnv2.py:270-271
-        store_sp16(arena + op.raw16, G.slot, 0, qof(G, s, y, x), v);
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
+        float2 c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int i = i0 + u * SBC2_NTHR; c[u] = xin[i < n ? i : 0]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * SBC2_NTHR;
+            if (i >= n) continue;
+            int s, e, y, x;
+            D.sex(i, s, e);
+            D.yx(e, y, x);
+            float v[8] = {2.f * c[u].x - 1.f, 2.f * c[u].y - 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // ncsnv2.py:270-271
+            store_sp16(arena + op.raw16, G.slot, 0, qof(G, s, y, x), v);
+        }
     }
 }
 
@@ -236,42 +287,54 @@ __device__ __forceinline__ void op_elu(const sbc2::Op& op, const Sbc2Launch& L, 
     const sbc2::Geo& G = L.geo[op.gs];
     const Dec D(G);
     const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
-    for (int i = tid; i < n; i += SBC2_NTHR) {
-        const int oct = i / per, r = i - oct * per;
-        int s, e, y, x;
-        D.sex(r, s, e);
-        D.yx(e, y, x);
-        const int q = qof(G, s, y, x);
-        float v[8];
-        load_f32x8(arena + op.src0, G.slot, oct, q, v);
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
+        Item it[U];
+        float v[U][8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
-        store_sp16(arena + op.elu16, G.slot, oct, q, v);
+        for (int u = 0; u < U; u++) {
+            it[u] = item_of(G, D, i0 + u * SBC2_NTHR, n, per);
+            load_f32x8(arena + op.src0, G.slot, it[u].oct, it[u].q, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!it[u].ok) continue;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[u][k] = elu(v[u][k]);
+            store_sp16(arena + op.elu16, G.slot, it[u].oct, it[u].q, v[u]);
+        }
     }
 }
 
-// MaxPool2d(5, 1, 2) with -inf padding (layers.py:70): F32 in, SP16 out
+// MaxPool2d(5, 1, 2) with -inf padding (layers.py:70): F32 in, SP16 out.  Clamped (replicated) coordinates give the
+// same maximum as -inf padding and make all 25 taps unconditional, independent loads.
 __device__ __forceinline__ void op_maxpool5(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
     const sbc2::Geo& G = L.geo[op.gs];
     const Dec D(G);
     const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
+    const uint8_t* src = arena + op.src0;
     for (int i = tid; i < n; i += SBC2_NTHR) {
-        const int oct = i / per, r = i - oct * per;
-        int s, e, y, x;
-        D.sex(r, s, e);
-        D.yx(e, y, x);
-        const int y0 = max(y - 2, 0), y1 = min(y + 2, G.h - 1), x0 = max(x - 2, 0), x1 = min(x + 2, G.w - 1);
+        const Item it = item_of(G, D, i, n, per);
+        int xo[5], yo[5];
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            xo[d] = min(max(it.x + d - 2, 0), G.w - 1);
+            yo[d] = G.lead + it.s * G.pps + min(max(it.y + d - 2, 0), G.h - 1) * G.wp;
+        }
         float m[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) m[k] = -INFINITY;
-        for (int yy = y0; yy <= y1; yy++)
-            for (int xx = x0; xx <= x1; xx++) {
-                float v[8];
-                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, yy, xx), v);
 #pragma unroll
-                for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
-            }
-        store_sp16(arena + op.raw16, G.slot, oct, qof(G, s, y, x), m);
+        for (int dy = 0; dy < 5; dy++) {
+            float v[5][8];
+#pragma unroll
+            for (int dx = 0; dx < 5; dx++) load_f32x8(src, G.slot, it.oct, yo[dy] + xo[dx], v[dx]);
+#pragma unroll
+            for (int dx = 0; dx < 5; dx++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[dx][k]);
+        }
+        store_sp16(arena + op.raw16, G.slot, it.oct, it.q, m);
     }
 }
 
@@ -284,29 +347,36 @@ __device__ __forceinline__ void op_upacc(const sbc2::Op& op, const Sbc2Launch& L
     const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
     const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
-    for (int i = tid; i < n; i += SBC2_NTHR) {
-        const int oct = i / per, r = i - oct * per;
-        int s, e, y, x;
-        D.sex(r, s, e);
-        D.yx(e, y, x);
-        const float fy = sy * (float)y, fx = sx * (float)x;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        float p00[8], p01[8], p10[8], p11[8], a[8];
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y0, x0), p00);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y0, x1), p01);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y1, x0), p10);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, y1, x1), p11);
-        const int q = qof(GD, s, y, x);
-        load_f32x8(arena + op.acc32, GD.slot, oct, q, a);
+    constexpr int U = 2;
+    for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
+        Item it[U];
+        float p00[U][8], p01[U][8], p10[U][8], p11[U][8], a[U][8], ly[U], lx[U];
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[k] += hy * (hx * p00[k] + lx * p01[k]) + ly * (hx * p10[k] + lx * p11[k]);
-        store_f32x8(arena + op.acc32, GD.slot, oct, q, a);
-        if (op.elu32 >= 0) {
+        for (int u = 0; u < U; u++) {
+            it[u] = item_of(GD, D, i0 + u * SBC2_NTHR, n, per);
+            const float fy = sy * (float)it[u].y, fx = sx * (float)it[u].x;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+            ly[u] = fy - (float)y0; lx[u] = fx - (float)x0;
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, qof(GS, it[u].s, y0, x0), p00[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, qof(GS, it[u].s, y0, x1), p01[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, qof(GS, it[u].s, y1, x0), p10[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, qof(GS, it[u].s, y1, x1), p11[u]);
+            load_f32x8(arena + op.acc32, GD.slot, it[u].oct, it[u].q, a[u]);
+        }
 #pragma unroll
-            for (int k = 0; k < 8; k++) a[k] = elu(a[k]);
-            store_f32x8(arena + op.elu32, GD.slot, oct, q, a);
+        for (int u = 0; u < U; u++) {
+            if (!it[u].ok) continue;
+            const float hy = 1.f - ly[u], hx = 1.f - lx[u];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                a[u][k] += hy * (hx * p00[u][k] + lx[u] * p01[u][k]) + ly[u] * (hx * p10[u][k] + lx[u] * p11[u][k]);
+            store_f32x8(arena + op.acc32, GD.slot, it[u].oct, it[u].q, a[u]);
+            if (op.elu32 >= 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[u][k] = elu(a[u][k]);
+                store_f32x8(arena + op.elu32, GD.slot, it[u].oct, it[u].q, a[u]);
+            }
         }
     }
 }
@@ -317,26 +387,34 @@ __device__ __forceinline__ void op_pool2(const sbc2::Op& op, const Sbc2Launch& L
     const sbc2::Geo& GD = L.geo[op.gd];
     const Dec D(GD);
     const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
-    for (int i = tid; i < n; i += SBC2_NTHR) {
-        const int oct = i / per, r = i - oct * per;
-        int s, e, y, x;
-        D.sex(r, s, e);
-        D.yx(e, y, x);
-        float a[8], b[8], c[8], d[8], v[8];
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y, 2 * x), a);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y + 1, 2 * x), b);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y, 2 * x + 1), c);
-        load_f32x8(arena + op.src0, GS.slot, oct, qof(GS, s, 2 * y + 1, 2 * x + 1), d);
+    constexpr int U = 2;
+    for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
+        Item it[U];
+        float a[U][8], b[U][8], c[U][8], d[U][8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (a[k] + b[k] + c[k] + d[k]) * 0.25f;   // same order as layers.py:311-312
-        const int q = qof(GD, s, y, x);
-        store_f32x8(arena + op.dst32, GD.slot, oct, q, v);
-        if (op.raw16 >= 0) store_sp16(arena + op.raw16, GD.slot, oct, q, v);
+        for (int u = 0; u < U; u++) {
+            it[u] = item_of(GD, D, i0 + u * SBC2_NTHR, n, per);
+            const int q0 = qof(GS, it[u].s, 2 * it[u].y, 2 * it[u].x);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, q0, a[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, q0 + GS.wp, b[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, q0 + 1, c[u]);
+            load_f32x8(arena + op.src0, GS.slot, it[u].oct, q0 + GS.wp + 1, d[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!it[u].ok) continue;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (a[u][k] + b[u][k] + c[u][k] + d[u][k]) * 0.25f;   // order of layers.py:311-312
+            store_f32x8(arena + op.dst32, GD.slot, it[u].oct, it[u].q, v);
+            if (op.raw16 >= 0) store_sp16(arena + op.raw16, GD.slot, it[u].oct, it[u].q, v);
+        }
     }
 }
 
-// InstanceNorm2dPlus + ELU (normalization.py:163-176): F32 in, SP16 out.  Work unit = (sample, octet, pixel chunk),
-// one warp per unit; two-pass statistics, partial sums exchanged through shared memory.
+// InstanceNorm2dPlus + ELU (normalization.py:163-176): F32 in, SP16 out.  Statistics: work unit = (sample, octet, chunk
+// of <= 256 pixels), one warp per unit, all 8 loads of a lane in flight at once; two passes (mean, centred squares),
+// partial sums exchanged through shared memory.
 __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, float* spart, int tid) {
     const sbc2::Geo& G = L.geo[op.gs];
     const Dec D(G);
@@ -344,67 +422,65 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = SBC2_NTHR / 32;
     const float* wseg = reinterpret_cast<const float*>(L.blob + op.w_off);
-    float* stats = reinterpret_cast<float*>(arena + op.scratch);       // [S][C][2] = (mean, M2)
-    float* coef = stats + (size_t)S * C * 2;                            // [S][C][2] = (scale, shift)
     const int n_items = S * noct;
-    int nchunk = 1;
-    while (nchunk * 2 * n_items <= NW && nchunk * 2 * 32 <= hw) nchunk *= 2;
-    const int lchunk = 31 - __clz(nchunk);
-    const int batch_items = min(n_items, 64 >> lchunk);
+    const int nchunk = (hw + 255) >> 8;
+    // shared scratch (1024 floats): small problems keep the statistics and coefficients on chip as well
+    const bool small = S * C <= 128 && n_items * nchunk <= 32;
+    float* stats = small ? spart + 512 : reinterpret_cast<float*>(arena + op.scratch);       // [S][C][2] = (mean, M2)
+    float* coef = small ? spart + 768 : stats + (size_t)S * C * 2;                            // [S][C][2] = (scale, shift)
+    const int cap = small ? 32 : 64;
+    const int batch_items = max(1, min(n_items, cap / nchunk));
     const float inv_hw = 1.f / (float)hw;
-    float* part1 = spart;                 // [64 units][8]
-    float* part2 = spart + 512;
+    float* part1 = spart;                 // [cap units][8]
+    float* part2 = spart + (small ? 256 : 512);
     for (int it0 = 0; it0 < n_items; it0 += batch_items) {
-        const int nit = min(batch_items, n_items - it0), nunits = nit << lchunk;
-        // pass 1: sums
-        for (int u = warp; u < nunits; u += NW) {
-            const int item = it0 + (u >> lchunk), ch = u & (nchunk - 1);
-            const int s = item / noct, oct = item - s * noct;
-            const int e0 = (hw * ch) >> lchunk, e1 = (hw * (ch + 1)) >> lchunk;
-            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int e = e0 + lane; e < e1; e += 32) {
-                int y, x;
-                D.yx(e, y, x);
-                float v[8];
-                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, y, x), v);
+        const int nit = min(batch_items, n_items - it0), nunits = nit * nchunk;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int u = warp; u < nunits; u += NW) {
+                const int li = u / nchunk, ch = u - li * nchunk, item = it0 + li;
+                const int s = item / noct, oct = item - s * noct;
+                const int e0 = ch << 8, e1 = min(hw, e0 + 256);
+                float mean[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) a[k] += v[k];
+                for (int k = 0; k < 8; k++) mean[k] = 0.f;
+                if (pass == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        float t = 0.f;
+                        for (int c2 = 0; c2 < nchunk; c2++) t += part1[(li * nchunk + c2) * 8 + k];
+                        mean[k] = t * inv_hw;
+                    }
+                }
+                float v[8][8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = min(e0 + lane + 32 * j, e1 - 1);
+                    int y, x;
+                    D.yx(e, y, x);
+                    load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, y, x), v[j]);
+                }
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool ok = e0 + lane + 32 * j < e1;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float d = v[j][k] - mean[k];
+                        const float t = pass == 0 ? d : d * d;
+                        a[k] += ok ? t : 0.f;
+                    }
+                }
+                warp_sum8(a);
+                if (lane < 8) (pass == 0 ? part1 : part2)[u * 8 + lane] = a[lane];
             }
-            warp_sum8(a);
-            if (lane < 8) part1[u * 8 + lane] = a[lane];
+            __syncthreads();
         }
-        __syncthreads();
-        // pass 2: centred sums of squares
-        for (int u = warp; u < nunits; u += NW) {
-            const int item = it0 + (u >> lchunk), ch = u & (nchunk - 1);
-            const int s = item / noct, oct = item - s * noct;
-            const int e0 = (hw * ch) >> lchunk, e1 = (hw * (ch + 1)) >> lchunk;
-            float mean[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                float t = 0.f;
-                for (int c2 = 0; c2 < nchunk; c2++) t += part1[(((u >> lchunk) << lchunk) + c2) * 8 + k];
-                mean[k] = t * inv_hw;
-            }
-            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int e = e0 + lane; e < e1; e += 32) {
-                int y, x;
-                D.yx(e, y, x);
-                float v[8];
-                load_f32x8(arena + op.src0, G.slot, oct, qof(G, s, y, x), v);
-#pragma unroll
-                for (int k = 0; k < 8; k++) { const float d = v[k] - mean[k]; a[k] = fmaf(d, d, a[k]); }
-            }
-            warp_sum8(a);
-            if (lane < 8) part2[u * 8 + lane] = a[lane];
-        }
-        __syncthreads();
         // per (item, channel): stats[s][c] = (mean, M2)
         for (int i = tid; i < nit * 8; i += SBC2_NTHR) {
             const int li = i >> 3, k = i & 7, item = it0 + li;
             const int s = item / noct, oct = item - s * noct;
             float t1 = 0.f, t2 = 0.f;
-            for (int c2 = 0; c2 < nchunk; c2++) { t1 += part1[((li << lchunk) + c2) * 8 + k]; t2 += part2[((li << lchunk) + c2) * 8 + k]; }
+            for (int c2 = 0; c2 < nchunk; c2++) { t1 += part1[(li * nchunk + c2) * 8 + k]; t2 += part2[(li * nchunk + c2) * 8 + k]; }
             stats[(s * C + oct * 8 + k) * 2] = t1 * inv_hw;
             stats[(s * C + oct * 8 + k) * 2 + 1] = t2;
         }
@@ -429,22 +505,29 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch
     }
     __syncthreads();
     const int per = S * hw, n = noct * per;
-    for (int i = tid; i < n; i += SBC2_NTHR) {
-        const int oct = i / per, r = i - oct * per;
-        int s, e, y, x;
-        D.sex(r, s, e);
-        D.yx(e, y, x);
-        const int q = qof(G, s, y, x);
-        float v[8];
-        load_f32x8(arena + op.src0, G.slot, oct, q, v);
-        const float4* cf = reinterpret_cast<const float4*>(coef + (s * C + oct * 8) * 2);
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
+        Item it[U];
+        float v[U][8];
+        float4 cf[U][4];
 #pragma unroll
-        for (int k2 = 0; k2 < 4; k2++) {
-            const float4 c4 = cf[k2];
-            v[2 * k2] = elu(fmaf(v[2 * k2], c4.x, c4.y));
-            v[2 * k2 + 1] = elu(fmaf(v[2 * k2 + 1], c4.z, c4.w));
+        for (int u = 0; u < U; u++) {
+            it[u] = item_of(G, D, i0 + u * SBC2_NTHR, n, per);
+            load_f32x8(arena + op.src0, G.slot, it[u].oct, it[u].q, v[u]);
+            const float4* cp = reinterpret_cast<const float4*>(coef + (it[u].s * C + it[u].oct * 8) * 2);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) cf[u][k2] = cp[k2];
         }
-        store_sp16(arena + op.elu16, G.slot, oct, q, v);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!it[u].ok) continue;
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) {
+                v[u][2 * k2] = elu(fmaf(v[u][2 * k2], cf[u][k2].x, cf[u][k2].y));
+                v[u][2 * k2 + 1] = elu(fmaf(v[u][2 * k2 + 1], cf[u][k2].z, cf[u][k2].w));
+            }
+            store_sp16(arena + op.elu16, G.slot, it[u].oct, it[u].q, v[u]);
+        }
     }
 }
 
@@ -457,8 +540,85 @@ struct Pipe {
     uint32_t conv_n;                // convs executed so far (weight buffer = conv_n & 1)
 };
 
-__device__ __forceinline__ void op_conv(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, uint8_t* smem,
-                                        uint64_t* bars, uint32_t tmem, Pipe& P, int tid, bool prefetch_next) {
+#define SBC2_TR(role, t, k) do { if (tr && (t) < 64) tr[((role) * 64 + (t)) * 4 + (k)] = clock64(); } while (0)
+
+// epilogue of one conv for the 4 epilogue warps, NCH = cout8 / 8 channel octets per pixel (compile-time: no runtime
+// indexed register arrays).  Warp w owns TMEM lanes 32w .. 32w+31 = pixels m0 + 32w + lane.
+template <int NCH>
+__device__ __forceinline__ void conv_epilogue(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, const uint8_t* wb,
+                                              uint64_t* tfull, uint64_t* tempty, uint32_t tmem, uint32_t acc_n0, int T,
+                                              int warp, int lane, long long* tr) {
+    const sbc2::Geo& G = L.geo[op.gs];
+    const float* bias = op.bias_rel >= 0 ? reinterpret_cast<const float*>(wb + op.bias_rel) : nullptr;
+    const int slot = G.slot, cout8 = NCH * 8;
+    const float us = op.unscale;
+    const int flags = op.flags, dst32 = op.dst32, acc32 = op.acc32, raw16 = op.raw16, elu16 = op.elu16, elu32 = op.elu32;
+    const bool has_acc = acc32 >= 0 && !(L.dbg & 4);
+    const int qbase = G.lead + warp * 32 + lane;
+    float accn[NCH][8];                           // residual values of the tile ahead (issued one tile early: L2 latency)
+    if (has_acc) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) load_f32x8(arena + acc32, slot, c, qbase, accn[c]);
+    }
+    for (int t = 0; t < T; t++) {
+        const uint32_t n = acc_n0 + (uint32_t)t, a = n % SBC2_NACC;
+        const int q = qbase + t * sbc2::TILE_M;
+        const int px = pix_of(G, L.S, q);
+        if (warp == 0) SBC2_TR(2, t, 0);
+        mbar_wait(&tfull[a], (n / SBC2_NACC) & 1u);
+        if (warp == 0) SBC2_TR(2, t, 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + a * 64u + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            float hi[8], lo[8], v[8];
+            tmem_ld8(taddr + (uint32_t)(c * 8), hi);
+            tmem_ld8(taddr + (uint32_t)(cout8 + c * 8), lo);
+            tmem_ld_wait();
+            if (c == NCH - 1) {                   // every column of this slot is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[a]);
+            }
+            if (L.dbg & 4) continue;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = fmaf(hi[k] + lo[k], us, bias ? bias[c * 8 + k] : 0.f);
+            if (flags & sbc2::F_COMPACT) {     // network output: couts (0,1) = (re, im) of element px
+                if (px >= 0) reinterpret_cast<float2*>(arena + dst32)[px] = make_float2(v[0], v[1]);
+                continue;
+            }
+            if (px < 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = 0.f;      // pads of every output stay zero
+            }
+            if (dst32 >= 0) store_f32x8(arena + dst32, slot, c, q, v);     // the raw conv result
+            if (acc32 >= 0) {
+                if (px >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] += accn[c][k];
+                }
+                store_f32x8(arena + acc32, slot, c, q, v);
+            }
+            if (raw16 >= 0) store_sp16(arena + raw16, slot, c, q, v);
+            if (elu16 >= 0 || elu32 >= 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
+                if (elu16 >= 0) store_sp16(arena + elu16, slot, c, q, v);
+                if (elu32 >= 0) store_f32x8(arena + elu32, slot, c, q, v);
+            }
+        }
+        if (has_acc && t + 1 < T) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) load_f32x8(arena + acc32, slot, c, q + sbc2::TILE_M, accn[c]);
+        }
+        if (warp == 0) SBC2_TR(2, t, 2);
+    }
+}
+
+// i = op index (warp-uniform: the per-op constants in sbc2_c_conv are read through it)
+__device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, uint8_t* smem,
+                                        uint64_t* bars, uint32_t tmem, Pipe& P, int tid, bool prefetch_next, long long* trace) {
+    long long* tr = (trace && (tid & 31) == 0) ? trace : nullptr;
     uint64_t* sfull = bars;            // [4]
     uint64_t* sempty = bars + 4;       // [4]
     uint64_t* tfull = bars + 8;        // [4]
@@ -469,110 +629,92 @@ __device__ __forceinline__ void op_conv(const sbc2::Op& op, const Sbc2Launch& L,
     uint8_t* wb = smem + (size_t)wslot * L.wmax;
     uint8_t* stage = smem + 2 * (size_t)L.wmax;
     const sbc2::Geo& G = L.geo[op.gs];
-    const int T = op.T, ns = op.nstage, nsub = op.nsub0 + op.nsub1;
-    const uint32_t stage_bytes = (uint32_t)nsub * (uint32_t)op.sps;
+    const int T = G.T;                                  // == op.T
+    const int4 cc = sbc2_c_conv[i];                     // uniform: list base, entries, idesc, ring depth
+    const int ns = cc.w;
+    const int nsub0 = op.nsub0, nsub1 = op.nsub1, sps = op.sps;
+    const uint32_t stage_bytes = (uint32_t)(nsub0 + nsub1) * (uint32_t)sps;
 
     if (warp == 4) {
-        if (lane == 0) {
-            if (prefetch_next) {   // the other buffer held the previous conv's segment: that conv is complete
-                uint64_t* wn = &wfull[wslot ^ 1u];
+        // ---------------- producer: the whole warp runs the loop (converged), one elected lane issues ----------------
+        if (prefetch_next) {   // the other buffer held the previous conv's segment: that conv is complete
+            uint64_t* wn = &wfull[wslot ^ 1u];
+            if (elect_one()) {
                 mbar_expect_tx(wn, (uint32_t)op.nw_len);
                 bulk_g2s(smem + (size_t)(wslot ^ 1u) * L.wmax, L.blob + op.nw_off, (uint32_t)op.nw_len, wn);
             }
-            for (int t = 0; t < T; t++) {
-                const int b = t & (ns - 1);
-                mbar_wait(&sempty[b], (P.sempty_k >> b) & 1u);
-                P.sempty_k ^= 1u << b;
+        }
+        const uint8_t* g0 = arena + op.src0 + (size_t)(G.lead - op.halo) * 16;
+        const uint8_t* g1 = arena + op.src1 + (size_t)(G.lead - op.halo) * 16;
+        const int slot = G.slot;
+        for (int t = 0; t < T; t++) {
+            const int b = t & (ns - 1);
+            SBC2_TR(0, t, 0);
+            mbar_wait(&sempty[b], (P.sempty_k >> b) & 1u);
+            SBC2_TR(0, t, 1);
+            P.sempty_k ^= 1u << b;
+            uint8_t* sb = stage + (size_t)b * stage_bytes;
+            const size_t toff = (size_t)t * (sbc2::TILE_M * 16);
+            if (L.dbg & 2) {
+                if (elect_one()) mbar_arrive(&sfull[b]);
+            } else if (elect_one()) {
                 mbar_expect_tx(&sfull[b], stage_bytes);
-                uint8_t* sb = stage + (size_t)b * stage_bytes;
-                const size_t goff = (size_t)(G.lead + t * sbc2::TILE_M - op.halo) * 16;
-                const uint8_t* g0 = arena + op.src0 + goff;
-                for (int j = 0; j < op.nsub0; j++) bulk_g2s(sb + (size_t)j * op.sps, g0 + (size_t)j * G.slot, (uint32_t)op.sps, &sfull[b]);
-                if (op.nsub1 > 0) {
-                    const uint8_t* g1 = arena + op.src1 + goff;
-                    for (int j = 0; j < op.nsub1; j++)
-                        bulk_g2s(sb + (size_t)(op.nsub0 + j) * op.sps, g1 + (size_t)j * G.slot, (uint32_t)op.sps, &sfull[b]);
-                }
+                for (int j = 0; j < nsub0; j++) bulk_g2s(sb + (size_t)j * sps, g0 + toff + (size_t)j * slot, (uint32_t)sps, &sfull[b]);
+                for (int j = 0; j < nsub1; j++)
+                    bulk_g2s(sb + (size_t)(nsub0 + j) * sps, g1 + toff + (size_t)j * slot, (uint32_t)sps, &sfull[b]);
             }
+            __syncwarp();
+            SBC2_TR(0, t, 2);
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            mbar_wait(&wfull[wslot], wpar);
-            const uint4* list = reinterpret_cast<const uint4*>(wb + op.mma_rel);
-            const uint32_t wb_s = smem_u32(wb), nlbo = (uint32_t)op.N * 16u;
-            for (int t = 0; t < T; t++) {
-                const int b = t & (ns - 1);
-                const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
-                mbar_wait(&sfull[b], (P.sfull_k >> b) & 1u);
-                P.sfull_k ^= 1u << b;
-                mbar_wait(&tempty[a], ((n / SBC2_NACC) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t sb_s = smem_u32(stage + (size_t)b * stage_bytes);
-                const uint32_t td = tmem + a * 64u;
-                for (int i = 0; i < op.n_mma; i++) {
-                    const uint4 e = list[i];
-                    umma_f16(td, make_desc(sb_s + e.x, e.y, 128u), make_desc(wb_s + e.z, nlbo, 128u), (uint32_t)op.idesc, i > 0 ? 1u : 0u);
+        // ---------------- MMA issuer: converged warp, uniform-datapath descriptors, one elected lane issues ----------------
+        mbar_wait(&wfull[wslot], wpar);
+        const uint32_t wb16 = smem_u32(wb) >> 4;
+        const uint32_t idesc = (uint32_t)cc.z;
+        const int n_mma = (L.dbg & 1) ? 0 : cc.y;
+        const uint32_t st16 = smem_u32(stage) >> 4, sbytes16 = stage_bytes >> 4;
+        for (int t = 0; t < T; t++) {
+            const int b = t & (ns - 1);
+            const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
+            SBC2_TR(1, t, 0);
+            mbar_wait(&sfull[b], (P.sfull_k >> b) & 1u);
+            SBC2_TR(1, t, 1);
+            P.sfull_k ^= 1u << b;
+            mbar_wait(&tempty[a], ((n / SBC2_NACC) & 1u) ^ 1u);
+            SBC2_TR(1, t, 2);
+            tc_fence_after();
+            const uint32_t sb16 = st16 + (uint32_t)b * sbytes16;
+            const uint32_t td = tmem + a * 64u;
+            if (elect_one()) {
+                if (cc.x >= 0) {
+                    const uint2* cl = sbc2_c_mma + cc.x;
+#pragma unroll 4
+                    for (int k = 0; k < n_mma; k++) {
+                        const uint2 e = cl[k];
+                        umma_f16(td, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16), ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16),
+                                 idesc, k > 0 ? 1u : 0u);
+                    }
+                } else {
+                    const uint2* list = reinterpret_cast<const uint2*>(wb + op.mma_rel);
+#pragma unroll 2
+                    for (int k = 0; k < n_mma; k++) {
+                        const uint2 e = list[k];
+                        umma_f16(td, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16), ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16),
+                                 idesc, k > 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&sempty[b]);     // the stage may be refilled once these MMAs have read it
                 umma_commit(&tfull[a]);      // accumulator complete
             }
+            __syncwarp();
+            SBC2_TR(1, t, 3);
         }
     } else {
-        // ---------------- epilogue: warp w owns TMEM lanes 32w .. 32w+31 = pixels m0 + 32w + lane ----------------
-        mbar_wait(&wfull[wslot], wpar);
-        const float* bias = op.bias_rel >= 0 ? reinterpret_cast<const float*>(wb + op.bias_rel) : nullptr;
-        const int32_t* pix = L.pix[op.gd];
-        const int slot = G.slot, nchunk = op.cout8 >> 3;
-        const float us = op.unscale;
-        for (int t = 0; t < T; t++) {
-            const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
-            const int q = G.lead + t * sbc2::TILE_M + warp * 32 + lane;
-            const int px = pix[q];
-            mbar_wait(&tfull[a], (n / SBC2_NACC) & 1u);
-            tc_fence_after();
-            const uint32_t taddr = tmem + a * 64u + ((uint32_t)(warp * 32) << 16);
-            for (int c = 0; c < nchunk; c++) {
-                float hi[8], lo[8], v[8];
-                tmem_ld8(taddr + (uint32_t)(c * 8), hi);
-                tmem_ld8(taddr + (uint32_t)(op.cout8 + c * 8), lo);
-                tmem_ld_wait();
-                if (c == nchunk - 1) {     // every column of this slot is in registers: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[a]);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    v[k] = (hi[k] + lo[k]) * us;
-                    if (bias) v[k] += bias[c * 8 + k];
-                }
-                if (op.flags & sbc2::F_COMPACT) {     // network output: couts (0,1) = (re, im) of element px
-                    if (px >= 0) reinterpret_cast<float2*>(arena + op.dst32)[px] = make_float2(v[0], v[1]);
-                    continue;
-                }
-                if (px < 0) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = 0.f;      // pads of every output stay zero
-                }
-                if (op.dst32 >= 0) store_f32x8(arena + op.dst32, slot, c, q, v);     // the raw conv result
-                if (op.acc32 >= 0) {
-                    if (px >= 0) {
-                        float o[8];
-                        load_f32x8(arena + op.acc32, slot, c, q, o);
-#pragma unroll
-                        for (int k = 0; k < 8; k++) v[k] += o[k];
-                    }
-                    store_f32x8(arena + op.acc32, slot, c, q, v);
-                }
-                if (op.raw16 >= 0) store_sp16(arena + op.raw16, slot, c, q, v);
-                if (op.elu16 >= 0 || op.elu32 >= 0) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
-                    if (op.elu16 >= 0) store_sp16(arena + op.elu16, slot, c, q, v);
-                    if (op.elu32 >= 0) store_f32x8(arena + op.elu32, slot, c, q, v);
-                }
-            }
-        }
+        mbar_wait(&wfull[wslot], wpar);      // the bias lives in the parameter segment
+        const int nch = op.cout8 >> 3;
+        if (nch == 1) conv_epilogue<1>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
+        else if (nch == 2) conv_epilogue<2>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
+        else conv_epilogue<4>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
     }
     P.acc_n += (uint32_t)T;
     P.conv_n++;
@@ -602,6 +744,9 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)L.wmax + (size_t)L.stage_bytes);
     float* spart = reinterpret_cast<float*>(bars + SBC2_NBARS);
     __shared__ uint32_t s_tmem;
+    // op records are prefetched global -> shared one op ahead (first 40 threads, one word each; the word loaded at the
+    // start of op i is stored at its end), so decoding an op never waits on L2
+    __shared__ __align__(16) sbc2::Op s_ops[2];
     __shared__ SbcStepScalars s_sc[SBC2_MAXS];
     __shared__ float s_hnorm[SBC2_MAXS];
     __shared__ float s_red[SBC2_NTHR / 32];
@@ -612,6 +757,7 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
         for (int i = 0; i < 4; i++) { mbar_init(&bars[i], 1); mbar_init(&bars[4 + i], 1); mbar_init(&bars[8 + i], 1); mbar_init(&bars[12 + i], 4); }
         mbar_init(&bars[16], 1);
         mbar_init(&bars[17], 1);
+        mbar_init(&bars[18], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -633,13 +779,17 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
 
     Pipe P;
     P.sfull_k = 0u; P.sempty_k = 0xFu; P.acc_n = 0u; P.conv_n = 0u;
+    uint32_t tail_par = 0u;   // parity of the tail's bulk-copy barrier (bars[18])
     bool w_pending = false;   // a parameter-segment prefetch is in flight (or landed) for conv number P.conv_n
     const int n_groups = (L.B + S - 1) / S;
     const int Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
     const int nsteps = (L.mode == 1) ? (L.level_end - L.level_begin) * L.steps_each : 1;
     int last_conv = -1;
     for (int i = 0; i < L.n_ops; i++)
-        if (L.ops[i].kind == sbc2::K_CONV) last_conv = i;
+        if (sbc2_c_conv[i].y > 0) last_conv = i;
+    if (tid < 40) reinterpret_cast<int*>(&s_ops[0])[tid] = reinterpret_cast<const int*>(L.ops)[tid];
+    uint32_t opc = 0;                         // ops executed so far (parity = ring slot)
+    __syncthreads();
 
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const bool last_group = (g + (int)gridDim.x >= n_groups);
@@ -699,12 +849,15 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                     s_sc[tid].nscale = (float)sqrt(2. * alpha * (double)L.beta[b]);
                 }
             }
-            const bool do_prof = (L.prof != nullptr) && blockIdx.x == 0 && g == 0 && gs == (nsteps > 1 ? 1 : 0) && tid == 0;
+            const bool do_prof_all = (L.prof != nullptr) && blockIdx.x == 0 && g == 0 && gs == (nsteps > 1 ? 1 : 0);
+            const bool do_prof = do_prof_all && tid == 0;
 
             // ---------------- the network ----------------
-            for (int i = 0; i < L.n_ops; i++) {
+            for (int i = 0; i < L.n_ops; i++, opc++) {
                 if (do_prof) L.prof[i] = clock64();
-                const sbc2::Op op = L.ops[i];
+                const sbc2::Op& op = s_ops[opc & 1u];
+                int pend = 0;
+                if (tid < 40) pend = reinterpret_cast<const int*>(L.ops + (i + 1 < L.n_ops ? i + 1 : 0))[tid];
                 if (op.kind == sbc2::K_CONV) {
                     if (!w_pending) {      // very first conv of the launch: nobody prefetched its segment
                         if (tid == 4 * 32) {
@@ -714,8 +867,9 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                     }
                     // the last conv of the launch must not leave a copy in flight
                     const bool pf = !(i == last_conv && last_step && last_group);
-                    op_conv(op, L, arena, smem, bars, tmem, P, tid, pf);
+                    op_conv(i, op, L, arena, smem, bars, tmem, P, tid, pf, (do_prof_all && i == L.trace_op) ? L.prof + L.n_ops + 2 : nullptr);
                     w_pending = pf;
+                } else if (L.dbg & 8) {
                 } else if (op.kind == sbc2::K_NORM_ELU) {
                     op_norm_elu(op, L, arena, spart, tid);
                 } else if (op.kind == sbc2::K_MAXPOOL5) {
@@ -729,7 +883,8 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                 } else if (op.kind == sbc2::K_AFFINE) {
                     op_affine(op, L, arena, tid);
                 }
-                fence_proxy_async();      // generic-proxy stores -> visible to the next op's bulk copies
+                if (op.fence_after) fence_proxy_async();      // generic-proxy stores -> visible to the next conv's bulk copies
+                if (tid < 40) reinterpret_cast<int*>(&s_ops[(opc + 1u) & 1u])[tid] = pend;
                 __syncthreads();
             }
             if (do_prof) L.prof[L.n_ops] = clock64();
@@ -751,14 +906,16 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                     }
                 }
             } else {
-                // data-consistency residual P x - y for every sample, then gradient + Langevin update + NMSE
-                for (int s = 0; s < S && b0 + s < L.B; s++) {
-                    const int b = b0 + s;
-                    const float* ax = reinterpret_cast<const float*>(arena + L.x_off) + (size_t)s * ne * 2;
-                    float* res = reinterpret_cast<float*>(arena + L.post_off) + (size_t)s * ne * 2;
-                    sbc_dc_residual(ax, res, L.P + (size_t)b * L.Np * Nt * 2, L.Y + (size_t)b * L.Np * Nr * 2, Nt, Nr, L.Np, tid, SBC2_NTHR);
-                }
-                __syncthreads();
+                // data-consistency residual P x - y, gradient, Langevin update and NMSE, sample by sample.  The state x, the
+                // residual, Y (staging ring, idle now) and P (the weight buffer that is not holding the prefetched first
+                // conv) are staged in shared memory: the two complex matrix products read each operand ~Nt / ~Np times.
+                const size_t pbytes = (size_t)L.Np * Nt * 8, ybytes = (size_t)L.Np * Nr * 8;
+                const bool staged = pbytes <= (size_t)L.wmax && (size_t)ne * 8 + 2 * ybytes <= (size_t)L.stage_bytes &&
+                                    ((reinterpret_cast<uintptr_t>(L.P) & 15) == 0);
+                float* xs = reinterpret_cast<float*>(smem + 2 * (size_t)L.wmax);
+                float* rs = xs + (size_t)ne * 2;
+                float* ys = rs + (size_t)L.Np * Nr * 2;
+                float* ps = reinterpret_cast<float*>(smem + (size_t)((P.conv_n & 1u) ^ 1u) * L.wmax);
                 for (int s = 0; s < S && b0 + s < L.B; s++) {
                     const int b = b0 + s;
                     int st_last = nsteps - 1;
@@ -766,16 +923,38 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                     if (gs > st_last) continue;                        // this sample stopped early
                     float* ax = reinterpret_cast<float*>(arena + L.x_off) + (size_t)s * ne * 2;
                     const float* net = reinterpret_cast<const float*>(arena + L.out_off) + (size_t)s * ne * 2;
-                    const float* res = reinterpret_cast<const float*>(arena + L.post_off) + (size_t)s * ne * 2;
                     const float* Pm = L.P + (size_t)b * L.Np * Nt * 2;
+                    const float* Ym = L.Y + (size_t)b * L.Np * Nr * 2;
                     const float* Hc = L.Hor ? L.Hor + (size_t)b * ne * 2 : nullptr;
                     const float* en = L.ext_noise ? L.ext_noise + ((size_t)gs * L.B + b) * ne * 2 : nullptr;
                     const unsigned long long sid = L.sample_ids ? L.sample_ids[b] : (unsigned long long)b;
                     const uint32_t gstep = (uint32_t)(lvl * L.steps_each + gs % L.steps_each);
-                    const float part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                    float part;
+                    if (staged) {
+                        if (tid == 0) {
+                            mbar_expect_tx(&bars[18], (uint32_t)pbytes);
+                            bulk_g2s(ps, Pm, (uint32_t)pbytes, &bars[18]);
+                        }
+                        for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(xs)[e] = reinterpret_cast<const float2*>(ax)[e];
+                        for (int e = tid; e < L.Np * Nr; e += SBC2_NTHR) reinterpret_cast<float2*>(ys)[e] = reinterpret_cast<const float2*>(Ym)[e];
+                        mbar_wait(&bars[18], tail_par);
+                        tail_par ^= 1u;
+                        __syncthreads();
+                        sbc_dc_residual(xs, rs, ps, ys, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                        __syncthreads();
+                        part = sbc_langevin_update(xs, net, rs, ps, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                        for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(ax)[e] = reinterpret_cast<const float2*>(xs)[e];   // own elements
+                    } else {
+                        float* res = reinterpret_cast<float*>(arena + L.post_off) + (size_t)s * ne * 2;
+                        sbc_dc_residual(ax, res, Pm, Ym, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                        __syncthreads();
+                        part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                    }
                     if (L.nmse_log && Hc) {
                         const float tot = block_sum(part, s_red, tid);
                         if (tid == 0) L.nmse_log[(size_t)gs * L.B + b] = tot / s_hnorm[s];
+                    } else {
+                        __syncthreads();
                     }
                 }
             }

@@ -41,12 +41,13 @@ enum : int32_t { F_COMPACT = 1 };      // conv: couts 0,1 go to the compact (re,
 constexpr int TILE_M = 128;            // UMMA M
 constexpr int MAX_LEVELS = 4;
 
-struct Geo {                           // 12 words
+struct Geo {                           // 14 words
     int32_t h, w, hy, hx, wp, rps, pps, lead;
     int32_t npx;                       // allocated pixels per slot = lead + 128*T + lead (multiple of 8)
     int32_t T;                         // 128-pixel tiles covering [lead, lead + S*pps)
     int32_t slot;                      // bytes per slot = npx * 16
     int32_t hw;                        // h * w
+    uint32_t mg_pps, mg_wp;            // ceil(2^32 / pps), ceil(2^32 / wp): n / d = umulhi(n, magic) for n * d < 2^32
 };
 
 // one op = 40 int32 words = 160 bytes.  Offsets are bytes relative to the group arena (or to the blob); -1 = unused.
@@ -70,11 +71,19 @@ struct Op {
     int32_t scratch;                   // norm: byte offset of the statistics scratch (RAW region)
     int32_t nw_off, nw_len;            // conv: segment of the NEXT conv (wraps to the first) for the prefetch
     int32_t wslot;                     // conv: which of the two shared-memory weight buffers holds this segment
-    int32_t pad[7];
+    int32_t mma_idx;                   // conv: first entry of this op's UMMA list in the model-wide list (constant memory), or -1
+    int32_t fence_after;               // 1: the next op (wrapping) is a conv, i.e. reads through the async proxy
+    int32_t pad[5];
 };
 static_assert(sizeof(Op) == 160, "Op must be 40 words");
 
-struct MmaEntry { uint32_t a_off, lbo, b_off, pad; };   // one tcgen05.mma: A start (bytes from the stage base), A LBO, B tile
+// one tcgen05.mma, as the low words of its two shared-memory matrix descriptors relative to the staging slot / to the
+// parameter segment: bits 0-13 = byte offset >> 4, bits 16-29 = LBO >> 4.  The kernel adds (base address >> 4); the high
+// word (SBO = 128 B, descriptor version 1) is the constant 0x4008.
+struct MmaEntry { uint32_t a_lo, b_lo; };
+static inline uint32_t desc_lo(uint32_t off, uint32_t lbo) { return ((off >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+static inline uint32_t desc_off(uint32_t lo) { return (lo & 0x3FFFu) << 4; }
+static inline uint32_t desc_lbo(uint32_t lo) { return ((lo >> 16) & 0x3FFFu) << 4; }
 
 struct TensorInfo {                    // debug / test view of the arena
     char name[48];
@@ -142,6 +151,7 @@ class Builder {
     int ngf, H, W, channels;
     int64_t conv_flops = 0;
     std::vector<uint8_t> blob;
+    std::vector<MmaEntry> all_mma;       // every conv's UMMA list back to back (Op::mma_idx), for the constant-memory copy
     int32_t max_seg = 0, max_stage = 0;
     int stage_cap;                       // bytes available for the A staging ring in shared memory
     std::string error;
@@ -163,6 +173,8 @@ class Builder {
                 if (dils[i] < g.w) g.hx = std::max(g.hx, dils[i]);
             }
             g.wp = g.w + g.hx; g.rps = g.h + g.hy; g.pps = g.rps * g.wp; g.lead = g.hy * g.wp + g.hx; g.hw = g.h * g.w;
+            g.mg_pps = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)g.pps - 1) / (uint64_t)g.pps);
+            g.mg_wp = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)g.wp - 1) / (uint64_t)g.wp);
         }
         build();
     }
@@ -176,6 +188,7 @@ class Builder {
             g.T = (S * g.pps + TILE_M - 1) / TILE_M;
             g.npx = (g.lead + TILE_M * g.T + g.lead + 7) / 8 * 8;
             g.slot = g.npx * 16;
+            if ((uint64_t)g.npx * (uint64_t)g.pps >= ((uint64_t)1 << 32)) throw std::runtime_error("group too large for the index arithmetic");
             P.geo[l] = g;
             std::vector<int32_t> pm((size_t)g.npx, -1);
             for (int s = 0; s < S; s++)
@@ -267,6 +280,7 @@ class Builder {
                 if (P.first_conv < 0) P.first_conv = (int)i;
             }
         }
+        for (size_t i = 0; i < P.ops.size(); i++) P.ops[i].fence_after = P.ops[(i + 1) % P.ops.size()].kind == K_CONV ? 1 : 0;
         // prefetch chain: every conv knows the segment of the next conv (the last wraps to the first)
         int next = P.first_conv;
         for (int i = (int)P.ops.size() - 1; i >= 0; i--) {
@@ -454,12 +468,13 @@ class Builder {
                             bt[at(c8 + n)] = lo;
                         }
                     const uint32_t a_base = (uint32_t)((halo + shift) * 16);
+                    const uint32_t blo = desc_lo(b_off, (uint32_t)N * 16u);       // rebased to the segment below
                     if (pair) {      // 16 channels of hi, then 16 channels of lo, same B tile
-                        list.push_back({(uint32_t)(subbase + 2 * p) * sps + a_base, (uint32_t)(2 * sps), b_off, 0});
-                        list.push_back({(uint32_t)(subbase + 2 * p + 1) * sps + a_base, (uint32_t)(2 * sps), b_off, 0});
+                        list.push_back({desc_lo((uint32_t)(subbase + 2 * p) * sps + a_base, (uint32_t)(2 * sps)), blo});
+                        list.push_back({desc_lo((uint32_t)(subbase + 2 * p + 1) * sps + a_base, (uint32_t)(2 * sps)), blo});
                         p += 2;
                     } else {         // [hi | lo] of 8 channels against [w | w]
-                        list.push_back({(uint32_t)(subbase + 2 * p) * sps + a_base, (uint32_t)sps, b_off, 0});
+                        list.push_back({desc_lo((uint32_t)(subbase + 2 * p) * sps + a_base, (uint32_t)sps), blo});
                         p += 1;
                     }
                 }
@@ -467,7 +482,9 @@ class Builder {
             subbase += nsub[bi];
         }
         if (list.empty()) throw std::runtime_error("conv without live taps");
-        // ---- segment: [mma list][bias c8 floats][B tiles] ----
+        // ---- segment: [mma list (padded to 16 B)][bias c8 floats][B tiles] ----
+        const size_t n_real = list.size();
+        if (n_real & 1) list.push_back(list.back());           // the kernel reads entry pairs; n_mma stays the real count
         const size_t seg0 = blob_align(128);
         const size_t mma_rel = 0, bias_rel = list.size() * sizeof(MmaEntry);
         size_t btile_rel = bias_rel + (size_t)c8 * 4;
@@ -479,7 +496,9 @@ class Builder {
         blob_align(16);
         // b_off of the entries is relative to the tile array: rebase to the segment
         MmaEntry* le = reinterpret_cast<MmaEntry*>(blob.data() + seg0);
-        for (size_t i = 0; i < list.size(); i++) le[i].b_off += (uint32_t)btile_rel;
+        for (size_t i = 0; i < list.size(); i++) le[i].b_lo += (uint32_t)(btile_rel >> 4);
+        const int32_t mma_idx = (int32_t)all_mma.size();
+        for (size_t i = 0; i < n_real; i++) all_mma.push_back(le[i]);
 
         Op o = blank(K_CONV);
         o.flags = out.compact ? F_COMPACT : 0;
@@ -487,12 +506,13 @@ class Builder {
         o.cin = tens[br[0].src].C; o.cout = std::min(c8, std::max(0, cout_real - co0));
         o.nsub0 = nsub[0]; o.nsub1 = nsub[1];
         o.w_off = (int32_t)seg0; o.w_len = (int32_t)(blob.size() - seg0);
-        o.n_mma = (int32_t)list.size(); o.mma_rel = (int32_t)mma_rel;
+        o.n_mma = (int32_t)n_real; o.mma_rel = (int32_t)mma_rel;
         o.bias_rel = any_bias ? (int32_t)bias_rel : -1;
         o.btile_rel = (int32_t)btile_rel;
         o.halo = halo; o.N = N; o.cout8 = c8; o.sps = sps;
         o.idesc = (int32_t)((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24));   // F32 accum, F16 x F16, K-major
         o.unscale = 1.0f / ws;
+        o.mma_idx = mma_idx;
         max_seg = std::max(max_seg, o.w_len);
         max_stage = std::max(max_stage, (nsub[0] + nsub[1]) * sps);
         R_ r;

@@ -472,7 +472,7 @@ extern "C" int sbc_model_create_from_state(const sbc_state_entry* entries, int32
 }
 
 extern "C" int sbc_debug_plan(void* handle, int32_t S, int32_t reuse, sbc_tensor_info* out, int32_t cap, int32_t* n_out,
-                              int64_t* arena_bytes, int32_t* geo_out /* [4][12] */) {
+                              int64_t* arena_bytes, int32_t* geo_out /* [4][14] */) {
     if (!handle) return sbc_fail(SBC_E_ARG, "sbc_debug_plan: null handle");
     SbcModel* m = (SbcModel*)handle;
     if (m->engine != 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_plan: engine 2 only");

@@ -62,7 +62,7 @@ class PackedModel:
         """(arena_bytes, [TensorInfo], geo[4][12]) of the engine-2 plan for group size S."""
         n, ab = C.c_int32(), C.c_int64()
         info = (_lib.TensorInfo * 2048)()
-        geo = np.zeros((4, 12), np.int32)
+        geo = np.zeros((4, 14), np.int32)
         _lib.check(_lib.lib().sbc_debug_plan(self.handle, S, int(reuse), info, 2048, C.byref(n), C.byref(ab),
                                              geo.ctypes.data), "sbc_debug_plan")
         return int(ab.value), list(info)[:n.value], geo

@@ -61,12 +61,12 @@ static void run_conv(const Op& op, const Plan& P, const uint8_t* blob, uint8_t* 
         for (int j = 0; j < op.nsub1; j++) memcpy(&stage[(size_t)(op.nsub0 + j) * op.sps], arena + op.src1 + goff + (size_t)j * G.slot, op.sps);
         std::fill(D.begin(), D.end(), 0.f);
         for (int i = 0; i < op.n_mma; i++) {
-            const MmaEntry& e = list[i];
-            const uint32_t nlbo = (uint32_t)N * 16u;
+            const uint32_t a_off = desc_off(list[i].a_lo), a_lbo = desc_lbo(list[i].a_lo);
+            const uint32_t b_off = desc_off(list[i].b_lo), nlbo = desc_lbo(list[i].b_lo);
             for (int m = 0; m < TILE_M; m++) {
                 float a[16];
                 for (int k = 0; k < 16; k++) {
-                    const size_t off = e.a_off + (size_t)(k >> 3) * e.lbo + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16 + (size_t)(k & 7) * 2;
+                    const size_t off = a_off + (size_t)(k >> 3) * a_lbo + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16 + (size_t)(k & 7) * 2;
                     uint16_t h;
                     memcpy(&h, &stage[off], 2);
                     a[k] = f16_to_f32(h);
@@ -74,7 +74,7 @@ static void run_conv(const Op& op, const Plan& P, const uint8_t* blob, uint8_t* 
                 for (int n = 0; n < N; n++) {
                     float acc = 0.f;
                     for (int k = 0; k < 16; k++) {
-                        const size_t off = e.b_off + (size_t)(k >> 3) * nlbo + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2;
+                        const size_t off = b_off + (size_t)(k >> 3) * nlbo + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2;
                         uint16_t h;
                         memcpy(&h, seg + off, 2);
                         acc += a[k] * f16_to_f32(h);

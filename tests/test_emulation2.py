@@ -75,7 +75,7 @@ class Emu2:
     def plan(self, S, reuse=True):
         n = C.c_int()
         info = (TensorInfo * 1024)()
-        geo = np.zeros((4, 12), np.int32)
+        geo = np.zeros((4, 14), np.int32)
         ab = self.lib.emu2_plan(self.h, S, int(reuse), info, 1024, C.byref(n), geo.ctypes.data, None)
         return ab, list(info)[:n.value], geo
 
