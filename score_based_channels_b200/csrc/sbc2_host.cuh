@@ -159,7 +159,6 @@ static std::string sbc2_prepare(Sbc2Model* m, int B, int S, bool reuse, Sbc2Laun
     }
     memset(&L, 0, sizeof L);
     L.ops = pd->d_ops; L.n_ops = (int)pd->plan.ops.size(); L.blob = m->d_blob;
-    for (int l = 0; l < sbc2::MAX_LEVELS; l++) { L.geo[l] = pd->plan.geo[l]; L.pix[l] = pd->d_pix[l]; }
     L.gws = m->d_gws; L.arena_bytes = pd->plan.arena_bytes;
     L.S = S; L.B = B;
     L.x_off = pd->plan.x_off; L.out_off = pd->plan.out_off; L.post_off = pd->plan.post_off;
@@ -184,9 +183,21 @@ static cudaError_t sbc2_launch(Sbc2Model* m, const Sbc2Launch& L, int grid, cuda
     const bool in_const = m->builder->all_mma.size() <= (size_t)SBC2_MAX_MMA;
     for (size_t i = 0; i < ops.size(); i++) {
         const sbc2::Op& o = ops[i];
-        cc[i] = o.kind == sbc2::K_CONV ? make_int4(in_const ? o.mma_idx : -1, o.n_mma, o.idesc, o.nstage) : make_int4(-1, 0, 0, 1);
+        if (o.kind != sbc2::K_CONV) { cc[i] = make_int4(-1, 0, 0, 1 | (1 << 8) | (1 << 16)); continue; }
+        // Split-K partial accumulators (SBC2_NPART=2|4): independent accumulation chains, summed by the epilogue.  Measured
+        // on B200 (tools/umma_rate.cu): a small tcgen05.mma costs ~54 clk whatever N <= 64, the layout or the accumulator
+        // it targets -- the chains do not serialise on the TMEM read-modify-write, so the default is ONE accumulator.
+        int npart = 1;
+        const int want = sbc2_env_int("SBC2_NPART", 1);
+        while (npart * 2 <= want && npart * 2 <= 4 && npart * 2 <= o.n_mma) npart *= 2;
+        int span = (npart * o.N + 63) / 64;
+        while (span > (o.T > 1 ? 2 : 4) && npart > 1) { npart /= 2; span = (npart * o.N + 63) / 64; }
+        span = span <= 1 ? 1 : (span <= 2 ? 2 : 4);
+        cc[i] = make_int4(in_const ? o.mma_idx : -1, o.n_mma, o.idesc, o.nstage | (npart << 8) | (span << 16));
     }
-    cudaError_t ce = cudaMemcpyToSymbolAsync(sbc2_c_conv, cc.data(), sizeof(int4) * cc.size(), 0, cudaMemcpyHostToDevice, st);
+    cudaError_t ce = cudaMemcpyToSymbolAsync(sbc2_c_geo, pd->plan.geo, sizeof(sbc2::Geo) * sbc2::MAX_LEVELS, 0, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaMemcpyToSymbolAsync(sbc2_c_conv, cc.data(), sizeof(int4) * cc.size(), 0, cudaMemcpyHostToDevice, st);
     if (ce != cudaSuccess) return ce;
     if (in_const) {
         ce = cudaMemcpyToSymbolAsync(sbc2_c_mma, m->builder->all_mma.data(), sizeof(sbc2::MmaEntry) * m->builder->all_mma.size(), 0,

@@ -38,14 +38,13 @@
 // UTCHMMA) without vector -> uniform register moves.  x = first list entry (-1: the list is read from the parameter
 // segment in shared memory instead), y = entries, z = instruction descriptor, w = staging ring depth.
 __constant__ int4 sbc2_c_conv[SBC2_MAX_OPS];
+__constant__ sbc2::Geo sbc2_c_geo[sbc2::MAX_LEVELS];     // level geometries of the plan in flight (dynamically indexed)
 __constant__ uint2 sbc2_c_mma[SBC2_MAX_MMA];
 
 struct Sbc2Launch {
     const sbc2::Op* ops;          // device copy of the layer program (records are prefetched into shared memory)
     int n_ops;
     const uint8_t* blob;
-    sbc2::Geo geo[sbc2::MAX_LEVELS];
-    const int32_t* pix[sbc2::MAX_LEVELS];
     uint8_t* gws;                 // [gridDim.x] group arenas
     long long arena_bytes;
     int S, B;
@@ -226,6 +225,7 @@ struct Dec {
 };
 __device__ __forceinline__ int qof(const sbc2::Geo& G, int s, int y, int x) { return G.lead + s * G.pps + y * G.wp + x; }
 
+__device__ __forceinline__ float inv_hw0(int hw) { return 1.f / (float)hw; }
 // sum over the warp of 8 per-lane values; every lane gets all 8 totals
 __device__ __forceinline__ void warp_sum8(float (&v)[8]) {
 #pragma unroll
@@ -260,12 +260,12 @@ __device__ __forceinline__ Item item_of(const sbc2::Geo& G, const Dec& D, int i,
     return it;
 }
 
-__device__ __forceinline__ void op_affine(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
-    const sbc2::Geo& G = L.geo[0];
+__device__ __forceinline__ void op_affine(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[0];
     const Dec D(G);
     const float2* xin = reinterpret_cast<const float2*>(arena + op.src0);
-    const int n = L.S * G.hw;
-    constexpr int U = 4;
+    const int n = S_ * G.hw;
+    constexpr int U = 2;
     for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
         float2 c[U];
 #pragma unroll
@@ -283,11 +283,11 @@ __device__ __forceinline__ void op_affine(const sbc2::Op& op, const Sbc2Launch& 
     }
 }
 
-__device__ __forceinline__ void op_elu(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
-    const sbc2::Geo& G = L.geo[op.gs];
+__device__ __forceinline__ void op_elu(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const Dec D(G);
-    const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
-    constexpr int U = 4;
+    const int noct = op.cin >> 3, per = S_ * G.hw, n = noct * per;
+    constexpr int U = 2;
     for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
         Item it[U];
         float v[U][8];
@@ -308,10 +308,10 @@ __device__ __forceinline__ void op_elu(const sbc2::Op& op, const Sbc2Launch& L, 
 
 // MaxPool2d(5, 1, 2) with -inf padding (layers.py:70): F32 in, SP16 out.  Clamped (replicated) coordinates give the
 // same maximum as -inf padding and make all 25 taps unconditional, independent loads.
-__device__ __forceinline__ void op_maxpool5(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
-    const sbc2::Geo& G = L.geo[op.gs];
+__device__ __forceinline__ void op_maxpool5(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const Dec D(G);
-    const int noct = op.cin >> 3, per = L.S * G.hw, n = noct * per;
+    const int noct = op.cin >> 3, per = S_ * G.hw, n = noct * per;
     const uint8_t* src = arena + op.src0;
     for (int i = tid; i < n; i += SBC2_NTHR) {
         const Item it = item_of(G, D, i, n, per);
@@ -339,15 +339,15 @@ __device__ __forceinline__ void op_maxpool5(const sbc2::Op& op, const Sbc2Launch
 }
 
 // acc += bilinear(src, align_corners=True) (layers.py:182-183); optional elu32 = ELU(acc)
-__device__ __forceinline__ void op_upacc(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
-    const sbc2::Geo& GS = L.geo[op.gs];
-    const sbc2::Geo& GD = L.geo[op.gd];
+__device__ __forceinline__ void op_upacc(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& GS = sbc2_c_geo[op.gs];
+    const sbc2::Geo& GD = sbc2_c_geo[op.gd];
     const Dec D(GD);
     const int H = GS.h, W = GS.w, OH = GD.h, OW = GD.w;
     const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-    const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
-    constexpr int U = 2;
+    const int noct = op.cin >> 3, per = S_ * GD.hw, n = noct * per;
+    constexpr int U = 1;
     for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
         Item it[U];
         float p00[U][8], p01[U][8], p10[U][8], p11[U][8], a[U][8], ly[U], lx[U];
@@ -382,12 +382,12 @@ __device__ __forceinline__ void op_upacc(const sbc2::Op& op, const Sbc2Launch& L
 }
 
 // 2x2 mean-pool of ConvMeanPool (layers.py:309-313): F32 level g -> F32 level g+1 (+ optional raw SP16)
-__device__ __forceinline__ void op_pool2(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, int tid) {
-    const sbc2::Geo& GS = L.geo[op.gs];
-    const sbc2::Geo& GD = L.geo[op.gd];
+__device__ __forceinline__ void op_pool2(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& GS = sbc2_c_geo[op.gs];
+    const sbc2::Geo& GD = sbc2_c_geo[op.gd];
     const Dec D(GD);
-    const int noct = op.cin >> 3, per = L.S * GD.hw, n = noct * per;
-    constexpr int U = 2;
+    const int noct = op.cin >> 3, per = S_ * GD.hw, n = noct * per;
+    constexpr int U = 1;
     for (int i0 = tid; i0 < n; i0 += SBC2_NTHR * U) {
         Item it[U];
         float a[U][8], b[U][8], c[U][8], d[U][8];
@@ -415,16 +415,21 @@ __device__ __forceinline__ void op_pool2(const sbc2::Op& op, const Sbc2Launch& L
 // InstanceNorm2dPlus + ELU (normalization.py:163-176): F32 in, SP16 out.  Statistics: work unit = (sample, octet, chunk
 // of <= 256 pixels), one warp per unit, all 8 loads of a lane in flight at once; two passes (mean, centred squares),
 // partial sums exchanged through shared memory.
-__device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, float* spart, int tid) {
-    const sbc2::Geo& G = L.geo[op.gs];
+// general InstanceNorm++ path: three sweeps over the tensor (statistics exchanged through shared / global scratch)
+// InstanceNorm2dPlus + ELU (normalization.py:163-176): F32 in, SP16 out.  Statistics: work unit = (sample, octet, chunk
+// of <= 256 pixels), one warp per unit, all 8 loads of a lane in flight at once; two passes (mean, centred squares),
+// partial sums exchanged through shared memory.
+// general InstanceNorm++ path: three sweeps over the tensor (statistics exchanged through shared / global scratch)
+__device__ __noinline__ void op_norm_elu_general(const sbc2::Op& op, const int S_, const uint8_t* blob, uint8_t* arena, float* spart, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const Dec D(G);
-    const int C = op.cin, noct = C >> 3, S = L.S, hw = G.hw;
+    const int C = op.cin, noct = C >> 3, S = S_, hw = G.hw;
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = SBC2_NTHR / 32;
-    const float* wseg = reinterpret_cast<const float*>(L.blob + op.w_off);
+    const float* wseg = reinterpret_cast<const float*>(blob + op.w_off);
     const int n_items = S * noct;
-    const int nchunk = (hw + 255) >> 8;
     // shared scratch (1024 floats): small problems keep the statistics and coefficients on chip as well
+    const int nchunk = (hw + 255) >> 8;
     const bool small = S * C <= 128 && n_items * nchunk <= 32;
     float* stats = small ? spart + 512 : reinterpret_cast<float*>(arena + op.scratch);       // [S][C][2] = (mean, M2)
     float* coef = small ? spart + 768 : stats + (size_t)S * C * 2;                            // [S][C][2] = (scale, shift)
@@ -531,12 +536,129 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const Sbc2Launch
     }
 }
 
+
+__device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, const uint8_t* blob, uint8_t* arena, float* spart, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
+    const Dec D(G);
+    const int C = op.cin, noct = C >> 3, S = S_, hw = G.hw;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = SBC2_NTHR / 32;
+    const float* wseg = reinterpret_cast<const float*>(blob + op.w_off);
+    const int n_items = S * noct;
+    // single-sweep layout: the warps are dealt evenly over the (sample, octet) items, each warp keeps its chunk of pixels
+    // (<= JMAX per lane) in registers across the two statistics phases and the normalisation
+    constexpr int JMAX = 6;
+    const int wpi = n_items <= NW ? NW / n_items : 0;                          // warps per item
+    const int nck = wpi > 0 ? min(wpi, (hw + 31) >> 5) : 0;                    // chunks per item actually used
+    const int csz = nck > 0 ? (((hw + nck - 1) / nck + 31) & ~31) : 0;         // pixels per chunk (multiple of 32)
+    if (nck > 0 && csz <= 32 * JMAX && S * C <= 128) {
+        float* part1 = spart;              // [units][8] sums
+        float* part2 = spart + 64;         // [units][8] centred squares
+        float* coefs = spart + 128;        // [S][C][2]
+        const int nchunk = nck;
+        const int nunits = n_items * nchunk;
+        const bool act = warp < nunits;
+        const int li = act ? warp / nchunk : 0, ch = act ? warp - li * nchunk : 0;
+        const int s = li / noct, oct = li - s * noct;
+        const int e0 = ch * csz, e1 = min(hw, e0 + csz);
+        float al = 0.f, ga = 0.f, be = 0.f;            // affine parameters of channel tid (loaded early: L2 latency)
+        if (tid < S * C) { const int c = tid % C; al = wseg[c]; ga = wseg[C + c]; be = wseg[2 * C + c]; }
+        float v[JMAX][8];
+        int qq[JMAX];
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < JMAX; j++) {
+                const int e = min(e0 + lane + 32 * j, e1 - 1);
+                int y, x;
+                D.yx(e, y, x);
+                qq[j] = qof(G, s, y, x);
+                load_f32x8(arena + op.src0, G.slot, oct, qq[j], v[j]);
+            }
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < JMAX; j++) {
+                const bool ok = e0 + lane + 32 * j < e1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k] += ok ? v[j][k] : 0.f;
+            }
+            warp_sum8(a);
+            if (lane < 8) part1[warp * 8 + lane] = a[lane];
+        }
+        __syncthreads();
+        float* cmean = spart + 384;        // [S][C] per-channel means
+        if (tid < S * C) {
+            const int it = tid >> 3, k = tid & 7;       // item = (sample, octet): tid = (s * noct + oct) * 8 + k = s * C + c
+            float t = 0.f;
+            for (int c2 = 0; c2 < nchunk; c2++) t += part1[(it * nchunk + c2) * 8 + k];
+            cmean[tid] = t * inv_hw0(hw);
+        }
+        __syncthreads();
+        if (act) {
+            float mean[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) mean[k] = cmean[li * 8 + k];
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < JMAX; j++) {
+                const bool ok = e0 + lane + 32 * j < e1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const float d = v[j][k] - mean[k]; a[k] += ok ? d * d : 0.f; }
+            }
+            warp_sum8(a);
+            if (lane < 8) part2[warp * 8 + lane] = a[lane];
+        }
+        __syncthreads();
+        if (tid < S * C) {     // cross-channel statistics of the per-channel means + the affine: out = ELU(x * cs + csh)
+            const int ss = tid / C;
+            const float ih = inv_hw0(hw);
+            const float* cm = cmean + ss * C;
+            float m0 = 0.f, m1 = 0.f, m2s = 0.f, m3 = 0.f;
+            for (int k = 0; k < C; k += 4) { m0 += cm[k]; m1 += cm[k + 1]; m2s += cm[k + 2]; m3 += cm[k + 3]; }
+            const float m = ((m0 + m1) + (m2s + m3)) / (float)C;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            for (int k = 0; k < C; k += 4) {
+                const float d0 = cm[k] - m, d1 = cm[k + 1] - m, d2 = cm[k + 2] - m, d3 = cm[k + 3] - m;
+                v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
+            }
+            const float vv = ((v0 + v1) + (v2 + v3)) / (float)(C - 1);
+            const float mean = cmean[tid];
+            const int it = tid >> 3, k = tid & 7;
+            float m2 = 0.f;
+            for (int c2 = 0; c2 < nchunk; c2++) m2 += part2[(it * nchunk + c2) * 8 + k];
+            const float cs = ga * rsqrtf(m2 * ih + 1e-5f);
+            const float csh = fmaf(ga, (mean - m) * rsqrtf(vv + 1e-5f) * al, be);
+            coefs[tid * 2] = cs;
+            coefs[tid * 2 + 1] = fmaf(-mean, cs, csh);
+        }
+        __syncthreads();
+        if (act) {
+            float4 cf[4];
+            const float4* cp = reinterpret_cast<const float4*>(coefs + (s * C + oct * 8) * 2);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) cf[k2] = cp[k2];
+#pragma unroll
+            for (int j = 0; j < JMAX; j++) {
+                if (e0 + lane + 32 * j >= e1) continue;
+                float o[8];
+#pragma unroll
+                for (int k2 = 0; k2 < 4; k2++) {
+                    o[2 * k2] = elu(fmaf(v[j][2 * k2], cf[k2].x, cf[k2].y));
+                    o[2 * k2 + 1] = elu(fmaf(v[j][2 * k2 + 1], cf[k2].z, cf[k2].w));
+                }
+                store_sp16(arena + op.elu16, G.slot, oct, qq[j], o);
+            }
+        }
+        return;
+    }
+    op_norm_elu_general(op, S_, blob, arena, spart, tid);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // conv op (warp-specialised; see the header comment)
 // ---------------------------------------------------------------------------------------------------------
 struct Pipe {
     uint32_t sfull_k, sempty_k;     // next parity per staging barrier (bit b)
-    uint32_t acc_n;                 // accumulator slots handed out so far (all roles count alike)
+    uint32_t tfull_k, tempty_k;     // next parity per accumulator barrier (bit a)
     uint32_t conv_n;                // convs executed so far (weight buffer = conv_n & 1)
 };
 
@@ -545,15 +667,15 @@ struct Pipe {
 // epilogue of one conv for the 4 epilogue warps, NCH = cout8 / 8 channel octets per pixel (compile-time: no runtime
 // indexed register arrays).  Warp w owns TMEM lanes 32w .. 32w+31 = pixels m0 + 32w + lane.
 template <int NCH>
-__device__ __forceinline__ void conv_epilogue(const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, const uint8_t* wb,
-                                              uint64_t* tfull, uint64_t* tempty, uint32_t tmem, uint32_t acc_n0, int T,
-                                              int warp, int lane, long long* tr) {
-    const sbc2::Geo& G = L.geo[op.gs];
+__device__ __forceinline__ uint32_t conv_epilogue(const sbc2::Op& op, const int S_, const int dbg, uint8_t* arena, const uint8_t* wb,
+                                              uint64_t* tfull, uint64_t* tempty, uint32_t tmem, uint32_t tfull_k, int T,
+                                              int npart, int span, int warp, int lane, long long* tr) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const float* bias = op.bias_rel >= 0 ? reinterpret_cast<const float*>(wb + op.bias_rel) : nullptr;
     const int slot = G.slot, cout8 = NCH * 8;
     const float us = op.unscale;
     const int flags = op.flags, dst32 = op.dst32, acc32 = op.acc32, raw16 = op.raw16, elu16 = op.elu16, elu32 = op.elu32;
-    const bool has_acc = acc32 >= 0 && !(L.dbg & 4);
+    const bool has_acc = acc32 >= 0 && !(dbg & 4);
     const int qbase = G.lead + warp * 32 + lane;
     float accn[NCH][8];                           // residual values of the tile ahead (issued one tile early: L2 latency)
     if (has_acc) {
@@ -561,11 +683,12 @@ __device__ __forceinline__ void conv_epilogue(const sbc2::Op& op, const Sbc2Laun
         for (int c = 0; c < NCH; c++) load_f32x8(arena + acc32, slot, c, qbase, accn[c]);
     }
     for (int t = 0; t < T; t++) {
-        const uint32_t n = acc_n0 + (uint32_t)t, a = n % SBC2_NACC;
+        const uint32_t a = (uint32_t)(t * span) & (SBC2_NACC - 1);
         const int q = qbase + t * sbc2::TILE_M;
-        const int px = pix_of(G, L.S, q);
+        const int px = pix_of(G, S_, q);
         if (warp == 0) SBC2_TR(2, t, 0);
-        mbar_wait(&tfull[a], (n / SBC2_NACC) & 1u);
+        mbar_wait(&tfull[a], (tfull_k >> a) & 1u);
+        tfull_k ^= 1u << a;
         if (warp == 0) SBC2_TR(2, t, 1);
         tc_fence_after();
         const uint32_t taddr = tmem + a * 64u + ((uint32_t)(warp * 32) << 16);
@@ -575,12 +698,20 @@ __device__ __forceinline__ void conv_epilogue(const sbc2::Op& op, const Sbc2Laun
             tmem_ld8(taddr + (uint32_t)(c * 8), hi);
             tmem_ld8(taddr + (uint32_t)(cout8 + c * 8), lo);
             tmem_ld_wait();
+            for (int p = 1; p < npart; p++) {     // split-K partial accumulators (independent MMA chains)
+                float h2[8], l2[8];
+                tmem_ld8(taddr + (uint32_t)(p * 2 * cout8 + c * 8), h2);
+                tmem_ld8(taddr + (uint32_t)(p * 2 * cout8 + cout8 + c * 8), l2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 8; k++) { hi[k] += h2[k]; lo[k] += l2[k]; }
+            }
             if (c == NCH - 1) {                   // every column of this slot is in registers: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[a]);
             }
-            if (L.dbg & 4) continue;
+            if (dbg & 4) continue;
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = fmaf(hi[k] + lo[k], us, bias ? bias[c * 8 + k] : 0.f);
             if (flags & sbc2::F_COMPACT) {     // network output: couts (0,1) = (re, im) of element px
@@ -613,11 +744,26 @@ __device__ __forceinline__ void conv_epilogue(const sbc2::Op& op, const Sbc2Laun
         }
         if (warp == 0) SBC2_TR(2, t, 2);
     }
+    return tfull_k;
 }
 
 // i = op index (warp-uniform: the per-op constants in sbc2_c_conv are read through it)
-__device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const Sbc2Launch& L, uint8_t* arena, uint8_t* smem,
-                                        uint64_t* bars, uint32_t tmem, Pipe& P, int tid, bool prefetch_next, long long* trace) {
+struct ConvEnv { const uint8_t* blob; int wmax, dbg, S; };     // the launch constants a conv needs
+// The pipeline state crosses the call boundary packed in ONE register (structs travel through the stack, and local
+// memory is an L2 round trip here): bits 0-3 sfull_k, 4-7 sempty_k, 8-11 tfull_k, 12-15 tempty_k, 16-31 conv_n.
+__device__ __forceinline__ uint32_t pipe_pack(const Pipe& P) {
+    return (P.sfull_k & 15u) | ((P.sempty_k & 15u) << 4) | ((P.tfull_k & 15u) << 8) | ((P.tempty_k & 15u) << 12) | (P.conv_n << 16);
+}
+__device__ __forceinline__ Pipe pipe_unpack(uint32_t v) {
+    Pipe P;
+    P.sfull_k = v & 15u; P.sempty_k = (v >> 4) & 15u; P.tfull_k = (v >> 8) & 15u; P.tempty_k = (v >> 12) & 15u; P.conv_n = v >> 16;
+    return P;
+}
+__device__ __forceinline__ uint32_t op_conv(const int i, const sbc2::Op& op, const uint8_t* blob, const int wmax, const int dbg_, const int S_,
+                                         uint8_t* arena, uint8_t* smem, uint64_t* bars, uint32_t tmem, uint32_t pipe, int tid,
+                                         bool prefetch_next, long long* trace) {
+    Pipe P = pipe_unpack(pipe);
+    const ConvEnv L{blob, wmax, dbg_, S_};
     long long* tr = (trace && (tid & 31) == 0) ? trace : nullptr;
     uint64_t* sfull = bars;            // [4]
     uint64_t* sempty = bars + 4;       // [4]
@@ -628,10 +774,10 @@ __device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const S
     const uint32_t wslot = P.conv_n & 1u, wpar = (P.conv_n >> 1) & 1u;
     uint8_t* wb = smem + (size_t)wslot * L.wmax;
     uint8_t* stage = smem + 2 * (size_t)L.wmax;
-    const sbc2::Geo& G = L.geo[op.gs];
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const int T = G.T;                                  // == op.T
     const int4 cc = sbc2_c_conv[i];                     // uniform: list base, entries, idesc, ring depth
-    const int ns = cc.w;
+    const int ns = cc.w & 0xFF, npart = (cc.w >> 8) & 0xFF, span = (cc.w >> 16) & 0xFF;
     const int nsub0 = op.nsub0, nsub1 = op.nsub1, sps = op.sps;
     const uint32_t stage_bytes = (uint32_t)(nsub0 + nsub1) * (uint32_t)sps;
 
@@ -670,17 +816,18 @@ __device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const S
         // ---------------- MMA issuer: converged warp, uniform-datapath descriptors, one elected lane issues ----------------
         mbar_wait(&wfull[wslot], wpar);
         const uint32_t wb16 = smem_u32(wb) >> 4;
-        const uint32_t idesc = (uint32_t)cc.z;
+        const uint32_t idesc = (uint32_t)cc.z, pmask = (uint32_t)npart - 1u, ncol = (uint32_t)op.N;
         const int n_mma = (L.dbg & 1) ? 0 : cc.y;
         const uint32_t st16 = smem_u32(stage) >> 4, sbytes16 = stage_bytes >> 4;
         for (int t = 0; t < T; t++) {
             const int b = t & (ns - 1);
-            const uint32_t n = P.acc_n + (uint32_t)t, a = n % SBC2_NACC;
+            const uint32_t a = (uint32_t)(t * span) & (SBC2_NACC - 1);
             SBC2_TR(1, t, 0);
             mbar_wait(&sfull[b], (P.sfull_k >> b) & 1u);
             SBC2_TR(1, t, 1);
             P.sfull_k ^= 1u << b;
-            mbar_wait(&tempty[a], ((n / SBC2_NACC) & 1u) ^ 1u);
+            mbar_wait(&tempty[a], (P.tempty_k >> a) & 1u);
+            P.tempty_k ^= 1u << a;
             SBC2_TR(1, t, 2);
             tc_fence_after();
             const uint32_t sb16 = st16 + (uint32_t)b * sbytes16;
@@ -691,16 +838,16 @@ __device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const S
 #pragma unroll 4
                     for (int k = 0; k < n_mma; k++) {
                         const uint2 e = cl[k];
-                        umma_f16(td, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16), ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16),
-                                 idesc, k > 0 ? 1u : 0u);
+                        umma_f16(td + ((uint32_t)k & pmask) * ncol, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16),
+                                 ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16), idesc, k >= npart ? 1u : 0u);
                     }
                 } else {
                     const uint2* list = reinterpret_cast<const uint2*>(wb + op.mma_rel);
 #pragma unroll 2
                     for (int k = 0; k < n_mma; k++) {
                         const uint2 e = list[k];
-                        umma_f16(td, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16), ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16),
-                                 idesc, k > 0 ? 1u : 0u);
+                        umma_f16(td + ((uint32_t)k & pmask) * ncol, ((uint64_t)0x4008u << 32) | (uint64_t)(e.x + sb16),
+                                 ((uint64_t)0x4008u << 32) | (uint64_t)(e.y + wb16), idesc, k >= npart ? 1u : 0u);
                     }
                 }
                 umma_commit(&sempty[b]);     // the stage may be refilled once these MMAs have read it
@@ -712,12 +859,12 @@ __device__ __forceinline__ void op_conv(const int i, const sbc2::Op& op, const S
     } else {
         mbar_wait(&wfull[wslot], wpar);      // the bias lives in the parameter segment
         const int nch = op.cout8 >> 3;
-        if (nch == 1) conv_epilogue<1>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
-        else if (nch == 2) conv_epilogue<2>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
-        else conv_epilogue<4>(op, L, arena, wb, tfull, tempty, tmem, P.acc_n, T, warp, lane, tr);
+        if (nch == 1) P.tfull_k = conv_epilogue<1>(op, L.S, L.dbg, arena, wb, tfull, tempty, tmem, P.tfull_k, T, npart, span, warp, lane, tr);
+        else if (nch == 2) P.tfull_k = conv_epilogue<2>(op, L.S, L.dbg, arena, wb, tfull, tempty, tmem, P.tfull_k, T, npart, span, warp, lane, tr);
+        else P.tfull_k = conv_epilogue<4>(op, L.S, L.dbg, arena, wb, tfull, tempty, tmem, P.tfull_k, T, npart, span, warp, lane, tr);
     }
-    P.acc_n += (uint32_t)T;
-    P.conv_n++;
+    P.conv_n = (P.conv_n + 1u) & 0xFFFFu;      // only its two low bits matter (weight buffer, barrier parity)
+    return pipe_pack(P);
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
@@ -734,6 +881,84 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
 
 }  // namespace sbc2k
 
+// Everything that follows one network evaluation of a group: the score output (forward mode) or the data-consistency
+// gradient, Langevin update and NMSE (test_score.py:157-170).  Out of line: the main loop stays small and spill free.
+__device__ __forceinline__ uint32_t after_network(const Sbc2Launch& L, uint8_t* arena, uint8_t* smem, uint64_t* bars, const SbcStepScalars* s_sc,
+                                               const float* s_hnorm, float* s_red, const int b0, const int gs, const int lvl, const int nsteps,
+                                               const int conv_par, uint32_t tail_par, const int tid) {
+    using namespace sbc2k;
+    const int S = L.S, Nt = L.Nt, Nr = L.Nr, ne = Nt * Nr;
+    if (L.mode == 0) {
+        for (int s = 0; s < S && b0 + s < L.B; s++) {   // score = net / sigmas[y]   (ncsnv2.py:295-298)
+            const int b = b0 + s;
+            long long lab = L.labels ? L.labels[b] : 0;
+            if (lab < 0) lab = 0;
+            if (lab >= L.n_sigmas) lab = L.n_sigmas - 1;
+            const float sg = L.sigmas[lab];
+            const float2* net = reinterpret_cast<const float2*>(arena + L.out_off) + (size_t)s * ne;
+            float* o = L.fout + (size_t)b * L.channels * ne;
+            for (int e = tid; e < ne; e += SBC2_NTHR) {
+                const float2 v = net[e];
+                o[e] = v.x / sg;
+                o[ne + e] = v.y / sg;
+            }
+        }
+    } else {
+        // data-consistency residual P x - y, gradient, Langevin update and NMSE, sample by sample.  The state x, the
+        // residual, Y (staging ring, idle now) and P (the weight buffer that is not holding the prefetched first
+        // conv) are staged in shared memory: the two complex matrix products read each operand ~Nt / ~Np times.
+        const size_t pbytes = (size_t)L.Np * Nt * 8, ybytes = (size_t)L.Np * Nr * 8;
+        const bool staged = pbytes <= (size_t)L.wmax && (size_t)ne * 8 + 2 * ybytes <= (size_t)L.stage_bytes &&
+                            ((reinterpret_cast<uintptr_t>(L.P) & 15) == 0);
+        float* xs = reinterpret_cast<float*>(smem + 2 * (size_t)L.wmax);
+        float* rs = xs + (size_t)ne * 2;
+        float* ys = rs + (size_t)L.Np * Nr * 2;
+        float* ps = reinterpret_cast<float*>(smem + (size_t)((uint32_t)conv_par ^ 1u) * L.wmax);
+        for (int s = 0; s < S && b0 + s < L.B; s++) {
+            const int b = b0 + s;
+            int st_last = nsteps - 1;
+            if (L.stop_step) { const int st = L.stop_step[b]; st_last = min(max(st, 0), nsteps - 1); }
+            if (gs > st_last) continue;                        // this sample stopped early
+            float* ax = reinterpret_cast<float*>(arena + L.x_off) + (size_t)s * ne * 2;
+            const float* net = reinterpret_cast<const float*>(arena + L.out_off) + (size_t)s * ne * 2;
+            const float* Pm = L.P + (size_t)b * L.Np * Nt * 2;
+            const float* Ym = L.Y + (size_t)b * L.Np * Nr * 2;
+            const float* Hc = L.Hor ? L.Hor + (size_t)b * ne * 2 : nullptr;
+            const float* en = L.ext_noise ? L.ext_noise + ((size_t)gs * L.B + b) * ne * 2 : nullptr;
+            const unsigned long long sid = L.sample_ids ? L.sample_ids[b] : (unsigned long long)b;
+            const uint32_t gstep = (uint32_t)(lvl * L.steps_each + gs % L.steps_each);
+            float part;
+            if (staged) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bars[18], (uint32_t)pbytes);
+                    bulk_g2s(ps, Pm, (uint32_t)pbytes, &bars[18]);
+                }
+                for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(xs)[e] = reinterpret_cast<const float2*>(ax)[e];
+                for (int e = tid; e < L.Np * Nr; e += SBC2_NTHR) reinterpret_cast<float2*>(ys)[e] = reinterpret_cast<const float2*>(Ym)[e];
+                mbar_wait(&bars[18], tail_par);
+                tail_par ^= 1u;
+                __syncthreads();
+                sbc_dc_residual(xs, rs, ps, ys, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                __syncthreads();
+                part = sbc_langevin_update(xs, net, rs, ps, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(ax)[e] = reinterpret_cast<const float2*>(xs)[e];   // own elements
+            } else {
+                float* res = reinterpret_cast<float*>(arena + L.post_off) + (size_t)s * ne * 2;
+                sbc_dc_residual(ax, res, Pm, Ym, Nt, Nr, L.Np, tid, SBC2_NTHR);
+                __syncthreads();
+                part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
+            }
+            if (L.nmse_log && Hc) {
+                const float tot = block_sum(part, s_red, tid);
+                if (tid == 0) L.nmse_log[(size_t)gs * L.B + b] = tot / s_hnorm[s];
+            } else {
+                __syncthreads();
+            }
+        }
+    }
+    return tail_par;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -747,11 +972,13 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
     // op records are prefetched global -> shared one op ahead (first 40 threads, one word each; the word loaded at the
     // start of op i is stored at its end), so decoding an op never waits on L2
     __shared__ __align__(16) sbc2::Op s_ops[2];
+    __shared__ __align__(16) Sbc2Launch s_L;        // copy of the launch record that out-of-line functions can take by reference
     __shared__ SbcStepScalars s_sc[SBC2_MAXS];
     __shared__ float s_hnorm[SBC2_MAXS];
     __shared__ float s_red[SBC2_NTHR / 32];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int S = L.S;
+    if (tid == 0) s_L = L;
 
     if (tid == 0) {
         for (int i = 0; i < 4; i++) { mbar_init(&bars[i], 1); mbar_init(&bars[4 + i], 1); mbar_init(&bars[8 + i], 1); mbar_init(&bars[12 + i], 4); }
@@ -778,7 +1005,7 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
     const uint32_t tmem = s_tmem;
 
     Pipe P;
-    P.sfull_k = 0u; P.sempty_k = 0xFu; P.acc_n = 0u; P.conv_n = 0u;
+    P.sfull_k = 0u; P.sempty_k = 0xFu; P.tfull_k = 0u; P.tempty_k = 0xFu; P.conv_n = 0u;
     uint32_t tail_par = 0u;   // parity of the tail's bulk-copy barrier (bars[18])
     bool w_pending = false;   // a parameter-segment prefetch is in flight (or landed) for conv number P.conv_n
     const int n_groups = (L.B + S - 1) / S;
@@ -867,21 +1094,29 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                     }
                     // the last conv of the launch must not leave a copy in flight
                     const bool pf = !(i == last_conv && last_step && last_group);
-                    op_conv(i, op, L, arena, smem, bars, tmem, P, tid, pf, (do_prof_all && i == L.trace_op) ? L.prof + L.n_ops + 2 : nullptr);
+#ifndef SBC2_X_NOCONV
+                    P = pipe_unpack(op_conv(i, op, L.blob, L.wmax, L.dbg, S, arena, smem, bars, tmem, pipe_pack(P), tid, pf, (do_prof_all && i == L.trace_op) ? L.prof + L.n_ops + 2 : nullptr));
+#endif
                     w_pending = pf;
                 } else if (L.dbg & 8) {
                 } else if (op.kind == sbc2::K_NORM_ELU) {
-                    op_norm_elu(op, L, arena, spart, tid);
+#ifndef SBC2_X_NONORM
+                    op_norm_elu(op, S, L.blob, arena, spart, tid);
+#endif
                 } else if (op.kind == sbc2::K_MAXPOOL5) {
-                    op_maxpool5(op, L, arena, tid);
+#ifndef SBC2_X_NOMISC
+                    op_maxpool5(op, S, arena, tid);
+#endif
                 } else if (op.kind == sbc2::K_ELU) {
-                    op_elu(op, L, arena, tid);
+                    op_elu(op, S, arena, tid);
                 } else if (op.kind == sbc2::K_UPACC) {
-                    op_upacc(op, L, arena, tid);
+#ifndef SBC2_X_NOMISC
+                    op_upacc(op, S, arena, tid);
+#endif
                 } else if (op.kind == sbc2::K_POOL2) {
-                    op_pool2(op, L, arena, tid);
+                    op_pool2(op, S, arena, tid);
                 } else if (op.kind == sbc2::K_AFFINE) {
-                    op_affine(op, L, arena, tid);
+                    op_affine(op, S, arena, tid);
                 }
                 if (op.fence_after) fence_proxy_async();      // generic-proxy stores -> visible to the next conv's bulk copies
                 if (tid < 40) reinterpret_cast<int*>(&s_ops[(opc + 1u) & 1u])[tid] = pend;
@@ -890,74 +1125,9 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
             if (do_prof) L.prof[L.n_ops] = clock64();
 
             // ---------------- after the network ----------------
-            if (L.mode == 0) {
-                for (int s = 0; s < S && b0 + s < L.B; s++) {   // score = net / sigmas[y]   (ncsnv2.py:295-298)
-                    const int b = b0 + s;
-                    long long lab = L.labels ? L.labels[b] : 0;
-                    if (lab < 0) lab = 0;
-                    if (lab >= L.n_sigmas) lab = L.n_sigmas - 1;
-                    const float sg = L.sigmas[lab];
-                    const float2* net = reinterpret_cast<const float2*>(arena + L.out_off) + (size_t)s * ne;
-                    float* o = L.fout + (size_t)b * L.channels * ne;
-                    for (int e = tid; e < ne; e += SBC2_NTHR) {
-                        const float2 v = net[e];
-                        o[e] = v.x / sg;
-                        o[ne + e] = v.y / sg;
-                    }
-                }
-            } else {
-                // data-consistency residual P x - y, gradient, Langevin update and NMSE, sample by sample.  The state x, the
-                // residual, Y (staging ring, idle now) and P (the weight buffer that is not holding the prefetched first
-                // conv) are staged in shared memory: the two complex matrix products read each operand ~Nt / ~Np times.
-                const size_t pbytes = (size_t)L.Np * Nt * 8, ybytes = (size_t)L.Np * Nr * 8;
-                const bool staged = pbytes <= (size_t)L.wmax && (size_t)ne * 8 + 2 * ybytes <= (size_t)L.stage_bytes &&
-                                    ((reinterpret_cast<uintptr_t>(L.P) & 15) == 0);
-                float* xs = reinterpret_cast<float*>(smem + 2 * (size_t)L.wmax);
-                float* rs = xs + (size_t)ne * 2;
-                float* ys = rs + (size_t)L.Np * Nr * 2;
-                float* ps = reinterpret_cast<float*>(smem + (size_t)((P.conv_n & 1u) ^ 1u) * L.wmax);
-                for (int s = 0; s < S && b0 + s < L.B; s++) {
-                    const int b = b0 + s;
-                    int st_last = nsteps - 1;
-                    if (L.stop_step) { const int st = L.stop_step[b]; st_last = min(max(st, 0), nsteps - 1); }
-                    if (gs > st_last) continue;                        // this sample stopped early
-                    float* ax = reinterpret_cast<float*>(arena + L.x_off) + (size_t)s * ne * 2;
-                    const float* net = reinterpret_cast<const float*>(arena + L.out_off) + (size_t)s * ne * 2;
-                    const float* Pm = L.P + (size_t)b * L.Np * Nt * 2;
-                    const float* Ym = L.Y + (size_t)b * L.Np * Nr * 2;
-                    const float* Hc = L.Hor ? L.Hor + (size_t)b * ne * 2 : nullptr;
-                    const float* en = L.ext_noise ? L.ext_noise + ((size_t)gs * L.B + b) * ne * 2 : nullptr;
-                    const unsigned long long sid = L.sample_ids ? L.sample_ids[b] : (unsigned long long)b;
-                    const uint32_t gstep = (uint32_t)(lvl * L.steps_each + gs % L.steps_each);
-                    float part;
-                    if (staged) {
-                        if (tid == 0) {
-                            mbar_expect_tx(&bars[18], (uint32_t)pbytes);
-                            bulk_g2s(ps, Pm, (uint32_t)pbytes, &bars[18]);
-                        }
-                        for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(xs)[e] = reinterpret_cast<const float2*>(ax)[e];
-                        for (int e = tid; e < L.Np * Nr; e += SBC2_NTHR) reinterpret_cast<float2*>(ys)[e] = reinterpret_cast<const float2*>(Ym)[e];
-                        mbar_wait(&bars[18], tail_par);
-                        tail_par ^= 1u;
-                        __syncthreads();
-                        sbc_dc_residual(xs, rs, ps, ys, Nt, Nr, L.Np, tid, SBC2_NTHR);
-                        __syncthreads();
-                        part = sbc_langevin_update(xs, net, rs, ps, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
-                        for (int e = tid; e < ne; e += SBC2_NTHR) reinterpret_cast<float2*>(ax)[e] = reinterpret_cast<const float2*>(xs)[e];   // own elements
-                    } else {
-                        float* res = reinterpret_cast<float*>(arena + L.post_off) + (size_t)s * ne * 2;
-                        sbc_dc_residual(ax, res, Pm, Ym, Nt, Nr, L.Np, tid, SBC2_NTHR);
-                        __syncthreads();
-                        part = sbc_langevin_update(ax, net, res, Pm, Hc, en, s_sc[s], L.seed, sid, gstep, Nt, Nr, L.Np, tid, SBC2_NTHR);
-                    }
-                    if (L.nmse_log && Hc) {
-                        const float tot = block_sum(part, s_red, tid);
-                        if (tid == 0) L.nmse_log[(size_t)gs * L.B + b] = tot / s_hnorm[s];
-                    } else {
-                        __syncthreads();
-                    }
-                }
-            }
+#ifndef SBC2_X_NOTAIL
+            tail_par = after_network(s_L, arena, smem, bars, s_sc, s_hnorm, s_red, b0, gs, lvl, nsteps, (int)(P.conv_n & 1u), tail_par, tid);
+#endif
             __syncthreads();
             if (do_prof) L.prof[L.n_ops + 1] = clock64();
         }
