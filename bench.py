@@ -1,21 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- headline metric of BASELINE.json: full-ALD channel-estimates/sec on B200.
 
-Workload (config[1], "CDL-C Fig-5c curve, batch=256, full sigma schedule, 1xB200"): one *step* is one
-pass of the hot path over one batch of 256 synthetic CDL-shaped 16x64 channels (Np = 38 pilots, SNR
-points of the Fig-5c sweep spread over the batch), every one taken through the complete schedule of
-2311 sigma levels x 3 Langevin steps = 6933 fused network evaluations + updates, random-init ngf=8
-weights of the shipped architecture (data: synthetic).  Under torchrun each rank runs its own batch of
-256 (weak scaling, no data-path collective) and the per-rank NMSE logs are all-gathered over NCCL once
-at the end of the step.
+A *step* is one pass of the hot path (one fused launch of the annealed-Langevin kernel through the C ABI) over one batch
+of synthetic CDL-shaped channels taken through the sigma schedule: per level 3 x (NCSNv2Deepest forward + data-consistency
+gradient + Langevin update + Philox noise + NMSE), random-init ngf=8 weights of the shipped architecture (data: synthetic).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--levels L]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5] [--engine auto|1|2]
+                  [--batch B] [--levels L] [--no-extra]
 
-`--levels` (default: full 2311) exists for quick functional runs only; the reported line always states
-the schedule it ran.  `--impl reference` times the CPU restatement of the reference path (the oracle
-port; the reference itself is Python-on-torch-CUDA and cannot travel to the GPU box) on the host cores.
+Workloads (BASELINE.json `configs`):
+  2 (default, the headline): "CDL-C Fig-5c curve, batch=256, full sigma schedule, 1xB200" -- 256 channels per GPU, 17 SNR
+    points spread over the batch, 2311 levels x 3 steps.  Weak scaling: every rank runs its own 256.
+  3: "SNR sweep -10..30 dB x 512 realisations, batch=4096" -- one launch of B=4096 per GPU with a per-sample noise_var.
+  4: "tune_hparams_score alpha x beta grid" -- a FIXED total of 20 400 trajectories (4 alpha x 3 beta x 17 SNR x 100
+    channels) sharded over the ranks: strong scaling.
+  5: "Nt=128 Nr=32, batch=8192" -- 8192 trajectories per GPU at 128x32 (Np=76), weak scaling.
+Configs 3-5 take minutes per full-schedule step; when they ride along with the default run (`extra`) they are timed on a
+truncated schedule (`levels_run`), which the line states -- the per-level cost does not depend on the level.
+
+Engines: 1 = fused shared-memory-arena kernel on mma.sync 3xTF32 (`tf32x3`); 2 = tcgen05 / TMEM kernel with fp16 hi/lo
+split operands (`fp16x2`).  Both are fp32-equivalent (forward error ~2e-6 against the reference).  `auto` picks the
+engine that is faster for the workload (measured: engine 1 for one-wave batches, engine 2 from ~2000 trajectories per GPU).
+`--impl reference` times the CPU restatement of the reference path (the oracle port; the reference itself is Python on
+torch-CUDA and cannot travel to the GPU box) on the host cores.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -30,21 +40,52 @@ sys.path.insert(0, REPO)
 
 SIGMA_END = 2.599515446446343e-4
 NUM_LEVELS, STEPS_EACH = 2311, 3
-NT, NR, NP = 64, 16, 38
 SNR_RANGE = np.arange(-10, 32.5, 2.5)           # test_score.py:72
 ALPHA_STEP, BETA = 3e-11, 0.01                  # test_score.py:46-48
 METRIC = "channel-estimates/sec (full ALD, 16x64 CDL-C)"
+ENGINE_PRECISION = {1: "tf32x3", 2: "fp16x2"}
+# HBM traffic of one launch, from the ncu captures committed under profiles/ (dram__bytes_read + write):
+# bytes = fixed + per_level * levels at the captured batch; scaled linearly with the batch.
+TRAFFIC = {1: {"batch": 256, "fixed": 9.5e6, "per_level": 0.15e6, "src": "profiles/r02_ncu_engine1_raw.txt"},
+           2: {"batch": 256, "fixed": 0.36e9, "per_level": 0.26e6, "src": "profiles/r02_ncu_engine2_raw.txt"}}
 
 
-def make_batch(B, rank=0):
+def workload(cfg, world, rank, batch=None):
+    """(B_local, Nt, Nr, Np, description, scaling, global_batch)"""
+    if cfg == 2:
+        B = batch or 256
+        return B, 64, 16, 38, "Fig-5c CDL-C synthetic, batch=%d per GPU, 17 SNR points spread over the batch" % B, "weak", B * world
+    if cfg == 3:
+        B = batch or 4096
+        return B, 64, 16, 38, "SNR sweep -10..30 dB x 512 realisations in launches of batch=%d per GPU, per-sample noise_var" % B, "weak", B * world
+    if cfg == 4:
+        total = batch or 20400
+        per = (total + world - 1) // world
+        lo = min(rank * per, total)
+        B = min(lo + per, total) - lo
+        return B, 64, 16, 38, "tune_hparams_score grid: 4 alpha x 3 beta x 17 SNR x 100 channels = %d trajectories in total, sharded" % total, "strong", total
+    if cfg == 5:
+        B = batch or 8192
+        return B, 128, 32, 76, "synthetic CDL mix Nt=128 Nr=32 Np=76, batch=%d per GPU" % B, "weak", B * world
+    raise ValueError(cfg)
+
+
+def make_batch(B, Nt, Nr, Np, rank=0, cfg=2):
     from score_based_channels_b200 import synth
-    H = synth.cdl_like_channels(B, NT, NR, seed=4321 + 100000 * rank)
-    P = synth.qpsk_pilots(B, NT, NP, seed=1234 + rank)
+    nuniq = min(B, 512)                                   # channel values do not change the work: tile a set of 512
+    H = np.resize(synth.cdl_like_channels(nuniq, Nt, Nr, seed=4321 + 100000 * rank), (B, Nt, Nr))
+    P = np.resize(synth.qpsk_pilots(nuniq, Nt, Np, seed=1234 + rank), (B, Np, Nt))
     snr = SNR_RANGE[np.arange(B) % len(SNR_RANGE)]
-    nv = synth.snr_to_noise_var(snr, NT).astype(np.float32)
+    nv = synth.snr_to_noise_var(snr, Nt).astype(np.float32)
     Y = synth.received_pilots(P, H, nv, seed=99 + rank)
-    X0 = synth.cn01((B, NT, NR), np.random.default_rng(7 + rank))
-    return P, Y, X0, H, nv
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(7 + rank))
+    al = np.full(B, ALPHA_STEP, np.float32)
+    be = np.full(B, BETA, np.float32)
+    if cfg == 4:                                          # the (alpha, beta) cell of every trajectory
+        cell = (np.arange(B) // (17 * 100)) % 12
+        al = np.asarray([3e-11, 6e-11, 1e-10, 3e-10], np.float32)[cell // 3]
+        be = np.asarray([0.1, 0.01, 0.001], np.float32)[cell % 3]
+    return [np.ascontiguousarray(a) for a in (P, Y, X0, H, nv, al, be)]
 
 
 class ClockSampler:
@@ -96,22 +137,22 @@ def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            d = json.load(f)
-        return d, "measured (MEASURED_PEAKS.json)"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
-def cpu_arm(args, levels, sample_b=None, max_seconds=25.0):
-    """The reference path restated on the CPU (oracle port), all host threads, bounded sample."""
+def cpu_arm(levels, B, max_seconds=25.0, Nt=64, Nr=16, Np=38):
+    """The reference path restated on the CPU (oracle port), all host threads, on a bounded sample of the SAME workload:
+    batch B (the GPU arm's batch), as many sigma levels as fit in `max_seconds`; the per-level cost does not depend on the
+    level, so the full schedule is extrapolated."""
     from oracle import oracle as orc
     from score_based_channels_b200 import params
     sd = params.random_state(8, seed=1)
     cores = os.cpu_count() or 1
     orc.set_num_threads(cores)
-    B = sample_b or max(cores, 8)
-    P, Y, X0, H, nv = make_batch(B)
-    net = orc.OracleNet(sd, 8, NT, NR)
-    kw = dict(noise_var=nv, alpha_step=ALPHA_STEP, beta=BETA, sigma_end=SIGMA_END, steps_each=STEPS_EACH, seed=1)
+    P, Y, X0, H, nv, al, be = make_batch(B, Nt, Nr, Np)
+    net = orc.OracleNet(sd, 8, Nt, Nr)
+    kw = dict(noise_var=nv, alpha_step=al, beta=be, sigma_end=SIGMA_END, steps_each=STEPS_EACH, seed=1)
     t0 = time.perf_counter()
     net.ald(P, Y, X0, H, level_begin=0, level_end=1, **kw)          # warm-up + calibration: 3 steps
     t_cal = (time.perf_counter() - t0) / STEPS_EACH
@@ -119,11 +160,74 @@ def cpu_arm(args, levels, sample_b=None, max_seconds=25.0):
     t0 = time.perf_counter()
     net.ald(P, Y, X0, H, level_begin=0, level_end=n_lvl, **kw)
     dt = time.perf_counter() - t0
-    t_step = dt / (n_lvl * STEPS_EACH)                              # seconds per Langevin step of the sample batch
+    t_step = dt / (n_lvl * STEPS_EACH)                              # seconds per Langevin step of the whole batch
     est_per_s = B / (t_step * levels * STEPS_EACH)
-    return {"value": est_per_s, "unit": "estimates/s", "cores": cores, "kind": "port",
-            "sample": "B=%d x %d levels x %d steps timed (%.1f s), per-step cost extrapolated to %d levels"
-                      % (B, n_lvl, STEPS_EACH, dt, levels), "ms_per_langevin_step": t_step * 1e3}
+    return {"value": est_per_s, "unit": "estimates/s", "cores": cores, "kind": "port", "batch": B,
+            "core_seconds_per_estimate": cores * t_step * levels * STEPS_EACH / B,
+            "sample": "B=%d x %d levels x %d steps timed (%.1f s on %d threads), per-level cost extrapolated to %d levels"
+                      % (B, n_lvl, STEPS_EACH, dt, cores, levels), "ms_per_langevin_step": t_step * 1e3}
+
+
+class Runner:
+    """One (config, engine) workload resident on this rank's GPU."""
+
+    def __init__(self, cfg, engine, levels, world, rank, dev, batch=None):
+        import torch
+        from score_based_channels_b200 import params
+        from score_based_channels_b200.models import make_model
+        self.torch, self.cfg, self.engine, self.levels, self.world, self.rank, self.dev = torch, cfg, engine, levels, world, rank, dev
+        self.B, self.Nt, self.Nr, self.Np, self.desc, self.scaling, self.global_batch = workload(cfg, world, rank, batch)
+        sd = params.random_state(8, seed=1)
+        self.model = make_model(sd, ngf=8, precision=ENGINE_PRECISION[engine], Nt=self.Nt, Nr=self.Nr).to(dev)
+        self.arrays = make_batch(self.B, self.Nt, self.Nr, self.Np, rank, cfg)
+        self.host = [torch.from_numpy(a).pin_memory() for a in self.arrays]
+        self.ids = torch.arange(rank * self.B, (rank + 1) * self.B, dtype=torch.int64, device=dev)
+        self.nsteps_ald = levels * STEPS_EACH
+        self.kw = dict(sigma_end=SIGMA_END, level_begin=0, level_end=levels, steps_each=STEPS_EACH, seed=2026)
+        self.gather = None
+        if world > 1:   # the single collective of the path: the per-rank NMSE logs (equal-sized shards only)
+            self.gather = [torch.empty((self.nsteps_ald, self.B), dtype=torch.float32, device=dev) for _ in range(world)]
+        self.pm = self.model.packed(self.Nt, self.Nr, dev)
+        self.dres = [t.to(dev) for t in self.host]
+        self.out_host = [torch.empty((self.B, self.Nt, self.Nr), dtype=torch.complex64).pin_memory(),
+                         torch.empty((self.nsteps_ald, self.B), dtype=torch.float32).pin_memory()]
+
+    def gpu_step(self, d):
+        from score_based_channels_b200 import sampler
+        import torch.distributed as dist
+        P, Y, X0, H, nv, al, be = d
+        X, nlog = sampler.ald_run(self.model, P, Y, X0, H, noise_var=nv, alpha_step=al, beta=be, sample_ids=self.ids, **self.kw)
+        if self.gather is not None and self.scaling == "weak":
+            dist.all_gather(self.gather, nlog)
+        return X, nlog
+
+    def resident(self):
+        return self.gpu_step(self.dres)
+
+    def e2e(self):
+        d = [t.to(self.dev, non_blocking=True) for t in self.host]
+        X, nlog = self.gpu_step(d)
+        self.out_host[0].copy_(X, non_blocking=True)
+        self.out_host[1].copy_(nlog, non_blocking=True)
+
+    def e2e_host_abi(self):
+        """The C-ABI host-buffer entry point sbc_ald_run_host on numpy arrays (what a non-torch caller uses)."""
+        from score_based_channels_b200 import _lib
+        P, Y, X0, H, nv, al, be = self.arrays
+        if not hasattr(self, "_hx"):
+            self._hx = X0.copy()
+            self._hlog = np.empty((self.nsteps_ald, self.B), np.float32)
+            self._hids = np.arange(self.rank * self.B, (self.rank + 1) * self.B, dtype=np.uint64)
+        np.copyto(self._hx, X0)
+        a = _lib.AldArgs(self.B, self.Nt, self.Nr, self.Np, 0, self.levels, STEPS_EACH, P.ctypes.data, Y.ctypes.data,
+                         self._hx.ctypes.data, H.ctypes.data, nv.ctypes.data, al.ctypes.data, be.ctypes.data, SIGMA_END,
+                         self._hlog.ctypes.data, 2026, self._hids.ctypes.data, None, None, None)
+        _lib.check(_lib.lib().sbc_ald_run_host(self.pm.handle, C.byref(a)), "sbc_ald_run_host")
+
+    def io_bytes(self):
+        h2d = sum(t.numel() * t.element_size() for t in self.host)
+        d2h = sum(t.numel() * t.element_size() for t in self.out_host)
+        return int(h2d), int(d2h)
 
 
 def main():
@@ -132,36 +236,38 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--levels", type=int, default=NUM_LEVELS)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--engine", default="auto", choices=["auto", "1", "2"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--levels", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other precision mode")
-    ap.add_argument("--precision", default=os.environ.get("SBC_PRECISION", "tf32x3"), choices=["tf32x3", "tf32"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other engine / the other configs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    levels = args.levels
-    config = {"workload": "Fig-5c CDL-C synthetic, batch=%d per GPU, %d sigma levels x %d steps, Nt=64 Nr=16 Np=38, "
-                          "17 SNR points spread over the batch" % (args.batch, levels, STEPS_EACH),
-              "global_batch": args.batch * world, "parallelism": "batch-sharded x%d" % world,
-              "l2_policy": "per-step working set is re-streamed weights (1.48 MB) + per-sample state; inputs are "
-                           "rewritten by the H2D copy every step in the e2e leg"}
+    cfg = args.config
+    levels = args.levels or NUM_LEVELS
+    B0, Nt, Nr, Np, desc, scaling, gbatch = workload(cfg, world, rank, args.batch)
+    config = {"workload": "config %d: %s; %d sigma levels x %d steps, Nt=%d Nr=%d Np=%d" % (cfg, desc, levels, STEPS_EACH, Nt, Nr, Np),
+              "global_batch": gbatch, "parallelism": "batch-sharded x%d" % world, "levels_run": levels,
+              "l2_policy": "every timed step rewrites the kernel's whole working set (engine 1: shared memory; engine 2: a "
+                           "per-CTA arena, 115 MB+ per launch > L2) and the e2e legs re-copy all inputs from the host"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         times = []
         for i in range(args.warmup + args.steps):
-            r = cpu_arm(args, levels, max_seconds=12.0)
+            r = cpu_arm(levels, B0 if cfg != 4 else min(B0, 256), max_seconds=12.0, Nt=Nt, Nr=Nr, Np=Np)
             if i >= args.warmup:
                 times.append(r)
         v = float(np.mean([r["value"] for r in times]))
         cb = dict(times[-1]); cb["value"] = v
         line = {"metric": METRIC, "value": v, "unit": "estimates/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "warmup": args.warmup, "ms_per_step": 1e3 * B0 / v, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "impl": "reference", "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": "estimates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -175,27 +281,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
-    from score_based_channels_b200 import params, sampler
-    from score_based_channels_b200.models import make_model
-
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    sd = params.random_state(8, seed=1)
-    model = make_model(sd, ngf=8, precision=args.precision).to(dev)
-    B = args.batch
-    P, Y, X0, H, nv = make_batch(B, rank)
-    host = [torch.from_numpy(a).pin_memory() for a in (P, Y, X0, H, nv)]
-    ids = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int64, device=dev)
-    kw = dict(alpha_step=ALPHA_STEP, beta=BETA, sigma_end=SIGMA_END, level_begin=0, level_end=levels,
-              steps_each=STEPS_EACH, seed=2026)
-    nsteps_ald = levels * STEPS_EACH
-    gather_buf = [torch.empty((nsteps_ald, B), dtype=torch.float32, device=dev) for _ in range(world)] if world > 1 else None
-
-    def gpu_step(dP, dY, dX0, dH, dnv):
-        X, nlog = sampler.ald_run(model, dP, dY, dX0, dH, noise_var=dnv, sample_ids=ids, **kw)
-        if world > 1:      # the single collective of the path: gather the per-rank NMSE logs
-            dist.all_gather(gather_buf, nlog)
-        return X, nlog
 
     def sync():
         if world > 1:
@@ -215,85 +302,95 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    pm = model.packed(NT, NR, dev)
-    launches0 = pm.info().kernel_launches
+    def est_per_s(total_traj, lv, n, ms):
+        return total_traj * n * (lv / NUM_LEVELS) / (ms * 1e-3)      # full-ALD-equivalent estimates per second
 
+    # engine choice: one-wave batches run fastest on engine 1, large batches on engine 2
+    if args.engine == "auto":
+        engine = 1 if (Nt, Nr) == (64, 16) and B0 <= 1024 else 2
+    else:
+        engine = int(args.engine)
+
+    R = Runner(cfg, engine, levels, world, rank, dev, args.batch)
+    launches0 = R.pm.info().kernel_launches
     # ---- leg 1: inputs resident in HBM ("value") ----
-    dres = [t.to(dev) for t in host]
-    res_fn = lambda: gpu_step(*dres)
     for _ in range(args.warmup):
-        res_fn()
+        R.resident()
     with ClockSampler(local_rank) as cs:
-        ms_res = timed(res_fn, args.steps)
+        ms_res = timed(R.resident, args.steps)
     clocks = cs.summary()
-    launches = pm.info().kernel_launches - launches0 - args.warmup
-
+    launches = R.pm.info().kernel_launches - launches0 - args.warmup
     # ---- leg 2: end to end through the public API with HOST buffers ("e2e") ----
-    out_host = [torch.empty((B, NT, NR), dtype=torch.complex64).pin_memory(),
-                torch.empty((nsteps_ald, B), dtype=torch.float32).pin_memory()]
-
-    def e2e_fn():
-        d = [t.to(dev, non_blocking=True) for t in host]
-        X, nlog = gpu_step(*d)
-        out_host[0].copy_(X, non_blocking=True)
-        out_host[1].copy_(nlog, non_blocking=True)
-
     for _ in range(max(1, args.warmup // 3)):
-        e2e_fn()
-    ms_e2e = timed(e2e_fn, args.steps)
-    h2d = sum(t.numel() * t.element_size() for t in host)
-    d2h = sum(t.numel() * t.element_size() for t in out_host)
+        R.e2e()
+    ms_e2e = timed(R.e2e, args.steps)
+    # ---- leg 3: the same through the C-ABI host-buffer call (pageable numpy arrays) ----
+    R.e2e_host_abi()
+    ms_abi = timed(R.e2e_host_abi, max(1, args.steps // 2))
+    n_abi = max(1, args.steps // 2)
+    h2d, d2h = R.io_bytes()
+    total = gbatch if scaling == "strong" else R.B * world
+    value = est_per_s(total, levels, args.steps, ms_res)
+    e2e = est_per_s(total, levels, args.steps, ms_e2e)
+    e2e_abi = est_per_s(total, levels, n_abi, ms_abi)
 
-    total_est = B * world * args.steps * (levels / NUM_LEVELS)      # full-ALD-equivalent estimates
-    value = total_est / (ms_res * 1e-3)
-    e2e = total_est / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant (only) kernel: sbc_ald_kernel, timed inside the long step ----
+    # ---- roofline of the dominant (only) kernel, timed inside the long step ----
     peaks, how = measured_peaks()
-    flops_per_launch = float(pm.prog.conv_flops) * nsteps_ald * B          # dense conv FLOP, reference convention
-    kern_s = ms_res * 1e-3 / args.steps                                    # one launch per step dominates the step
+    info = R.pm.info()
+    flops_per_launch = float(R.pm.conv_flops) * R.nsteps_ald * R.B       # dense conv FLOP, reference convention
+    kern_s = ms_res * 1e-3 / args.steps                                  # one launch per step dominates the step
     achieved = flops_per_launch / kern_s / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    # context for the fraction: this kernel's MMAs are mma.sync TF32, measured at one m16n8k8 per ~12 clk per SM
-    # sub-partition (~683 FLOP/clk/SM, ~199 TFLOP/s per B200), and the fp32-equivalent mode
-    # issues 3 of them per algorithmic MMA
-    sm_clk_ghz = 1.965
-    mma_sync_tf32_peak = (2 * 1024 * 4 / 12.0) * 148 * sm_clk_ghz / 1e3
+    tr = TRAFFIC[engine]
+    traffic = (tr["fixed"] + tr["per_level"] * levels) * R.B / tr["batch"]
+    kernel_name = {1: "sbc_ald_kernel<smem arena, 3xTF32 mma.sync>", 2: "sbc2_ald_kernel (tcgen05.mma kind::f16 hi/lo split, TMEM accumulators)"}[engine]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 11.9e6 if levels == 16 else None,
-                "traffic_note": "ncu dram__bytes_read+write = 11.9 MB for the 16-level launch at B=256 captured in "
-                                "profiles/ (inputs once, log/outputs stay in L2): HBM is idle, the kernel lives in "
-                                "shared memory; not captured for other schedule lengths",
-                "peak_source": how + ", sustained dense bf16",
-                "kernel": "sbc_ald_kernel<smem arena>, conv arithmetic = %s" % args.precision,
-                "executed_mma_tflops": achieved * (3.0 if args.precision == "tf32x3" else 1.0),
-                "mma_sync_tf32_ceiling_tflops": mma_sync_tf32_peak}
+                "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of the ncu capture in %s (fixed + per-level bytes at batch %d), scaled to this "
+                                "launch's batch and schedule" % (tr["src"], tr["batch"]),
+                "peak_source": how + ", sustained dense bf16", "kernel": kernel_name,
+                "algorithmic_flops_per_launch": flops_per_launch, "engine": engine, "group_size": int(info.group_size),
+                "ctas_per_sm": int(info.ctas_per_sm)}
 
-    # ---- the other precision mode, one short timed step (reported, not the headline) ----
-    alt = None
-    if world == 1 and not args.no_alt:
-        ap_name = "tf32" if args.precision == "tf32x3" else "tf32x3"
-        alt_model = make_model(sd, ngf=8, precision=ap_name).to(dev)
-        alt_kw = dict(kw, level_end=min(levels, 96))
-        alt_fn = lambda: sampler.ald_run(alt_model, *dres[:4], noise_var=dres[4], sample_ids=ids, **alt_kw)
-        alt_fn()
-        ms_alt = timed(alt_fn, 2)
-        alt = {"precision": ap_name, "value": B * 2 * (alt_kw["level_end"] / NUM_LEVELS) / (ms_alt * 1e-3),
-               "unit": "estimates/s", "sample": "2 steps of %d levels" % alt_kw["level_end"]}
+    extra = []
+    if not args.no_extra and cfg == 2:
+        # the other engine on the same workload, and configs 3 / 5 on a truncated schedule (see the module docstring)
+        def short(c, e, lv, nrep=2, batch=None):
+            try:
+                r = Runner(c, e, lv, world, rank, dev, batch)
+                r.resident()
+                ms = timed(r.resident, nrep)
+                tot = workload(c, world, rank, batch)[6] if workload(c, world, rank, batch)[5] == "strong" else r.B * world
+                out = {"config": c, "engine": e, "precision": ENGINE_PRECISION[e], "batch_per_gpu": r.B, "levels_run": lv,
+                       "value": est_per_s(tot, lv, nrep, ms), "unit": "estimates/s (full-ALD equivalent)",
+                       "ms_per_step": ms / nrep, "workload": workload(c, world, rank, batch)[4]}
+                del r
+                torch.cuda.empty_cache()
+                return out
+            except Exception as ex:     # an extra must never take the headline line down
+                return {"config": c, "engine": e, "error": str(ex)[:200]}
+        extra.append(short(2, 2 if engine == 1 else 1, min(levels, 96)))
+        extra.append(short(3, 2, min(levels, 12)))
+        extra.append(short(3, 1, min(levels, 12)))
+        extra.append(short(4, 2, min(levels, 6)))
+        extra.append(short(5, 2, min(levels, 3), batch=2368))
+        extra.append(short(5, 1, min(levels, 3), batch=2368))
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_arm(args, levels)
+            cpu = cpu_arm(levels, min(R.B, 256), Nt=Nt, Nr=Nr, Np=Np)
         line = {"metric": METRIC, "value": value, "unit": "estimates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
-                "dtype": {"tf32x3": "tf32x3 (3xTF32 split, fp32-equivalent), f32 accumulate",
-                          "tf32": "tf32 operands, f32 accumulate"}[args.precision],
+                "scaling": scaling, "vs_baseline": None,
+                "dtype": {1: "tf32x3 (3xTF32 split, fp32-equivalent), f32 accumulate",
+                          2: "fp16x2 (fp16 hi/lo split operands, 22 significant bits, fp32-equivalent), f32 accumulate"}[engine],
                 "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e, "unit": "estimates/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu, "alt_precision": alt}
+                "e2e": {"value": e2e, "unit": "estimates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps, "api": "sampler.ald_run on pinned host tensors"},
+                "e2e_host_abi": {"value": e2e_abi, "unit": "estimates/s", "ms_per_step": ms_abi / n_abi,
+                                 "api": "sbc_ald_run_host (C ABI, pageable numpy buffers, preallocated device workspace)"},
+                "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -31,7 +31,7 @@
 #define SBC2_NBARS 24
 #define SBC2_PART_FLOATS 1024      // shared scratch of the norm statistics: 2 x 64 units x 8 channels
 
-#define SBC2_MAX_OPS 320
+#define SBC2_MAX_OPS 1536
 #define SBC2_MAX_MMA 4096
 // Per-op constants of the conv pipeline and every conv's UMMA descriptor list, in constant memory (uploaded by
 // sbc2_launch): indexed by warp-uniform values only, so the MMA issue loop runs on the uniform datapath (ULDC -> UIADD ->
@@ -238,7 +238,7 @@ __device__ __forceinline__ void warp_sum8(float (&v)[8]) {
 __device__ __forceinline__ int pix_of(const sbc2::Geo& G, int S, int q) {
     const uint32_t n = (uint32_t)(q - G.lead);
     const uint32_t s = __umulhi(n, G.mg_pps), r = n - s * (uint32_t)G.pps;
-    const uint32_t y = __umulhi(r, G.mg_wp), x = r - y * (uint32_t)G.wp;
+    const uint32_t y = G.wp == 1 ? r : __umulhi(r, G.mg_wp), x = r - y * (uint32_t)G.wp;     // ceil(2^32 / 1) does not fit 32 bits
     return (q >= G.lead && s < (uint32_t)S && y < (uint32_t)G.h && x < (uint32_t)G.w) ? (int)(s * G.hw + y * G.w + x) : -1;
 }
 
@@ -377,6 +377,34 @@ __device__ __forceinline__ void op_upacc(const sbc2::Op& op, const int S_, uint8
                 for (int k = 0; k < 8; k++) a[u][k] = elu(a[u][k]);
                 store_f32x8(arena + op.elu32, GD.slot, it[u].oct, it[u].q, a[u]);
             }
+        }
+    }
+}
+
+// epilogue of a conv whose input channels were split over several ops (wide nets): the finished sum `src0` gets the
+// outputs a single conv op would have produced (dst32 = v; v += acc32; raw16 = split(v); elu16 / elu32 = ELU(v))
+__device__ __forceinline__ void op_epilogue(const sbc2::Op& op, const int S_, uint8_t* arena, int tid) {
+    const sbc2::Geo& G = sbc2_c_geo[op.gs];
+    const Dec D(G);
+    const int noct = op.cin >> 3, per = S_ * G.hw, n = noct * per;
+    for (int i = tid; i < n; i += SBC2_NTHR) {
+        const Item it = item_of(G, D, i, n, per);
+        float v[8];
+        load_f32x8(arena + op.src0, G.slot, it.oct, it.q, v);
+        if (op.dst32 >= 0) store_f32x8(arena + op.dst32, G.slot, it.oct, it.q, v);
+        if (op.acc32 >= 0) {
+            float o[8];
+            load_f32x8(arena + op.acc32, G.slot, it.oct, it.q, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += o[k];
+            store_f32x8(arena + op.acc32, G.slot, it.oct, it.q, v);
+        }
+        if (op.raw16 >= 0) store_sp16(arena + op.raw16, G.slot, it.oct, it.q, v);
+        if (op.elu16 >= 0 || op.elu32 >= 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = elu(v[k]);
+            if (op.elu16 >= 0) store_sp16(arena + op.elu16, G.slot, it.oct, it.q, v);
+            if (op.elu32 >= 0) store_f32x8(arena + op.elu32, G.slot, it.oct, it.q, v);
         }
     }
 }
@@ -1115,6 +1143,8 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
 #endif
                 } else if (op.kind == sbc2::K_POOL2) {
                     op_pool2(op, S, arena, tid);
+                } else if (op.kind == sbc2::K_EPILOGUE) {
+                    op_epilogue(op, S, arena, tid);
                 } else if (op.kind == sbc2::K_AFFINE) {
                     op_affine(op, S, arena, tid);
                 }

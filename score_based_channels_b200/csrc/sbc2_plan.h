@@ -35,7 +35,7 @@
 
 namespace sbc2 {
 
-enum : int32_t { K_AFFINE = 0, K_CONV = 1, K_NORM_ELU = 2, K_ELU = 3, K_MAXPOOL5 = 4, K_UPACC = 5, K_POOL2 = 6 };
+enum : int32_t { K_AFFINE = 0, K_CONV = 1, K_NORM_ELU = 2, K_ELU = 3, K_MAXPOOL5 = 4, K_UPACC = 5, K_POOL2 = 6, K_EPILOGUE = 7 };
 enum : int32_t { F_COMPACT = 1 };      // conv: couts 0,1 go to the compact (re, im) output buffer
 
 constexpr int TILE_M = 128;            // UMMA M
@@ -264,7 +264,7 @@ class Builder {
         for (size_t i = 0; i < P.ops.size(); i++) {
             Op& o = P.ops[i];
             const R_& r = refs[i];
-            o.src0 = res(r.src0); o.src1 = res(r.src1);
+            o.src0 = res(r.src0, 8 * r.sp0); o.src1 = res(r.src1, 8 * r.sp1);     // first staged plane of each branch
             o.dst32 = (o.flags & F_COMPACT) ? res(r.dst32) : res(r.dst32, r.co0);
             o.acc32 = res(r.acc32, r.co0); o.raw16 = res(r.raw16, r.co0); o.elu16 = res(r.elu16, r.co0);
             o.elu32 = res(r.elu32, r.co0); o.scratch = res(r.scratch);
@@ -299,7 +299,7 @@ class Builder {
 
   private:
     struct T_ { std::string name; int fmt, level, C, born, died; int64_t raw_per_sample; };
-    struct R_ { int src0 = -1, src1 = -1, dst32 = -1, acc32 = -1, raw16 = -1, elu16 = -1, elu32 = -1, scratch = -1, co0 = 0; };
+    struct R_ { int src0 = -1, src1 = -1, dst32 = -1, acc32 = -1, raw16 = -1, elu16 = -1, elu32 = -1, scratch = -1, co0 = 0, sp0 = 0, sp1 = 0; };
     struct LT { int f32 = -1, s16 = -1; int C = 0, level = 0; };   // a logical tensor: optional F32 and SP16 copies
 
     const StateDict& sd;
@@ -340,11 +340,14 @@ class Builder {
     size_t blob_align(size_t a) { while (blob.size() % a) blob.push_back(0); return blob.size(); }
 
     // ---- conv --------------------------------------------------------------------------------------------
-    struct Branch { std::string prefix; int src; int dil; };
+    struct Branch { std::string prefix; int src; int dil; int p0 = 0, p1 = -1; bool bias = true; };   // planes [p0, p1) of src (-1: all)
     struct Outs { int dst32 = -1, acc32 = -1, raw16 = -1, elu16 = -1, elu32 = -1; bool compact = false; };
 
     void conv(std::vector<Branch> br, Outs out) {
         // stage footprint of the merged op; fall back to one op per branch when it exceeds the staging ring
+        bool wide = false;
+        for (auto& b : br) wide = wide || tens[b.src].C / 8 > KMAX_PLANES;
+        if (wide) { conv1(br, out); return; }
         if (br.size() > 1) {
             int nsub = 0, halo = 0;
             for (auto& b : br) {
@@ -384,7 +387,38 @@ class Builder {
         return halo;
     }
 
+    static constexpr int KMAX_PLANES = 4;      // input channels per conv op = 32: bounds the staged window and the B tiles
+
     void conv1(const std::vector<Branch>& br, const Outs& out) {
+        bool wide = false;
+        for (auto& b : br) wide = wide || tens[b.src].C / 8 > KMAX_PLANES;
+        if (!wide) { conv_chunks(br, out); return; }
+        // wide inputs: one op per group of 32 input channels, summed in an F32 temporary; a K_EPILOGUE op then applies the
+        // requested outputs to the finished sum
+        if (out.compact) throw std::runtime_error("compact conv with a wide input is not supported");
+        const auto& w0 = P_(br[0].prefix + ".weight");
+        const int cout = (int)w0.shape[0], lvl = tens[br[0].src].level;
+        const int T = new32((cout + 7) / 8 * 8, lvl, "ks");
+        bool first = true;
+        for (auto& b : br) {
+            const int planes = tens[b.src].C / 8;
+            for (int p0 = 0; p0 < planes; p0 += KMAX_PLANES) {
+                Branch piece = b;
+                piece.p0 = p0; piece.p1 = std::min(planes, p0 + KMAX_PLANES); piece.bias = (p0 == 0);
+                Outs o;
+                if (first) o.dst32 = T; else o.acc32 = T;
+                first = false;
+                conv_chunks({piece}, o);
+            }
+        }
+        Op o = blank(K_EPILOGUE);
+        o.gs = o.gd = lvl; o.cin = o.cout = (cout + 7) / 8 * 8;
+        R_ r; r.src0 = T; r.dst32 = out.dst32; r.acc32 = out.acc32; r.raw16 = out.raw16; r.elu16 = out.elu16; r.elu32 = out.elu32;
+        push(o, r, "epilogue(" + br[0].prefix + ")");
+        rel(T);
+    }
+
+    void conv_chunks(const std::vector<Branch>& br, const Outs& out) {
         const auto& w0 = P_(br[0].prefix + ".weight");
         const int cout = (int)w0.shape[0];
         const int cout8 = std::max(8, (cout + 7) / 8 * 8);
@@ -432,10 +466,11 @@ class Builder {
             const T_& st = tens[b.src];
             if (st.fmt != 1 || st.level != lvl) throw std::runtime_error("conv source must be an SP16 tensor of the op's level: " + b.prefix);
             if (cin > st.C) throw std::runtime_error("conv source has too few channels: " + b.prefix);
-            if (co0 == 0) conv_flops += 2LL * g.h * g.w * cin * k * k * bco;   // dense count, reference convention
-            const int planes = st.C / 8;
+            const int pb = b.p0, pe = b.p1 < 0 ? st.C / 8 : b.p1;     // plane range of this piece
+            if (co0 == 0 && pb == 0) conv_flops += 2LL * g.h * g.w * cin * k * k * bco;   // dense count, reference convention
+            const int planes = pe - pb;
             nsub[bi] = 2 * planes;
-            if (has(b.prefix + ".bias") && true) {
+            if (has(b.prefix + ".bias") && b.bias) {
                 const auto& bt = P_(b.prefix + ".bias");
                 for (int c = 0; c < c8; c++)
                     if (co0 + c < bco) bias[c] += bt.data[co0 + c];
@@ -458,7 +493,7 @@ class Builder {
                     uint16_t* bt = reinterpret_cast<uint16_t*>(tiles.data() + b_off);
                     for (int n = 0; n < c8; n++)
                         for (int kk = 0; kk < 16; kk++) {
-                            const int ci = pair ? (8 * p + kk) : (8 * p + (kk & 7));
+                            const int ci = pair ? (8 * (pb + p) + kk) : (8 * (pb + p) + (kk & 7));
                             const float wv = W_(co0 + n, ci, tap);
                             const uint16_t hi = f32_to_f16(wv);
                             const uint16_t lo = f32_to_f16(wv - f16_to_f32(hi));
@@ -517,10 +552,12 @@ class Builder {
         max_stage = std::max(max_stage, (nsub[0] + nsub[1]) * sps);
         R_ r;
         r.src0 = br[0].src; r.src1 = br.size() > 1 ? br[1].src : -1;
+        r.sp0 = br[0].p0; r.sp1 = br.size() > 1 ? br[1].p0 : 0;
         r.dst32 = out.dst32; r.acc32 = out.acc32; r.raw16 = out.raw16; r.elu16 = out.elu16; r.elu32 = out.elu32; r.co0 = co0;
         std::string nm = br[0].prefix;
         for (size_t i = 1; i < br.size(); i++) nm += "+" + br[i].prefix;
         if (co0 || c8 < (cout_real + 7) / 8 * 8) nm += "[co" + std::to_string(co0) + "]";
+        if (br[0].p1 >= 0) nm += "[ci" + std::to_string(8 * br[0].p0) + "]";
         push(o, r, nm);
     }
 

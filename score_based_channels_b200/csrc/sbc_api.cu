@@ -49,8 +49,22 @@ struct SbcModel {
     SbcGeo geo[SBC_MAX_GEO];
     int n_geo = 0;
     int halo_off[SBC_MAX_GEO] = {0};
+    // grow-only device buffers of the host-buffer entry points (sbc_*_host): allocated once, reused by every call
+    void* hws[16] = {nullptr};
+    size_t hws_cap[16] = {0};
+    void* host_ws(int slot, size_t bytes) {
+        if (bytes > hws_cap[slot]) {
+            cudaFree(hws[slot]);
+            hws[slot] = nullptr; hws_cap[slot] = 0;
+            const size_t want = bytes + bytes / 4 + 256;
+            if (cudaMalloc(&hws[slot], want) != cudaSuccess) return nullptr;
+            hws_cap[slot] = want;
+        }
+        return hws[slot];
+    }
     ~SbcModel() {   // owns its device buffers: every early return of sbc_model_create releases them
         cudaFree(d_ops); cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
+        for (auto p : hws) cudaFree(p);
         delete e2;
     }
 };
@@ -349,8 +363,8 @@ extern "C" int sbc_forward_host(void* handle, const float* x, const int64_t* lab
     if (m->engine == 2) { m->d.channels = m->e2->channels; m->d.Nt = m->e2->Nt; m->d.Nr = m->e2->Nr; m->device = m->e2->device; }
     SBC_CUDA(cudaSetDevice(m->device));
     const size_t n = (size_t)B * m->d.channels * m->d.Nt * m->d.Nr;
-    DevBuf dx, dl, dout;
-    if (dx.alloc(n * 4) || dl.alloc((size_t)B * 8) || dout.alloc(n * 4)) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
+    struct { void* p; } dx{m->host_ws(12, n * 4)}, dl{m->host_ws(13, (size_t)B * 8)}, dout{m->host_ws(14, n * 4)};
+    if (!dx.p || !dl.p || !dout.p) return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
     SBC_CUDA(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
     SBC_CUDA(cudaMemcpy(dl.p, labels, (size_t)B * 8, cudaMemcpyHostToDevice));
     const int64_t st[4] = {(int64_t)m->d.channels * m->d.Nt * m->d.Nr, (int64_t)m->d.Nt * m->d.Nr, m->d.Nr, 1};
@@ -369,7 +383,10 @@ extern "C" int sbc_ald_run_host(void* handle, const sbc_ald_args* a) {
     SBC_CUDA(cudaSetDevice(m->engine == 2 ? m->e2->device : m->device));
     const size_t B = a->B, ne = (size_t)a->Nt * a->Nr, steps = (size_t)(a->level_end - a->level_begin) * a->steps_each;
     const size_t nP = B * a->Np * a->Nt * 8, nY = B * a->Np * a->Nr * 8, nX = B * ne * 8;
-    DevBuf dP, dY, dX, dH, dnv, dal, dbe, dlog, dids, dn, ddb, dst;
+    // device buffers come from the handle's grow-only workspace: no cudaMalloc / cudaFree per call
+    struct Slot { void* p = nullptr; SbcModel* m; int id; int alloc(size_t n) { p = m->host_ws(id, n ? n : 1); return p ? 0 : -1; } };
+    Slot dP{nullptr, m, 0}, dY{nullptr, m, 1}, dX{nullptr, m, 2}, dH{nullptr, m, 3}, dnv{nullptr, m, 4}, dal{nullptr, m, 5}, dbe{nullptr, m, 6},
+        dlog{nullptr, m, 7}, dids{nullptr, m, 8}, dn{nullptr, m, 9}, ddb{nullptr, m, 10}, dst{nullptr, m, 11};
     if (dP.alloc(nP) || dY.alloc(nY) || dX.alloc(nX) || dnv.alloc(B * 4) || dal.alloc(B * 4) || dbe.alloc(B * 4))
         return sbc_fail(SBC_E_NOMEM, "cudaMalloc failed");
     SBC_CUDA(cudaMemcpy(dP.p, a->P, nP, cudaMemcpyHostToDevice));

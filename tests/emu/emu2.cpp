@@ -191,6 +191,29 @@ static void run_op(const Op& op, const Plan& P, const uint8_t* blob, uint8_t* ar
                     }
         break;
     }
+    case K_EPILOGUE:
+        for (int oct = 0; oct < op.cin / 8; oct++)
+            for (int s = 0; s < S; s++)
+                for (int y = 0; y < GS.h; y++)
+                    for (int x = 0; x < GS.w; x++) {
+                        const int q = qof(GS, s, y, x);
+                        float v[8];
+                        load_f32x8(arena + op.src0, GS.slot, oct, q, v);
+                        if (op.dst32 >= 0) store_f32x8(arena + op.dst32, GS.slot, oct, q, v);
+                        if (op.acc32 >= 0) {
+                            float o[8];
+                            load_f32x8(arena + op.acc32, GS.slot, oct, q, o);
+                            for (int k = 0; k < 8; k++) v[k] += o[k];
+                            store_f32x8(arena + op.acc32, GS.slot, oct, q, v);
+                        }
+                        if (op.raw16 >= 0) store_sp16(arena + op.raw16, GS.slot, oct, q, v);
+                        if (op.elu16 >= 0 || op.elu32 >= 0) {
+                            for (int k = 0; k < 8; k++) v[k] = elu_ref(v[k]);
+                            if (op.elu16 >= 0) store_sp16(arena + op.elu16, GS.slot, oct, q, v);
+                            if (op.elu32 >= 0) store_f32x8(arena + op.elu32, GS.slot, oct, q, v);
+                        }
+                    }
+        break;
     case K_POOL2:
         for (int oct = 0; oct < op.cin / 8; oct++)
             for (int s = 0; s < S; s++)

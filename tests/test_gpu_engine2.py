@@ -1,0 +1,255 @@
+"""GPU tests of engine 2 (tcgen05 / TMEM kernel, precision "fp16x2"), through the C ABI.  Forward / ALD parity against the
+reference goldens runs in test_gpu_parity.py (parametrised over the precision modes); here: the kernel against the CPU plan
+emulation tensor by tensor, a model built with plain ctypes and NO Python planner, group-size invariance, the other
+resolutions, lazily conjugated inputs, and the long-horizon trajectory comparisons with the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, REPO
+
+pytestmark = pytest.mark.gpu
+
+from score_based_channels_b200 import _lib, params, sampler, synth  # noqa: E402
+from score_based_channels_b200.models import make_model  # noqa: E402
+
+SIGMA_END = 2.599515446446343e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+def _decode(arena, t, geo, S):
+    G = geo[t.level]
+    h, w, wp, pps, lead, npx = (int(G[i]) for i in (0, 1, 4, 6, 7, 8))
+    raw = arena[t.off:t.off + t.bytes]
+    ss, yy, xx = np.meshgrid(np.arange(S), np.arange(h), np.arange(w), indexing="ij")
+    q = lead + ss * pps + yy * wp + xx
+    res = np.zeros((S, t.C, h, w), np.float32)
+    if t.fmt == 0:
+        a = raw.view(np.float32).reshape(t.C // 4, npx, 4)
+        for c in range(t.C):
+            res[:, c] = a[c // 4, q, c % 4]
+    else:
+        a = raw.view(np.float16).reshape(t.C // 8, 2, npx, 8).astype(np.float32)
+        for c in range(t.C):
+            res[:, c] = a[c // 8, 0, q, c % 8] + a[c // 8, 1, q, c % 8]
+    return res
+
+
+def test_engine2_is_tcgen05_and_two_ctas_per_sm(dev):
+    sd = params.random_state(8, seed=1)
+    m = make_model(sd, ngf=8, precision="fp16x2").to(dev)
+    x = torch.zeros(3, 2, 64, 16, device=dev)
+    m(x, torch.zeros(3, dtype=torch.long, device=dev))
+    info = m.packed(64, 16, dev).info()
+    assert info.engine == 2 and info.ctas_per_sm == 2 and info.threads_per_cta == 192 and info.n_ops > 100
+    assert info.conv_flops_per_forward == 51740672
+
+
+def test_kernel_matches_cpu_plan_emulation_tensor_by_tensor(dev):
+    """Every activation tensor of a forward (no arena reuse, group of 2 samples) against tests/emu/emu2.cpp, which replays
+    each tcgen05.mma from its packed descriptor on the CPU."""
+    import test_emulation2 as T
+    g = np.load(os.path.join(GOLDEN, "forward_ngf8.npz"))
+    sd = params.random_state(8, seed=int(g["wseed"]))
+    m = make_model(sd, ngf=8, precision="fp16x2").to(dev)
+    pm = m.packed(64, 16, dev)
+    S = 2
+    emu = T.Emu2(T.load_emu2(), sd, 8, 64, 16)
+    ab, tens, geo = pm.debug_plan(S, reuse=False)
+    ab2, tens2, geo2 = emu.plan(S, reuse=False)
+    assert ab == ab2 and (geo == geo2).all() and len(tens) == len(tens2)
+    xs = np.ascontiguousarray(g["x"][:S])
+    ea = np.zeros(ab, np.uint8)
+    eo = np.empty_like(xs)
+    assert emu.lib.emu2_forward(emu.h, S, 0, xs.ctypes.data, eo.ctypes.data, ea.ctypes.data, -1) == 0
+    ga = torch.zeros(ab, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().sbc_debug_run(pm.handle, torch.from_numpy(xs).to(dev).data_ptr(), S, 0, ga.data_ptr(), None), "sbc_debug_run")
+    ga = ga.cpu().numpy()
+    worst = 0.0
+    for t in tens:
+        if t.fmt == 2:
+            continue
+        a, b = _decode(ga, t, geo, S), _decode(ea, t, geo, S)
+        err = float(np.abs(a - b).max()) / (float(np.abs(b).max()) + 1e-30)
+        worst = max(worst, err)
+        assert err < 5e-5, (t.name, t.born, err)     # fp32 accumulation order + MUFU vs libm
+    assert worst > 0.0
+
+
+def test_model_built_with_plain_ctypes_and_no_python_planner(dev):
+    """The self-contained C ABI: sbc_model_create_from_state + sbc_forward_host on numpy arrays only."""
+    g = np.load(os.path.join(GOLDEN, "forward_ngf8.npz"))
+    sd = params.random_state(8, seed=int(g["wseed"]))
+    L = C.CDLL(_lib.LIB_PATH)
+
+    class Entry(C.Structure):
+        _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("shape", C.c_void_p), ("ndim", C.c_int32)]
+
+    keep, ents = [], (Entry * len(sd))()
+    for i, (k, v) in enumerate(sd.items()):
+        a = np.ascontiguousarray(v, np.float32)
+        shp = np.asarray(a.shape, np.int64)
+        keep += [a, shp]
+        ents[i] = Entry(k.encode(), a.ctypes.data, shp.ctypes.data, a.ndim)
+    h = C.c_void_p()
+    L.sbc_last_error.restype = C.c_char_p
+    rc = L.sbc_model_create_from_state(ents, len(sd), 8, 64, 16, 2, 0, C.byref(h))
+    assert rc == 0, L.sbc_last_error()
+    x = np.ascontiguousarray(g["x"], np.float32)
+    y = np.ascontiguousarray(g["y"], np.int64)
+    out = np.empty_like(x)
+    L.sbc_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    assert L.sbc_forward_host(h, x.ctypes.data, y.ctypes.data, out.ctypes.data, x.shape[0]) == 0, L.sbc_last_error()
+    for b in range(x.shape[0]):
+        assert _rel(out[b], g["out"][b]) < 2e-5
+    # bit-identical to the torch front end (same library, same plan)
+    m = make_model(sd, ngf=8, precision="fp16x2").to(dev)
+    o2 = m(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)).cpu().numpy()
+    assert np.array_equal(out, o2)
+    L.sbc_model_free.argtypes = [C.c_void_p]
+    L.sbc_model_free(h)
+    # error path: a state dict without a required tensor
+    h2 = C.c_void_p()
+    assert L.sbc_model_create_from_state(ents, 5, 8, 64, 16, 2, 0, C.byref(h2)) != 0
+
+
+def test_group_size_does_not_change_results(dev, monkeypatch):
+    sd = params.random_state(8, seed=1)
+    B, Nt, Nr, Np = 11, 64, 16, 38
+    H = synth.cdl_like_channels(B, Nt, Nr)
+    P = synth.qpsk_pilots(B, Nt, Np)
+    nv = float(synth.snr_to_noise_var(5.0, Nt))
+    Y = synth.received_pilots(P, H, nv)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(3))
+    d = [torch.from_numpy(a).to(dev) for a in (P, Y, X0, H)]
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=SIGMA_END, level_begin=7, level_end=9, steps_each=3, seed=5)
+    outs = []
+    for S in ("1", "2", "4", "8"):
+        monkeypatch.setenv("SBC2_S", S)
+        m = make_model(sd, ngf=8, precision="fp16x2").to(dev)
+        X, nlog = sampler.ald_run(m, *d, **kw)
+        assert m.packed(Nt, Nr, dev).info().group_size == int(S)
+        outs.append((X.cpu().numpy(), nlog.cpu().numpy()))
+    for X, n in outs[1:]:
+        assert np.abs(X - outs[0][0]).max() <= 1e-6 * np.abs(outs[0][0]).max()
+        assert np.allclose(n, outs[0][1], rtol=1e-5)
+
+
+@pytest.mark.parametrize("Nt,Nr", [(24, 8), (128, 32)])
+def test_other_antenna_counts_match_oracle(dev, Nt, Nr):
+    from oracle import oracle as orc
+    sd = params.random_state(8, seed=4)
+    m = make_model(sd, ngf=8, precision="fp16x2", Nt=Nt, Nr=Nr).to(dev)
+    rng = np.random.default_rng(9)
+    x = (rng.standard_normal((3, 2, Nt, Nr)) * np.array([20.0, 1.0, 0.1])[:, None, None, None]).astype(np.float32)
+    y = np.array([0, 1200, 2310])
+    out = m(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)).cpu().numpy()
+    ref = orc.OracleNet(sd, 8, Nt, Nr).forward(x, y)
+    for b in range(3):
+        assert _rel(out[b], ref[b]) < 2e-5, (Nt, Nr, b, _rel(out[b], ref[b]))
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x2"])
+def test_lazily_conjugated_inputs_are_materialised(dev, prec):
+    """torch's conj bit keeps data_ptr(): a contiguous P.conj() must not be read un-conjugated (advisor finding)."""
+    sd = params.random_state(8, seed=1)
+    m = make_model(sd, ngf=8, precision=prec).to(dev)
+    B, Nt, Nr, Np = 3, 64, 16, 38
+    H = synth.cdl_like_channels(B, Nt, Nr)
+    P = synth.qpsk_pilots(B, Nt, Np)
+    nv = float(synth.snr_to_noise_var(10.0, Nt))
+    Y = synth.received_pilots(P, H, nv)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(3))
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=SIGMA_END, level_begin=0, level_end=2, steps_each=3, seed=5)
+    tP, tY, tX, tH = (torch.from_numpy(a).to(dev) for a in (P, Y, X0, H))
+    Xa, na = sampler.ald_run(m, tP, tY, tX, tH, **kw)
+    lazy = torch.from_numpy(np.conj(P)).to(dev).conj()          # same values as tP, conj bit set, contiguous
+    assert lazy.is_conj() and lazy.is_contiguous()
+    Xb, nb = sampler.ald_run(m, lazy, tY, tX, tH, **kw)
+    assert torch.equal(Xa, Xb) and torch.equal(na, nb)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# long-horizon parity: the FULL 2311 x 3 schedule with the same Philox noise on both sides (reference loop:
+# test_score.py:135-175).  The oracle needs ~13 ms per Langevin step for 16 trajectories on 16 cores.
+# ---------------------------------------------------------------------------------------------------------------------
+def _shipped():
+    from score_based_channels_b200 import entry_common as ec, hdf5_min
+    ck = os.path.join(REPO, "fixtures_local", "score-deepest-cdl-c.pt")
+    mat = os.path.join(REPO, "fixtures_local", "CDL-C_Nt64_Nr16_ULA0.50_seed4321.mat")
+    if not (os.path.exists(ck) and os.path.exists(mat)):
+        pytest.skip("shipped checkpoint / channels not available on this box")
+    contents = ec.load_checkpoint(ck, "CDL-C")
+    h = hdf5_min.loadmat_v73(mat)["output_h"][:, 0].astype(np.complex64)      # [100, Nr, Nt]
+    Hn = np.ascontiguousarray(np.conj(np.transpose(h, (0, 2, 1))) / 0.363263)    # Hermitian, normalised (loaders.py:88-91)
+    return contents, Hn
+
+
+@pytest.mark.timeout(1500)
+def test_full_schedule_same_noise_trajectories_match_oracle(dev):
+    from oracle import oracle as orc
+    from score_based_channels_b200 import entry_common as ec
+    contents, Hn = _shipped()
+    sd = {k: v.numpy() for k, v in contents["model_state"].items()}
+    snrs = np.array([0.0, 10.0, 20.0, 30.0])
+    nch = 4
+    H = np.concatenate([Hn[:nch]] * len(snrs))
+    B, Nt, Nr, Np = H.shape[0], 64, 16, 38
+    P = np.concatenate([synth.qpsk_pilots(nch, Nt, Np, seed=1234)] * len(snrs))
+    nv = np.repeat(synth.snr_to_noise_var(snrs, Nt), nch).astype(np.float32)
+    Y = synth.received_pilots(P, H, nv, seed=99)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(3))
+    kw = dict(noise_var=nv, alpha_step=3e-11, beta=0.01, sigma_end=float(contents["config"].model.sigma_end),
+              level_begin=0, level_end=2311, steps_each=3, seed=20260101)
+    orc.set_num_threads(os.cpu_count() or 1)
+    Xo, no = orc.OracleNet(sd, 8, Nt, Nr).ald(P, Y, X0, H, **kw)
+    steps = np.array([0, 10, 100, 1000, 3000, 5000, 6000, 6500, 6900, 6932])
+    for prec, dtol, rtol in (("tf32x3", 1e-4, 1e-3), ("fp16x2", 1e-4, 1e-3), ("tf32", 1e-3, 2e-2)):
+        m = ec.build_model(contents["config"], contents["model_state"], dev, prec)
+        X, nlog = sampler.ald_run(m, *(torch.from_numpy(a).to(dev) for a in (P, Y, X0, H)),
+                                  **{**kw, "noise_var": torch.from_numpy(nv).to(dev)})
+        n = nlog.cpu().numpy()
+        assert np.abs(n[-1] - no[-1]).max() <= dtol, (prec, np.abs(n[-1] - no[-1]).max())        # per-channel final NMSE
+        assert np.allclose(n[steps], no[steps], rtol=rtol, atol=dtol * 1e-2), (prec, np.abs(n[steps] / no[steps] - 1).max())
+        assert np.abs(X.cpu().numpy() - Xo).max() <= 20 * dtol * np.abs(Xo).max(), prec
+
+
+@pytest.mark.timeout(900)
+def test_fig5c_points_within_0p2_dB_of_the_reference_path(dev):
+    """10 log10(best NMSE) on the 100 shipped CDL-C channels at the five SNR points of BASELINE.md section 2 (reference loop
+    restated on the CPU with the shipped checkpoint: -2.01 / -8.32 / -15.78 / -23.98 / -32.71 dB): different noise draws,
+    so the comparison is statistical -- 0.2 dB."""
+    from score_based_channels_b200 import entry_common as ec
+    contents, Hn = _shipped()
+    ref_db = {-10.0: -2.01, 0.0: -8.32, 10.0: -15.78, 20.0: -23.98, 30.0: -32.71}
+    snrs = np.array(sorted(ref_db))
+    H = np.concatenate([Hn] * len(snrs))
+    B, Nt, Nr, Np = H.shape[0], 64, 16, 38
+    rng = np.random.default_rng(1234)
+    p = (2 * rng.integers(0, 2, (100, Nt, Np)) - 1 + 1j * (2 * rng.integers(0, 2, (100, Nt, Np)) - 1)) / np.sqrt(2)
+    P1 = np.ascontiguousarray(np.conj(np.transpose(p, (0, 2, 1))), np.complex64)
+    P = np.concatenate([P1] * len(snrs))
+    nv = np.repeat(synth.snr_to_noise_var(snrs, Nt), 100).astype(np.float32)
+    Y = synth.received_pilots(P, H, nv, seed=99)
+    X0 = synth.cn01((B, Nt, Nr), np.random.default_rng(3))
+    for prec in ("tf32x3", "fp16x2"):
+        m = ec.build_model(contents["config"], contents["model_state"], dev, prec)
+        _, nlog = sampler.ald_run(m, *(torch.from_numpy(a).to(dev) for a in (P, Y, X0, H)), noise_var=torch.from_numpy(nv).to(dev),
+                                  alpha_step=3e-11, beta=0.01, sigma_end=float(contents["config"].model.sigma_end), level_begin=0,
+                                  level_end=2311, steps_each=3, seed=7)
+        n = nlog.cpu().numpy().reshape(-1, len(snrs), 100)
+        best = 10 * np.log10(n.mean(axis=2).min(axis=0))           # test_score.py:174-175
+        for i, s in enumerate(snrs):
+            assert abs(best[i] - ref_db[float(s)]) <= 0.2, (prec, float(s), float(best[i]), ref_db[float(s)])

@@ -63,12 +63,12 @@ def test_real_checkpoint_forward_matches_reference_golden():
     g = np.load(os.path.join(GOLDEN, "real_ckpt_forward.npz"))
     contents = ec.load_checkpoint(CKPT)
     rel = lambda a, b: float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
-    for prec in ("tf32x3", "tf32"):
+    for prec in ("tf32x3", "fp16x2", "tf32"):
         m = ec.build_model(contents["config"], contents["model_state"], dev, prec)
         out = m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)).cpu().numpy().astype(np.float64)
         for b in range(out.shape[0]):
             e32, e = rel(g["out32"][b].astype(np.float64), g["out64"][b]), rel(out[b], g["out64"][b])
-            if prec == "tf32x3":
+            if prec in ("tf32x3", "fp16x2"):
                 assert e <= 3 * e32 + 2e-6, (prec, b, e, e32)
             else:
                 assert e <= 4096 * e32, (prec, b, e, e32)

@@ -16,7 +16,7 @@ ge.build()
 from score_based_channels_b200 import _lib, params, sampler, synth  # noqa: E402
 from score_based_channels_b200.models import make_model  # noqa: E402
 
-KINDS = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "pool2"}
+KINDS = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "pool2", 7: "epilogue"}
 
 
 def main():
