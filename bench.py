@@ -20,7 +20,7 @@ truncated schedule (`levels_run`), which the line states -- the per-level cost d
 
 Engines: 1 = fused shared-memory-arena kernel on mma.sync 3xTF32 (`tf32x3`); 2 = tcgen05 / TMEM kernel with fp16 hi/lo
 split operands (`fp16x2`).  Both are fp32-equivalent (forward error ~2e-6 against the reference).  `auto` picks the
-engine that is faster for the workload (measured: engine 1 for one-wave batches, engine 2 from ~2000 trajectories per GPU).
+engine that is faster for the workload (measured: engine 1 at 64x16 where a sample fits one SM's shared memory, engine 2 at 128x32).
 `--impl reference` times the CPU restatement of the reference path (the oracle port; the reference itself is Python on
 torch-CUDA and cannot travel to the GPU box) on the host cores.
 """
@@ -46,8 +46,11 @@ METRIC = "channel-estimates/sec (full ALD, 16x64 CDL-C)"
 ENGINE_PRECISION = {1: "tf32x3", 2: "fp16x2"}
 # HBM traffic of one launch, from the ncu captures committed under profiles/ (dram__bytes_read + write):
 # bytes = fixed + per_level * levels at the captured batch; scaled linearly with the batch.
-TRAFFIC = {1: {"batch": 256, "fixed": 9.5e6, "per_level": 0.15e6, "src": "profiles/r02_ncu_engine1_raw.txt"},
-           2: {"batch": 256, "fixed": 0.36e9, "per_level": 0.26e6, "src": "profiles/r02_ncu_engine2_raw.txt"}}
+TRAFFIC = {1: {"batch": 256, "fixed": 11.9e6, "per_level": 3.1e3, "src": "profiles/r02_ncu_engine1_raw.txt (16-level launch: 11.9 MB read, "
+                                                                       "0 written; the NMSE log, 3 KB per level, stays in L2)"},
+           2: {"batch": 256, "fixed": 0.21e9, "per_level": 0.833e9, "src": "profiles/r02_ncu_engine2_raw.txt and r02_ncu_engine2_2levels_raw.txt "
+                                                                         "(16 / 2 levels: 13.5 / 1.88 GB: the 115 MB working set of 256 per-CTA arenas "
+                                                                         "does not stay in the 126 MB L2, dirty lines are written back)"}}
 
 
 def workload(cfg, world, rank, batch=None):
@@ -161,11 +164,11 @@ def cpu_arm(levels, B, max_seconds=25.0, Nt=64, Nr=16, Np=38):
     net.ald(P, Y, X0, H, level_begin=0, level_end=n_lvl, **kw)
     dt = time.perf_counter() - t0
     t_step = dt / (n_lvl * STEPS_EACH)                              # seconds per Langevin step of the whole batch
-    est_per_s = B / (t_step * levels * STEPS_EACH)
+    est_per_s = B / (t_step * NUM_LEVELS * STEPS_EACH)              # full-ALD estimates (2311 levels x 3 steps each)
     return {"value": est_per_s, "unit": "estimates/s", "cores": cores, "kind": "port", "batch": B,
-            "core_seconds_per_estimate": cores * t_step * levels * STEPS_EACH / B,
+            "core_seconds_per_estimate": cores * t_step * NUM_LEVELS * STEPS_EACH / B,
             "sample": "B=%d x %d levels x %d steps timed (%.1f s on %d threads), per-level cost extrapolated to %d levels"
-                      % (B, n_lvl, STEPS_EACH, dt, cores, levels), "ms_per_langevin_step": t_step * 1e3}
+                      % (B, n_lvl, STEPS_EACH, dt, cores, NUM_LEVELS), "ms_per_langevin_step": t_step * 1e3}
 
 
 class Runner:
@@ -305,9 +308,10 @@ def main():
     def est_per_s(total_traj, lv, n, ms):
         return total_traj * n * (lv / NUM_LEVELS) / (ms * 1e-3)      # full-ALD-equivalent estimates per second
 
-    # engine choice: one-wave batches run fastest on engine 1, large batches on engine 2
+    # engine choice (measured): the shared-memory-resident engine 1 wherever one sample fits an SM
+    # (64x16, ngf 8); the tcgen05 engine 2 for the shapes that do not (128x32: engine 1 falls back to an L2 arena)
     if args.engine == "auto":
-        engine = 1 if (Nt, Nr) == (64, 16) and B0 <= 1024 else 2
+        engine = 1 if (Nt, Nr) == (64, 16) else 2
     else:
         engine = int(args.engine)
 

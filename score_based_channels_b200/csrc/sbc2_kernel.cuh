@@ -565,7 +565,8 @@ __device__ __noinline__ void op_norm_elu_general(const sbc2::Op& op, const int S
 }
 
 
-__device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, const uint8_t* blob, uint8_t* arena, float* spart, int tid) {
+#define SBC2_NT(k) do { if (ntr) ntr[k] = clock64(); } while (0)
+__device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, const uint8_t* blob, uint8_t* arena, float* spart, int tid, long long* ntr) {
     const sbc2::Geo& G = sbc2_c_geo[op.gs];
     const Dec D(G);
     const int C = op.cin, noct = C >> 3, S = S_, hw = G.hw;
@@ -591,6 +592,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
         const int e0 = ch * csz, e1 = min(hw, e0 + csz);
         float al = 0.f, ga = 0.f, be = 0.f;            // affine parameters of channel tid (loaded early: L2 latency)
         if (tid < S * C) { const int c = tid % C; al = wseg[c]; ga = wseg[C + c]; be = wseg[2 * C + c]; }
+        SBC2_NT(0);
         float v[JMAX][8];
         int qq[JMAX];
         if (act) {
@@ -609,10 +611,13 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
 #pragma unroll
                 for (int k = 0; k < 8; k++) a[k] += ok ? v[j][k] : 0.f;
             }
+            SBC2_NT(1);
             warp_sum8(a);
+            SBC2_NT(2);
             if (lane < 8) part1[warp * 8 + lane] = a[lane];
         }
         __syncthreads();
+        SBC2_NT(3);
         float* cmean = spart + 384;        // [S][C] per-channel means
         if (tid < S * C) {
             const int it = tid >> 3, k = tid & 7;       // item = (sample, octet): tid = (s * noct + oct) * 8 + k = s * C + c
@@ -621,6 +626,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
             cmean[tid] = t * inv_hw0(hw);
         }
         __syncthreads();
+        SBC2_NT(4);
         if (act) {
             float mean[8];
 #pragma unroll
@@ -636,6 +642,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
             if (lane < 8) part2[warp * 8 + lane] = a[lane];
         }
         __syncthreads();
+        SBC2_NT(5);
         if (tid < S * C) {     // cross-channel statistics of the per-channel means + the affine: out = ELU(x * cs + csh)
             const int ss = tid / C;
             const float ih = inv_hw0(hw);
@@ -659,6 +666,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
             coefs[tid * 2 + 1] = fmaf(-mean, cs, csh);
         }
         __syncthreads();
+        SBC2_NT(6);
         if (act) {
             float4 cf[4];
             const float4* cp = reinterpret_cast<const float4*>(coefs + (s * C + oct * 8) * 2);
@@ -676,6 +684,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
                 store_sp16(arena + op.elu16, G.slot, oct, qq[j], o);
             }
         }
+        SBC2_NT(7);
         return;
     }
     op_norm_elu_general(op, S_, blob, arena, spart, tid);
@@ -1129,7 +1138,7 @@ __global__ void __launch_bounds__(SBC2_NTHR, 2) sbc2_ald_kernel(const __grid_con
                 } else if (L.dbg & 8) {
                 } else if (op.kind == sbc2::K_NORM_ELU) {
 #ifndef SBC2_X_NONORM
-                    op_norm_elu(op, S, L.blob, arena, spart, tid);
+                    op_norm_elu(op, S, L.blob, arena, spart, tid, (do_prof && i == L.trace_op) ? L.prof + L.n_ops + 2 : nullptr);
 #endif
                 } else if (op.kind == sbc2::K_MAXPOOL5) {
 #ifndef SBC2_X_NOMISC

@@ -65,6 +65,9 @@ def main():
     if top >= 0:
         tr = st[n_ops + 2:].reshape(3, 64, 4)
         t0 = st[top]
+        if kinds[top] == 2:
+            lines.append("norm trace of op %d (%s): start, loads+sum, shuffles, sync1, cmean+sync2, pass2+sync3, coef+sync4, apply; cycles from op start: %s; op end %d"
+                         % (top, names[top], [int(v - t0) for v in st[n_ops + 2:n_ops + 10]], st[top + 1] - t0))
         lines.append("intra-conv trace of op %d (%s), cycles relative to the op start:" % (top, names[top]))
         lines.append("  tile | producer: loop-top  stage-free  issued | mma: loop-top  stage-full  acc-free  issued | epilogue(warp0): loop-top  acc-full  stored")
         for t in range(64):
