@@ -149,6 +149,7 @@ typedef std::map<std::string, TensorArg> StateDict;
 class Builder {
   public:
     int ngf, H, W, channels;
+    int arch = 2, npools = 3;            // 0 NCSNv2, 1 NCSNv2Deeper, 2 NCSNv2Deepest
     int64_t conv_flops = 0;
     std::vector<uint8_t> blob;
     std::vector<MmaEntry> all_mma;       // every conv's UMMA list back to back (Op::mma_idx), for the constant-memory copy
@@ -158,15 +159,20 @@ class Builder {
 
     Builder(const StateDict& sd_, int ngf_, int H_, int W_, int channels_, int stage_cap_ = 35 * 1024)
         : ngf(ngf_), H(H_), W(W_), channels(channels_), stage_cap(stage_cap_), sd(sd_) {
-        if (H <= 0 || W <= 0 || H % 8 || W % 8) throw std::runtime_error("Nt and Nr must be positive multiples of 8");
+        // the architecture is read off the state dict: NCSNv2Deepest has res31 (ncsnv2.py:198-262), NCSNv2Deeper res5 but no
+        // res31 (ncsnv2.py:104-156), NCSNv2 neither (ncsnv2.py:11-68)
+        arch = has("res31.0.conv1.weight") ? 2 : (has("res5.0.conv1.weight") ? 1 : 0);
+        npools = arch == 2 ? 3 : (arch == 1 ? 2 : 1);
+        const int div = 1 << npools;
+        if (H <= 0 || W <= 0 || H % div || W % div || H % 8 || W % 8) throw std::runtime_error("Nt and Nr must be positive multiples of 8");
         if (ngf <= 0 || ngf % 8) throw std::runtime_error("ngf must be a positive multiple of 8");
         if (channels != 2) throw std::runtime_error("channels must be 2 (re, im)");
         for (int l = 0; l < MAX_LEVELS; l++) {
             Geo& g = base[l];
             memset(&g, 0, sizeof g);
-            g.h = H >> l; g.w = W >> l;
+            g.h = std::max(1, H >> l); g.w = std::max(1, W >> l);
             const int dils[3] = {1, 2, 4};
-            const int nd = l < 3 ? 1 : 3;    // the dilated stages run at the lowest resolution (ncsnv2.py:240-254)
+            const int nd = l < npools ? 1 : 3;    // the dilated stages run at the lowest resolution (ncsnv2.py:240-254)
             g.hy = g.hx = 0;
             for (int i = 0; i < nd; i++) {
                 if (dils[i] < g.h) g.hy = std::max(g.hy, dils[i]);
@@ -736,26 +742,42 @@ class Builder {
         rel(a);
         residual_same("res1.0", o, 1, -1, false);
         residual_same("res1.1", o, 1, -1, true);          // l1: raw SP16 feeds res2.0's shortcut conv
-        LT l1 = o;
-        int el4 = -1, el5 = -1;
-        // the raw SP16 copy of a skip only feeds the next stage's shortcut conv: dead right after that stage
-        LT l2 = stage("res2", l1, 2 * ngf, 0, false, nullptr, true);
-        rel(l1.s16); l1.s16 = -1;
-        LT l3 = stage("res3", l2, 2 * ngf, 0, false, nullptr, true);
-        rel(l2.s16); l2.s16 = -1;
-        LT l31 = stage("res31", l3, 2 * ngf, 0, false, nullptr, true);
-        rel(l3.s16); l3.s16 = -1;
-        LT l4 = stage("res4", l31, 4 * ngf, 2, true, &el4, true);
-        rel(l31.s16); l31.s16 = -1;
-        LT l5 = stage("res5", l4, 4 * ngf, 4, true, &el5, false);
-        rel(l4.s16); l4.s16 = -1;
-        int e1 = -1, e2 = -1, e31 = -1, e3 = -1, e4 = -1;
-        LT r1 = refine("refine1", {l5}, {el5}, 4 * ngf, false, &e1);
-        LT r2 = refine("refine2", {l4, r1}, {el4, e1}, 2 * ngf, false, &e2);
-        LT r31 = refine("refine31", {l31, r2}, {-1, e2}, 2 * ngf, false, &e31);
-        LT r3 = refine("refine3", {l3, r31}, {-1, e31}, 2 * ngf, false, &e3);
-        LT r4 = refine("refine4", {l2, r3}, {-1, e3}, ngf, false, &e4);
-        LT r5 = refine("refine5", {l1, r4}, {-1, e4}, ngf, true, nullptr);
+        // encoder stages after res1 (name, width multiplier, dilation; 0 = ConvMeanPool) and decoder blocks (name, width
+        // multiplier), per architecture (ncsnv2.py:26-58, 118-150, 218-262)
+        struct St { const char* name; int mult, dil; };
+        struct Rf { const char* name; int mult; };
+        std::vector<St> stages;
+        std::vector<Rf> rfs;
+        if (arch == 2) {
+            stages = {{"res2", 2, 0}, {"res3", 2, 0}, {"res31", 2, 0}, {"res4", 4, 2}, {"res5", 4, 4}};
+            rfs = {{"refine1", 4}, {"refine2", 2}, {"refine31", 2}, {"refine3", 2}, {"refine4", 1}, {"refine5", 1}};
+        } else if (arch == 1) {
+            stages = {{"res2", 2, 0}, {"res3", 2, 0}, {"res4", 4, 2}, {"res5", 4, 4}};
+            rfs = {{"refine1", 4}, {"refine2", 2}, {"refine3", 2}, {"refine4", 1}, {"refine5", 1}};
+        } else {
+            stages = {{"res2", 2, 0}, {"res3", 2, 2}, {"res4", 2, 4}};
+            rfs = {{"refine1", 2}, {"refine2", 2}, {"refine3", 1}, {"refine4", 1}};
+        }
+        std::vector<LT> skips = {o};            // l1, l2, ...
+        std::vector<int> elus = {-1};           // SP16 ELU(skip) where the stage's last conv emitted it (dilated stages)
+        for (size_t i = 0; i < stages.size(); i++) {
+            int e = -1;
+            const bool dilated = stages[i].dil > 0;
+            // the raw SP16 copy of a skip only feeds the next stage's shortcut conv: dead right after that stage
+            LT out = stage(stages[i].name, skips.back(), stages[i].mult * ngf, stages[i].dil, dilated, &e, i + 1 < stages.size());
+            rel(skips.back().s16); skips.back().s16 = -1;
+            skips.push_back(out);
+            elus.push_back(e);
+        }
+        const int n = (int)skips.size();
+        int e_prev = -1;
+        LT r5 = refine(rfs[0].name, {skips[n - 1]}, {elus[n - 1]}, rfs[0].mult * ngf, false, &e_prev);
+        for (int j = 1; j < n; j++) {
+            int e = -1;
+            const bool end = (j == n - 1);
+            r5 = refine(rfs[j].name, {skips[n - 1 - j], r5}, {elus[n - 1 - j], e_prev}, rfs[j].mult * ngf, end, end ? nullptr : &e);
+            e_prev = e;
+        }
         int t = new16(ngf, 0);
         norm_elu("normalizer", r5.f32, t);
         rel(r5.f32);

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, params
-from .engine import PackedModel
+from .engine import ENGINE2_PRECISIONS, PackedModel
 
 
 class _Node(nn.Module):
@@ -36,7 +36,7 @@ def _cfg_get(node, key, default=None):
 
 
 class NCSNv2Deepest(nn.Module):
-    """``precision`` selects the arithmetic of the 113 convolutions (everything else is fp32):
+    """``precision`` selects the arithmetic of the convolutions (everything else is fp32):
 
     * ``"fp16x2"``: engine 2 -- tcgen05 tensor cores with TMEM accumulators; every operand is an fp16 hi/lo pair
       (22 significant bits), fp32 accumulate: fp32-equivalent results;
@@ -45,10 +45,16 @@ class NCSNv2Deepest(nn.Module):
     * ``"tf32"``: tensor cores, plain TF32 operands (round to nearest), fp32 accumulate (fastest).
     The environment variable ``SBC_PRECISION`` overrides the default."""
 
+    ARCH = "deepest"
+
     def __init__(self, config, precision: Optional[str] = None):
         super().__init__()
         self.config = config
-        self.precision = precision or os.environ.get("SBC_PRECISION", "tf32x3")
+        default = "tf32x3" if self.ARCH == "deepest" else "fp16x2"
+        self.precision = precision or os.environ.get("SBC_PRECISION", default)
+        if self.ARCH != "deepest" and self.precision not in ENGINE2_PRECISIONS:
+            raise NotImplementedError("%s runs on engine 2 only (precision 'fp16x2'); the engine-1 planner knows "
+                                      "NCSNv2Deepest" % type(self).__name__)
         model, data = config.model, config.data
         self.ngf = int(model.ngf)
         self.num_classes = int(model.num_classes)
@@ -68,8 +74,8 @@ class NCSNv2Deepest(nn.Module):
         # parameters under the reference's names
         rng = np.random.default_rng(0)
         init = params.random_state(self.ngf, self.channels, self.num_classes, float(model.sigma_begin),
-                                   float(model.sigma_end), seed=int(rng.integers(1 << 30)))
-        for name, shape in params.param_shapes(self.ngf, self.channels, self.num_classes).items():
+                                   float(model.sigma_end), seed=int(rng.integers(1 << 30)), arch=self.ARCH)
+        for name, shape in params.param_shapes(self.ngf, self.channels, self.num_classes, self.ARCH).items():
             if name == "sigmas":
                 continue
             node = self
@@ -122,3 +128,16 @@ class NCSNv2Deepest(nn.Module):
             _lib.check(_lib.lib().sbc_forward(pm.handle, x.data_ptr(), strides, y.data_ptr(), out.data_ptr(), B,
                                               C.c_void_p(stream)), "sbc_forward")
         return out
+
+
+class NCSNv2Deeper(NCSNv2Deepest):
+    """Drop-in ``NCSNv2Deeper`` (reference ``ncsnv2/models/ncsnv2.py:94-195``): five encoder stages, two mean-pools, dilated
+    stages at a quarter of the input resolution.  Same forward contract; runs on engine 2 (tcgen05), whose C++ planner reads
+    the architecture off the state-dict keys."""
+    ARCH = "deeper"
+
+
+class NCSNv2(NCSNv2Deepest):
+    """Drop-in ``NCSNv2`` (reference ``ncsnv2/models/ncsnv2.py:11-91``): four encoder stages, one mean-pool, dilated stages
+    at half the input resolution.  Same forward contract; runs on engine 2 (tcgen05)."""
+    ARCH = "ncsnv2"

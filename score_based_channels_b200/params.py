@@ -19,7 +19,12 @@ def get_sigmas_np(sigma_begin: float, sigma_end: float, num_classes: int) -> np.
     return np.exp(np.linspace(np.log(sigma_begin), np.log(sigma_end), num_classes)).astype(np.float32)
 
 
-def param_shapes(ngf: int, channels: int = 2, num_classes: int = 2311) -> "OrderedDict[str, Tuple[int, ...]]":
+ARCHS = ("deepest", "deeper", "ncsnv2")     # NCSNv2Deepest / NCSNv2Deeper / NCSNv2 (reference ncsnv2/models/ncsnv2.py)
+
+
+def param_shapes(ngf: int, channels: int = 2, num_classes: int = 2311, arch: str = "deepest") -> "OrderedDict[str, Tuple[int, ...]]":
+    if arch not in ARCHS:
+        raise ValueError("arch must be one of %s" % (ARCHS,))
     d: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
     d["sigmas"] = (num_classes,)
 
@@ -50,9 +55,18 @@ def param_shapes(ngf: int, channels: int = 2, num_classes: int = 2311) -> "Order
                 conv(p + ".shortcut", cin, cout)
         norm(p + ".normalize1", cin)
 
-    plan = [("res1", ngf, ngf, False, None), ("res2", ngf, 2 * ngf, True, None),
-            ("res3", 2 * ngf, 2 * ngf, True, None), ("res31", 2 * ngf, 2 * ngf, True, None),
-            ("res4", 2 * ngf, 4 * ngf, True, 2), ("res5", 4 * ngf, 4 * ngf, True, 4)]
+    # stage plans per architecture (ncsnv2.py:26-58 NCSNv2, 118-150 NCSNv2Deeper, 218-262 NCSNv2Deepest)
+    if arch == "deepest":
+        plan = [("res1", ngf, ngf, False, None), ("res2", ngf, 2 * ngf, True, None),
+                ("res3", 2 * ngf, 2 * ngf, True, None), ("res31", 2 * ngf, 2 * ngf, True, None),
+                ("res4", 2 * ngf, 4 * ngf, True, 2), ("res5", 4 * ngf, 4 * ngf, True, 4)]
+    elif arch == "deeper":
+        plan = [("res1", ngf, ngf, False, None), ("res2", ngf, 2 * ngf, True, None),
+                ("res3", 2 * ngf, 2 * ngf, True, None), ("res4", 2 * ngf, 4 * ngf, True, 2),
+                ("res5", 4 * ngf, 4 * ngf, True, 4)]
+    else:
+        plan = [("res1", ngf, ngf, False, None), ("res2", ngf, 2 * ngf, True, None),
+                ("res3", 2 * ngf, 2 * ngf, True, 2), ("res4", 2 * ngf, 2 * ngf, True, 4)]
     for p, cin, cout, down, dil in plan:
         resblock(p + ".0", cin, cout, down, dil)
         resblock(p + ".1", cout, cout, False, dil)
@@ -72,21 +86,33 @@ def param_shapes(ngf: int, channels: int = 2, num_classes: int = 2311) -> "Order
         for i in range(2):
             conv("%s.crp.convs.%d" % (p, i), features, features, bias=False)
 
-    refine("refine1", [4 * ngf], 4 * ngf, start=True)
-    refine("refine2", [4 * ngf, 4 * ngf], 2 * ngf)
-    refine("refine3", [2 * ngf, 2 * ngf], 2 * ngf)
-    refine("refine31", [2 * ngf, 2 * ngf], 2 * ngf)
-    refine("refine4", [2 * ngf, 2 * ngf], ngf)
-    refine("refine5", [ngf, ngf], ngf, end=True)
+    if arch == "deepest":
+        refine("refine1", [4 * ngf], 4 * ngf, start=True)
+        refine("refine2", [4 * ngf, 4 * ngf], 2 * ngf)
+        refine("refine3", [2 * ngf, 2 * ngf], 2 * ngf)
+        refine("refine31", [2 * ngf, 2 * ngf], 2 * ngf)
+        refine("refine4", [2 * ngf, 2 * ngf], ngf)
+        refine("refine5", [ngf, ngf], ngf, end=True)
+    elif arch == "deeper":
+        refine("refine1", [4 * ngf], 4 * ngf, start=True)
+        refine("refine2", [4 * ngf, 4 * ngf], 2 * ngf)
+        refine("refine3", [2 * ngf, 2 * ngf], 2 * ngf)
+        refine("refine4", [2 * ngf, 2 * ngf], ngf)
+        refine("refine5", [ngf, ngf], ngf, end=True)
+    else:
+        refine("refine1", [2 * ngf], 2 * ngf, start=True)
+        refine("refine2", [2 * ngf, 2 * ngf], 2 * ngf)
+        refine("refine3", [2 * ngf, 2 * ngf], ngf)
+        refine("refine4", [ngf, ngf], ngf, end=True)
     return d
 
 
 def random_state(ngf: int = 8, channels: int = 2, num_classes: int = 2311, sigma_begin: float = 27.77,
-                 sigma_end: float = 2.599515446446343e-4, seed: int = 0) -> Dict[str, np.ndarray]:
+                 sigma_end: float = 2.599515446446343e-4, seed: int = 0, arch: str = "deepest") -> Dict[str, np.ndarray]:
     """Synthetic, machine-independent parameter set with every bias / affine term non-trivial."""
     rng = np.random.default_rng(seed)
     out: Dict[str, np.ndarray] = OrderedDict()
-    for k, shp in param_shapes(ngf, channels, num_classes).items():
+    for k, shp in param_shapes(ngf, channels, num_classes, arch).items():
         if k == "sigmas":
             out[k] = get_sigmas_np(sigma_begin, sigma_end, num_classes)
         elif k.endswith(".weight"):

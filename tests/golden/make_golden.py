@@ -27,14 +27,17 @@ from score_based_channels_b200 import dotmap_shim  # noqa: E402
 dotmap_shim.install()
 from dotmap import DotMap  # noqa: E402
 
-from ncsnv2.models.ncsnv2 import NCSNv2Deepest  # noqa: E402  (the reference module)
+from ncsnv2.models.ncsnv2 import NCSNv2, NCSNv2Deeper, NCSNv2Deepest  # noqa: E402  (the reference modules)
 from score_based_channels_b200 import params, synth  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 SIGMA_BEGIN, SIGMA_END, L = 27.77, 2.599515446446343e-4, 2311
 
 
-def ref_model(ngf, wseed, H=64, W=16):
+REF_CLASS = {"deepest": NCSNv2Deepest, "deeper": NCSNv2Deeper, "ncsnv2": NCSNv2}
+
+
+def ref_model(ngf, wseed, H=64, W=16, arch="deepest"):
     cfg = DotMap()
     cfg.device = "cpu"
     cfg.model.ngf = ngf
@@ -46,21 +49,21 @@ def ref_model(ngf, wseed, H=64, W=16):
     cfg.model.sigma_end = SIGMA_END
     cfg.data.channels = 2
     cfg.data.image_size = [W, H]
-    m = NCSNv2Deepest(cfg)
-    sd = params.random_state(ngf, seed=wseed, sigma_begin=SIGMA_BEGIN, sigma_end=SIGMA_END, num_classes=L)
+    m = REF_CLASS[arch](cfg)
+    sd = params.random_state(ngf, seed=wseed, sigma_begin=SIGMA_BEGIN, sigma_end=SIGMA_END, num_classes=L, arch=arch)
     print(m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}))
     return m.eval(), cfg
 
 
-def golden_forward(name, ngf, wseed, H, W, labels, scales, strided=False):
-    m, _ = ref_model(ngf, wseed, H, W)
+def golden_forward(name, ngf, wseed, H, W, labels, scales, strided=False, arch="deepest"):
+    m, _ = ref_model(ngf, wseed, H, W, arch)
     torch.manual_seed(100 + wseed)
     B = len(labels)
     x = torch.randn(B, 2, H, W) * torch.tensor(scales).view(B, 1, 1, 1)
     y = torch.tensor(labels)
     with torch.no_grad():
         out = m(x, y)
-    np.savez_compressed(os.path.join(OUT, name), ngf=ngf, wseed=wseed, x=x.numpy(), y=y.numpy(), out=out.numpy())
+    np.savez_compressed(os.path.join(OUT, name), ngf=ngf, wseed=wseed, x=x.numpy(), y=y.numpy(), out=out.numpy(), arch=arch)
     print(name, "out absmax per sample", out.abs().amax(dim=(1, 2, 3)))
 
 
@@ -150,6 +153,9 @@ if __name__ == "__main__":
     golden_forward("forward_ngf8.npz", 8, 1, 64, 16, [0, 1000, 2310, 17, 2000], [27.0, 0.5, 1.0, 10.0, 0.05])
     golden_forward("forward_ngf8_32x8.npz", 8, 2, 32, 8, [5, 1500], [20.0, 1.0])
     golden_forward("forward_ngf16.npz", 16, 3, 64, 16, [0, 2310], [27.0, 1.0])
+    # the other two score nets of the reference (ncsnv2.py:11-195)
+    golden_forward("forward_deeper_ngf8.npz", 8, 5, 64, 16, [0, 1200, 2310], [27.0, 1.0, 0.05], arch="deeper")
+    golden_forward("forward_ncsnv2_ngf8.npz", 8, 6, 64, 16, [0, 1200, 2310], [27.0, 1.0, 0.05], arch="ncsnv2")
     # BASELINE config 1: batch 4, 2 sigma levels x 3 steps, SNR 0 dB, alpha0 = 3e-11, beta = 0.01
     golden_ald("ald_cfg1.npz", 8, 1, B=4, Np=38, snr_db=0.0, levels=[0, 1], steps_each=3, alpha_step=3e-11,
                beta_noise=0.01)

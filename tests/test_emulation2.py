@@ -125,3 +125,18 @@ def test_plan_footprint_and_reuse(emu2):
         for b in live[i + 1:]:
             if a.born < b.died and b.born < a.died:
                 assert a.off + a.bytes <= b.off or b.off + b.bytes <= a.off, (a.name, b.name)
+
+
+@pytest.mark.parametrize("name", ["forward_deeper_ngf8.npz", "forward_ncsnv2_ngf8.npz"])
+def test_emulated_plan_of_the_other_score_nets_matches_reference_golden(emu2, name):
+    """NCSNv2Deeper / NCSNv2 (reference ncsnv2/models/ncsnv2.py:11-195): the C++ planner reads the architecture off the
+    state-dict keys; golden vectors come from the reference modules (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    arch = str(g["arch"])
+    sd = params.random_state(int(g["ngf"]), seed=int(g["wseed"]), arch=arch)
+    e = Emu2(emu2, sd, int(g["ngf"]), 64, 16)
+    x, y, ref = g["x"], g["y"], g["out"]
+    out = e.forward(x) / sd["sigmas"][y][:, None, None, None]
+    for b in range(x.shape[0]):
+        rel = np.linalg.norm(out[b] - ref[b]) / np.linalg.norm(ref[b])
+        assert rel < 2e-5, (name, b, rel)

@@ -161,6 +161,24 @@ def test_other_antenna_counts_match_oracle(dev, Nt, Nr):
         assert _rel(out[b], ref[b]) < 2e-5, (Nt, Nr, b, _rel(out[b], ref[b]))
 
 
+@pytest.mark.parametrize("name,cls", [("forward_deeper_ngf8.npz", "NCSNv2Deeper"), ("forward_ncsnv2_ngf8.npz", "NCSNv2")])
+def test_other_score_nets_match_reference_golden(dev, name, cls):
+    """The reference's other two score nets (ncsnv2/models/ncsnv2.py:11-195) through the drop-in classes."""
+    from score_based_channels_b200 import ncsnv2 as N
+    from score_based_channels_b200.models import make_config
+    g = np.load(os.path.join(GOLDEN, name))
+    arch = str(g["arch"])
+    sd = params.random_state(int(g["ngf"]), seed=int(g["wseed"]), arch=arch)
+    m = getattr(N, cls)(make_config(ngf=int(g["ngf"]), num_classes=sd["sigmas"].size))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in sd.items()})
+    m = m.eval().to(dev)
+    out = m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)).cpu().numpy()
+    for b in range(out.shape[0]):
+        assert _rel(out[b], g["out"][b]) < 2e-5, (name, b, _rel(out[b], g["out"][b]))
+    with pytest.raises(NotImplementedError):
+        getattr(N, cls)(make_config(ngf=8), precision="tf32x3")
+
+
 @pytest.mark.parametrize("prec", ["tf32x3", "fp16x2"])
 def test_lazily_conjugated_inputs_are_materialised(dev, prec):
     """torch's conj bit keeps data_ptr(): a contiguous P.conj() must not be read un-conjugated (advisor finding)."""
