@@ -63,6 +63,7 @@ static std::string sbc2_create(Sbc2Model* m, const sbc2::StateDict& sd_in, int n
     }
     auto it = m->sd.find("sigmas");
     if (it == m->sd.end()) return "state dict has no 'sigmas' entry";
+    if (it->second.shape.size() != 1 || it->second.shape[0] < 1) return "'sigmas' must be a non-empty 1-D tensor";
     m->n_sigmas = (int)it->second.shape[0];
     try {
         m->builder.reset(new sbc2::Builder(m->sd, ngf, Nt, Nr, channels, SBC2_STAGE_CAP));

@@ -322,6 +322,20 @@ class Builder {
         if (it == sd.end()) throw std::runtime_error("state dict has no entry '" + k + "'");
         return it->second;
     }
+    static int64_t numel(const TensorArg& t) {
+        int64_t n = 1;
+        for (auto d : t.shape) n *= d;
+        return n;
+    }
+    // conv weight [cout, cin, k, k] with a matching optional bias [cout]: shapes are validated before anything is indexed
+    const TensorArg& W4(const std::string& prefix) const {
+        const TensorArg& wt = P_(prefix + ".weight");
+        if (wt.shape.size() != 4 || wt.shape[0] <= 0 || wt.shape[1] <= 0 || wt.shape[2] != wt.shape[3] || (wt.shape[2] != 1 && wt.shape[2] != 3))
+            throw std::runtime_error("'" + prefix + ".weight' must be a [cout, cin, k, k] tensor with k in {1, 3}");
+        if (has(prefix + ".bias") && numel(P_(prefix + ".bias")) != wt.shape[0])
+            throw std::runtime_error("'" + prefix + ".bias' does not match the weight's output channels");
+        return wt;
+    }
     bool has(const std::string& k) const { return sd.find(k) != sd.end(); }
 
     int newt(int fmt, int C, int level, const std::string& tag) {
@@ -364,7 +378,7 @@ class Builder {
                 // first branch alone into an F32 tensor (the requested dst32, else a temporary); the rest accumulate
                 // on top of it in place and apply the remaining outputs
                 if (out.acc32 >= 0 || out.compact) throw std::runtime_error("unsupported sibling split");
-                const auto& w0 = P_(br[0].prefix + ".weight");
+                const auto& w0 = W4(br[0].prefix);
                 const int cout = (int)w0.shape[0], lvl = tens[br[0].src].level;
                 int tmp = -1;
                 if (out.dst32 < 0) tmp = new32((cout + 7) / 8 * 8, lvl, "sib");
@@ -382,7 +396,7 @@ class Builder {
         conv1(br, out);
     }
     int branch_halo(const Branch& b) const {
-        const auto& wt = P_(b.prefix + ".weight");
+        const auto& wt = W4(b.prefix);
         const int k = (int)wt.shape[2], r = k / 2, lvl = tens[b.src].level;
         const Geo& g = base[lvl];
         int halo = 0;
@@ -402,7 +416,7 @@ class Builder {
         // wide inputs: one op per group of 32 input channels, summed in an F32 temporary; a K_EPILOGUE op then applies the
         // requested outputs to the finished sum
         if (out.compact) throw std::runtime_error("compact conv with a wide input is not supported");
-        const auto& w0 = P_(br[0].prefix + ".weight");
+        const auto& w0 = W4(br[0].prefix);
         const int cout = (int)w0.shape[0], lvl = tens[br[0].src].level;
         const int T = new32((cout + 7) / 8 * 8, lvl, "ks");
         bool first = true;
@@ -425,7 +439,7 @@ class Builder {
     }
 
     void conv_chunks(const std::vector<Branch>& br, const Outs& out) {
-        const auto& w0 = P_(br[0].prefix + ".weight");
+        const auto& w0 = W4(br[0].prefix);
         const int cout = (int)w0.shape[0];
         const int cout8 = std::max(8, (cout + 7) / 8 * 8);
         const int N = 2 * cout8;
@@ -466,7 +480,7 @@ class Builder {
         if (br.size() > 2) throw std::runtime_error("at most two summed convs per op");
         for (size_t bi = 0; bi < br.size(); bi++) {
             const Branch& b = br[bi];
-            const auto& wt = P_(b.prefix + ".weight");
+            const auto& wt = W4(b.prefix);
             const int bco = (int)wt.shape[0], cin = (int)wt.shape[1], k = (int)wt.shape[2], r = k / 2;
             if (bco != cout_real || wt.shape[3] != k || (k != 1 && k != 3)) throw std::runtime_error("bad conv weight " + b.prefix);
             const T_& st = tens[b.src];
@@ -571,6 +585,7 @@ class Builder {
     void norm_elu(const std::string& p, int src32, int dst16) {
         const int C = tens[src32].C, lvl = tens[src32].level;
         const auto &al = P_(p + ".alpha"), &ga = P_(p + ".gamma"), &be = P_(p + ".beta");
+        if (numel(al) != C || numel(ga) != C || numel(be) != C) throw std::runtime_error("'" + p + "' alpha / gamma / beta must have " + std::to_string(C) + " entries");
         const size_t off = blob_align(16);
         blob.resize(off + (size_t)3 * C * 4);
         memcpy(blob.data() + off, al.data, (size_t)C * 4);

@@ -478,6 +478,7 @@ extern "C" int sbc_model_create_from_state(const sbc_state_entry* entries, int32
         for (int k = 0; k < e.ndim; k++) t.shape.push_back(e.shape[k]);
         sd[e.name] = t;
     }
+    if (ngf <= 0 || Nt <= 0 || Nr <= 0) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state: ngf, Nt, Nr must be positive");
     std::unique_ptr<SbcModel> mh(new SbcModel());
     mh->engine = 2;
     mh->e2 = new Sbc2Model();
@@ -494,6 +495,7 @@ extern "C" int sbc_debug_plan(void* handle, int32_t S, int32_t reuse, sbc_tensor
     SbcModel* m = (SbcModel*)handle;
     if (m->engine != 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_plan: engine 2 only");
     SBC_CUDA(cudaSetDevice(m->e2->device));
+    if (S < 1 || S > SBC2_MAXS) return sbc_fail(SBC_E_ARG, "sbc_debug_plan: group size must be in 1..%d", SBC2_MAXS);
     std::string err;
     Sbc2PlanDev* pd = sbc2_plan(m->e2, S, reuse != 0, err);
     if (!pd) return sbc_fail(SBC_E_CUDA, "sbc_debug_plan: %s", err.c_str());
@@ -511,6 +513,7 @@ extern "C" int sbc_debug_run(void* handle, const float* x, int32_t S, int32_t re
     SbcModel* m = (SbcModel*)handle;
     if (m->engine != 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_debug_run: engine 2 only");
     Sbc2Model* e = m->e2;
+    if (S < 1 || S > SBC2_MAXS) return sbc_fail(SBC_E_ARG, "sbc_debug_run: group size must be in 1..%d", SBC2_MAXS);
     SBC_CUDA(cudaSetDevice(e->device));
     Sbc2Launch L2;
     int grid = 0;

@@ -140,3 +140,27 @@ def test_emulated_plan_of_the_other_score_nets_matches_reference_golden(emu2, na
     for b in range(x.shape[0]):
         rel = np.linalg.norm(out[b] - ref[b]) / np.linalg.norm(ref[b])
         assert rel < 2e-5, (name, b, rel)
+
+
+def test_planner_rejects_malformed_state_dicts(emu2):
+    """The library builds a model from caller-supplied tensors: shapes are validated before anything is indexed."""
+    sd = params.random_state(8, seed=1)
+    err = C.create_string_buffer(256)
+
+    def create(d, ngf=8, H=64, W=16):
+        ents, keep = state_entries(d)
+        h = emu2.emu2_create(ents, len(d), ngf, H, W, 2, 32 * 1024, err, 256)
+        if h:
+            emu2.emu2_free(h)
+        return bool(h), err.value.decode()
+
+    assert create(sd)[0]
+    bad = dict(sd); del bad["res3.1.conv2.weight"]
+    ok, msg = create(bad); assert not ok and "res3.1.conv2.weight" in msg
+    bad = dict(sd); bad["begin_conv.weight"] = sd["begin_conv.weight"].reshape(8, -1)          # not 4-D
+    ok, msg = create(bad); assert not ok and "begin_conv.weight" in msg
+    bad = dict(sd); bad["res1.0.normalize1.alpha"] = np.zeros(3, np.float32)
+    ok, msg = create(bad); assert not ok and "normalize1" in msg
+    bad = dict(sd); bad["end_conv.bias"] = np.zeros(5, np.float32)
+    ok, msg = create(bad); assert not ok and "end_conv" in msg
+    assert not create(sd, H=60)[0] and not create(sd, ngf=12)[0]
