@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define SBC_VERSION 200   /* 0.2.0: engine 2 (tcgen05): sbc_model_create_from_state, sbc_info gained engine / ctas_per_sm /
+#define SBC_VERSION 210   /* 0.2.1: engine 1 plans for two CTAs per SM (park area: sbc_model_desc.park_floats appended);
+                           * 0.2.0: engine 2 (tcgen05): sbc_model_create_from_state, sbc_info gained engine / ctas_per_sm /
                            * group_size / n_ops (appended), debug views sbc_debug_plan / sbc_debug_run */
 
 enum {
@@ -62,6 +63,7 @@ typedef struct sbc_model_desc {
     int32_t n_sigmas;
     int64_t conv_flops;     /* dense conv FLOP / forward / sample (reported by sbc_query) */
     int32_t nthreads;       /* threads per CTA the program was planned for: must equal sbc_threads_per_cta() */
+    int32_t park_floats;    /* per-CTA park area in global memory (SPILL / FILL ops, SBC_F_ACC_G); 0 = none */
 } sbc_model_desc;
 
 typedef struct sbc_info {
@@ -153,8 +155,8 @@ int sbc_forward_host(void* handle, const float* x, const int64_t* labels, float*
 int sbc_ald_run_host(void* handle, const sbc_ald_args* args);
 
 /* Debug aid: run the layer program of sample x (device fp32 [channels,Nt,Nr], contiguous) up to but
- * excluding op `stop_op` (n_ops = all) and copy the whole arena to arena_out (device,
- * arena_floats). */
+ * excluding op `stop_op` (n_ops = all) and copy the whole arena, followed by the CTA's park area, to arena_out
+ * (device, arena_floats + park_floats). */
 int sbc_debug_arena(void* handle, const float* x, int32_t stop_op, float* arena_out, void* stream);
 
 /* Engine-2 debug views.  sbc_debug_plan: tensor table (up to `cap` entries), arena size and the four level

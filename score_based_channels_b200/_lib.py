@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbc_b200.so")
+LIB_PATH = os.environ.get("SBC_LIB") or os.path.join(_HERE, "libsbc_b200.so")   # SBC_LIB: experiment builds (tools/)
 
 EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_create_from_state",
            "sbc_model_free", "sbc_query", "sbc_forward", "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host",
@@ -20,7 +20,7 @@ class ModelDesc(C.Structure):
                 ("blob", C.c_void_p), ("blob_floats", C.c_int64),
                 ("arena_floats", C.c_int32), ("in_off", C.c_int32), ("out_off", C.c_int32), ("post_off", C.c_int32),
                 ("max_w_len", C.c_int32), ("sigmas", C.c_void_p), ("n_sigmas", C.c_int32), ("conv_flops", C.c_int64),
-                ("nthreads", C.c_int32)]
+                ("nthreads", C.c_int32), ("park_floats", C.c_int32)]
 
 
 class Info(C.Structure):

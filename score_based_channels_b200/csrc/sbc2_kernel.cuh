@@ -159,19 +159,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ELU (layers.py:13): expm1 by an 8-term Horner polynomial for small |v| (no cancellation), MUFU.EX2 otherwise
-__device__ __forceinline__ float elu(float v) {
-    float p = 2.4801587e-5f;            // 1/8!
-    p = fmaf(p, v, 1.9841270e-4f);
-    p = fmaf(p, v, 1.3888889e-3f);
-    p = fmaf(p, v, 8.3333333e-3f);
-    p = fmaf(p, v, 4.1666667e-2f);
-    p = fmaf(p, v, 1.6666667e-1f);
-    p = fmaf(p, v, 0.5f);
-    p = fmaf(p, v, 1.0f);
-    const float small = p * v, big = __expf(v) - 1.f;
-    return v > 0.f ? v : (v > -0.35f ? small : big);
-}
+// ELU (layers.py:13).  exp via MUFU.EX2: absolute error ~1e-7 = one ulp of the 1.0 that is subtracted (fp32 level).  A
+// cancellation-free polynomial branch for small |v| was measured and dropped: it costs 11 % of engine 1's step time (the
+// kernels are bound by exactly such dependent chains) and does not change the forward error (2.4e-6 either way).
+__device__ __forceinline__ float elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 
 struct alignas(16) H8 { __half2 a, b, c, d; };
 // v[0..7] -> fp16 hi / lo pair (hi = rn(v), lo = rn(v - hi)); |v| is clamped below the fp16 overflow threshold
@@ -226,12 +217,34 @@ struct Dec {
 __device__ __forceinline__ int qof(const sbc2::Geo& G, int s, int y, int x) { return G.lead + s * G.pps + y * G.wp + x; }
 
 __device__ __forceinline__ float inv_hw0(int hw) { return 1.f / (float)hw; }
-// sum over the warp of 8 per-lane values; every lane gets all 8 totals
+// Sum over the warp of 8 per-lane values by a transposing butterfly: 7 + 2 shuffles instead of 40.  On return lane l holds
+// in v[0] the warp total of value (l & 7) (lanes 0-7 are the ones the callers read).
 __device__ __forceinline__ void warp_sum8(float (&v)[8]) {
+    const int lane = threadIdx.x & 31;
+    {   // step 1 (xor 4): lanes with bit 2 clear keep values 0-3, the others 4-7
+        const bool up = lane & 4;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {   // step 2 (xor 2): keep 2 of the 4
+        const bool up = lane & 2;
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+        for (int i = 0; i < 2; i++) {
+            const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+    {   // step 3 (xor 1): keep 1 of the 2
+        const bool up = lane & 1;
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    // lane l now holds the partial sum of value (l & 7) over the 4 lanes {l ^ 0, ...} of its group of 8; finish over 8, 16
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
 // interior-pixel number s*hw + y*w + x of padded pixel q, or -1 for pads (exact magic-number divisions)
@@ -504,7 +517,7 @@ __device__ __noinline__ void op_norm_elu_general(const sbc2::Op& op, const int S
                     }
                 }
                 warp_sum8(a);
-                if (lane < 8) (pass == 0 ? part1 : part2)[u * 8 + lane] = a[lane];
+                if (lane < 8) (pass == 0 ? part1 : part2)[u * 8 + lane] = a[0];
             }
             __syncthreads();
         }
@@ -614,7 +627,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
             SBC2_NT(1);
             warp_sum8(a);
             SBC2_NT(2);
-            if (lane < 8) part1[warp * 8 + lane] = a[lane];
+            if (lane < 8) part1[warp * 8 + lane] = a[0];
         }
         __syncthreads();
         SBC2_NT(3);
@@ -639,7 +652,7 @@ __device__ __forceinline__ void op_norm_elu(const sbc2::Op& op, const int S_, co
                 for (int k = 0; k < 8; k++) { const float d = v[j][k] - mean[k]; a[k] += ok ? d * d : 0.f; }
             }
             warp_sum8(a);
-            if (lane < 8) part2[warp * 8 + lane] = a[lane];
+            if (lane < 8) part2[warp * 8 + lane] = a[0];
         }
         __syncthreads();
         SBC2_NT(5);

@@ -39,6 +39,8 @@ struct SbcModel {
     float* d_blob = nullptr;
     float* d_sigmas = nullptr;
     float* d_gws = nullptr;
+    float* d_park = nullptr;       // park area of two-CTAs-per-SM plans: park_floats per resident CTA
+    int ctas_per_sm = 1;
     int first_w = -1;
     bool arena_in_smem = false;
     bool stage = false;
@@ -63,7 +65,7 @@ struct SbcModel {
         return hws[slot];
     }
     ~SbcModel() {   // owns its device buffers: every early return of sbc_model_create releases them
-        cudaFree(d_ops); cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws);
+        cudaFree(d_ops); cudaFree(d_blob); cudaFree(d_sigmas); cudaFree(d_gws); cudaFree(d_park);
         for (auto p : hws) cudaFree(p);
         delete e2;
     }
@@ -129,7 +131,17 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
             return sbc_fail(SBC_E_ARG, "op %d: bad geometry index", i);
         }
         {   // every arena offset an op touches must lie inside the arena (a malformed table must not write out of bounds)
-            const int offs[5] = {o.src, o.dst, o.acc, o.edst, o.scratch};
+            if (o.kind == SBC_OP_SPILL || o.kind == SBC_OP_FILL) {   // whole-tensor copies between the arena and the park area
+                const int a = o.kind == SBC_OP_SPILL ? o.src : o.dst, p = o.kind == SBC_OP_SPILL ? o.dst : o.src;
+                const long long n = 4ll * o.MT;
+                if (o.MT <= 0 || a < 0 || a % 4 || p < 0 || p % 4 || a + n > desc->arena_floats || p + n > desc->park_floats) {
+                    return sbc_fail(SBC_E_ARG, "op %d: spill / fill outside the arena or the park area", i);
+                }
+                continue;
+            }
+            const bool acc_g = (o.flags & SBC_F_ACC_G) != 0;
+            if (acc_g && (o.kind != SBC_OP_CONV_MMA || o.acc < 0)) { return sbc_fail(SBC_E_ARG, "op %d: ACC_G without a conv accumulator", i); }
+            const int offs[5] = {o.src, o.dst, acc_g ? -1 : o.acc, o.edst, o.scratch};
             for (int k = 0; k < 5; k++)
                 if (offs[k] < -1 || offs[k] >= desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: arena offset out of range", i); }
             const SbcGeo& gs = m->geo[o.sgeo]; const SbcGeo& gd = m->geo[o.dgeo];
@@ -137,7 +149,7 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
             const bool compact_in = o.kind == SBC_OP_AFFINE, compact_out = (o.kind == SBC_OP_CONV_MMA) && (o.flags & SBC_F_COMPACT);
             if (o.src >= 0 && !compact_in && o.src + in_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: input tensor exceeds the arena", i); }
             if (o.dst >= 0 && !compact_out && o.dst + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: output tensor exceeds the arena", i); }
-            if (o.acc >= 0 && o.acc + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: accumulator tensor exceeds the arena", i); }
+            if (o.acc >= 0 && o.acc + out_ext > (acc_g ? desc->park_floats : desc->arena_floats)) { return sbc_fail(SBC_E_ARG, "op %d: accumulator tensor exceeds the arena", i); }
             if (o.edst >= 0 && o.edst + out_ext > desc->arena_floats) { return sbc_fail(SBC_E_ARG, "op %d: ELU output tensor exceeds the arena", i); }
         }
         if (o.w_len > 0 && (o.wbuf < 0 || o.wbuf % 4 || o.wbuf + o.w_len > desc->arena_floats)) {
@@ -198,6 +210,20 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    // resident CTAs per SM: plans made for two CTAs per SM (program.py, park mode) keep their arena under half of the
+    // shared memory of an SM; the grid is sized to fill every slot (any grid is correct: CTAs stride over the batch)
+    m->ctas_per_sm = 1;
+    if (m->arena_in_smem) {
+        int nb = 0;
+        if (m->x3) SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, true, false>, SBC_NTHREADS, m->smem_bytes));
+        else SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, false, false>, SBC_NTHREADS, m->smem_bytes));
+        const int cap = env_int("SBC_CTAS", 0);
+        if (cap > 0 && nb > cap) nb = cap;
+        m->ctas_per_sm = nb < 1 ? 1 : nb;
+    }
+    if (desc->park_floats < 0 || desc->park_floats % 4) { return sbc_fail(SBC_E_ARG, "sbc_model_create: bad park_floats"); }
+    if (desc->park_floats > 0)
+        SBC_CUDA(cudaMalloc(&m->d_park, sizeof(float) * (size_t)desc->park_floats * (size_t)m->num_sms * (size_t)m->ctas_per_sm));
     *handle_out = mh.release();
     return SBC_OK;
 }
@@ -223,7 +249,7 @@ extern "C" int sbc_query(void* handle, sbc_info* out) {
         out->engine = 2; out->ctas_per_sm = e->ctas_per_sm; out->group_size = e->last_S; out->n_ops = e->builder->n_ops();
         return SBC_OK;
     }
-    out->engine = 1; out->ctas_per_sm = 1; out->group_size = 1; out->n_ops = m->d.n_ops;
+    out->engine = 1; out->ctas_per_sm = m->ctas_per_sm; out->group_size = 1; out->n_ops = m->d.n_ops;
     out->version = SBC_VERSION;
     out->device = m->device;
     out->num_sms = m->num_sms;
@@ -246,6 +272,7 @@ static void fill_common(const SbcModel* m, SbcLaunch& L) {
     L.arena_floats = m->d.arena_floats; L.in_off = m->d.in_off; L.out_off = m->d.out_off; L.post_off = m->d.post_off;
     L.Nt = m->d.Nt; L.Nr = m->d.Nr; L.channels = m->d.channels; L.max_w_len = m->d.max_w_len;
     L.sigmas = m->d_sigmas; L.n_sigmas = m->d.n_sigmas;
+    L.gpark = m->d_park; L.park_floats = m->d.park_floats;
     L.gws = m->d_gws; L.stage_weights = m->stage ? 1 : 0; L.debug_stop = -1;
     L.prof = m->d_prof;
     L.dbg = env_int("SBC_DBG", 0);
@@ -253,7 +280,8 @@ static void fill_common(const SbcModel* m, SbcLaunch& L) {
 
 static int launch(SbcModel* m, SbcLaunch& L, cudaStream_t st) {
     SBC_CUDA(cudaSetDevice(m->device));
-    const int grid = L.B < m->num_sms ? L.B : m->num_sms;
+    const int slots = m->num_sms * m->ctas_per_sm;
+    const int grid = L.B < slots ? L.B : slots;
     size_t smem = m->smem_bytes;
     if (L.debug_stop >= 0) L.stage_weights = 0;   // debug runs read parameters straight from global memory
     const bool instr = L.prof != nullptr || L.debug_stop >= 0 || L.dbg != 0;

@@ -15,11 +15,19 @@
 #include "sbc_mma.h"
 #include "sbc_ops.h"
 
+// 256 threads and (at least) two CTAs per SM: the kernel is a chain of short latency-bound ops -- measured on B200, one
+// sample runs only 6 % slower on 8 warps than on 16 -- so two channel realisations in flight per SM, each on its own 8
+// warps, nearly double the throughput of one on 16.  128 registers per thread either way.
 #ifndef SBC_NTHREADS
-#define SBC_NTHREADS 512
+#define SBC_NTHREADS 256
 #endif
 // pixel tiles one warp accumulates per pass (register budget: 128 regs/thread at 512 threads, 64 at 1024)
-#define SBC_MAXNS (SBC_NTHREADS > 512 ? 2 : 4)
+#ifndef SBC_MINCTAS
+#define SBC_MINCTAS 2
+#endif
+#ifndef SBC_MAXNS
+#define SBC_MAXNS (SBC_NTHREADS * SBC_MINCTAS > 512 ? 2 : 4)
+#endif
 
 struct SbcLaunch {
     // layer program
@@ -59,6 +67,8 @@ struct SbcLaunch {
     const int* stop_step;    // [B] or null: last step index executed by a sample
     // execution
     float* gws;              // global arena workspace (when the arena does not fit in shared memory)
+    float* gpark;            // park area: park_floats per CTA (SBC_OP_SPILL / SBC_OP_FILL / SBC_F_ACC_G), or null
+    int park_floats;
     int stage_weights;       // 1: cp.async.bulk double buffering, 0: read parameters from global/L2
     int debug_stop;          // >=0: stop sample 0 / step 0 before op `debug_stop`, dump the arena
     float* debug_out;
@@ -303,7 +313,7 @@ __device__ __forceinline__ void sbc_epilogue_batch(const SbcEpi& e, float* arena
 #pragma unroll
                 for (int half = 0; half < 2; half++)
                     old[j][n][half] = (live[n] && pd[j][half] >= 0)
-                                          ? *reinterpret_cast<const float2*>(arena + e.acc + pd[j][half] + cofs[n])
+                                          ? *reinterpret_cast<const float2*>(e.accb + e.acc + pd[j][half] + cofs[n])
                                           : make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NS; j++)
@@ -314,7 +324,7 @@ __device__ __forceinline__ void sbc_epilogue_batch(const SbcEpi& e, float* arena
                     acc[j][n][2 * half] += old[j][n][half].x;
                     acc[j][n][2 * half + 1] += old[j][n][half].y;
                     if (live[n] && pd[j][half] >= 0)
-                        *reinterpret_cast<float2*>(arena + e.acc + pd[j][half] + cofs[n]) = make_float2(acc[j][n][2 * half], acc[j][n][2 * half + 1]);
+                        *reinterpret_cast<float2*>(e.accb + e.acc + pd[j][half] + cofs[n]) = make_float2(acc[j][n][2 * half], acc[j][n][2 * half + 1]);
                 }
     }
     if (e.edst >= 0) {
@@ -333,7 +343,7 @@ __device__ __forceinline__ void sbc_epilogue_batch(const SbcEpi& e, float* arena
 // one pass of a warp over NS tiles (mt0, mt0 + mstride, ...; only the first `ntile` are real) x NN cout tiles
 template <bool X3, bool SMEM, int NS, int NN>
 __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena,
-                                               const float* wseg, const SbcALane<SMEM>& A, const float* bfrag,
+                                               float* park, const float* wseg, const SbcALane<SMEM>& A, const float* bfrag,
                                                int bstride, int mt0, int mstride, int ntile, int nt0, int lane,
                                                long long* stamp) {
     int po[NS][2];
@@ -359,7 +369,7 @@ __device__ __forceinline__ void sbc_conv_tiles(const SbcOp& op, const SbcGeo& GS
     if (stamp) stamp[1] = clock64();
     sbc_mma_pass<X3, SMEM, NS, NN>(A, po, reinterpret_cast<const int*>(wseg), bfrag, bstride, 0, op.S, acc);
     if (stamp) stamp[2] = clock64();
-    const SbcEpi e = sbc_epi(op, GD);
+    const SbcEpi e = sbc_epi(op, GD, arena, park);
     int pd[NS][2], q0[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) {
@@ -404,7 +414,7 @@ __device__ __forceinline__ void sbc_conv_pooled(const SbcOp& op, const SbcGeo& G
 
 template <bool X3, bool SMEM>
 __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS, const SbcGeo& GD, float* arena,
-                                             const float* wseg, int tid, long long* stamp, int dbg) {
+                                             float* park, const float* wseg, int tid, long long* stamp, int dbg) {
     SbcOp op = op_;
     if (dbg & 1) op.S = 0;                                      // timing experiment: no K steps
     if (dbg & 2) { op.dst = op.acc = op.edst = -1; op.flags &= ~SBC_F_COMPACT; }   // timing experiment: no stores
@@ -442,7 +452,7 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
             if (ks == 1) {
                 int pd[2];
                 sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
-                sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0][0], c[0][1], c[0][2], c[0][3]);
+                sbc_mma_epilogue(sbc_epi(op, GD, arena, park), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0][0], c[0][1], c[0][2], c[0][3]);
             } else {
                 part[warp * 32 + lane] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
             }
@@ -457,13 +467,13 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
             }
             int pd[2];
             sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
-            sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0], c[1], c[2], c[3]);
+            sbc_mma_epilogue(sbc_epi(op, GD, arena, park), arena, wseg, pd[0], pd[1], mt * 16 + (lane >> 2), nt, lane, c[0], c[1], c[2], c[3]);
         }
         return;
     }
 
     if (pool) {
-        const SbcEpi e = sbc_epi(op, GD);
+        const SbcEpi e = sbc_epi(op, GD, arena, park);
         for (int mt = warp; mt < MT; mt += NW) {
             int pd[2];
             sbc_mma_dst_off(op, GD, mt, lane >> 2, pd);
@@ -493,14 +503,14 @@ __device__ __forceinline__ void sbc_conv_mma(const SbcOp& op_, const SbcGeo& GS,
             const float* bf = bf0 + nt0 * 32 * E;
             const bool two = NT - nt0 >= 2;
             if (ntile == 1) {
-                if (two) sbc_conv_tiles<X3, SMEM, 1, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
-                else sbc_conv_tiles<X3, SMEM, 1, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                if (two) sbc_conv_tiles<X3, SMEM, 1, 2>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, 1, 1>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             } else if (ntile == 2 || SBC_MAXNS == 2) {
-                if (two) sbc_conv_tiles<X3, SMEM, 2, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
-                else sbc_conv_tiles<X3, SMEM, 2, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                if (two) sbc_conv_tiles<X3, SMEM, 2, 2>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, 2, 1>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             } else {
-                if (two) sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 2>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
-                else sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 1>(op, GS, GD, arena, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                if (two) sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 2>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
+                else sbc_conv_tiles<X3, SMEM, SBC_MAXNS, 1>(op, GS, GD, arena, park, wseg, A, bf, bstride, mt0, NW, ntile, nt0, lane, stamp);
             }
         }
     }
@@ -613,7 +623,7 @@ __device__ __forceinline__ float sbc_block_sum(float v, float* red, int tid) {
 // INSTR = true: the instrumented build of the same kernel (per-op clock stamps, debug arena dump, timing
 // experiments); the production instantiation carries none of that code in its op loop.
 template <bool SMEM_ARENA, bool X3, bool INSTR>
-__global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_constant__ SbcLaunch L) {
+__global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(const __grid_constant__ SbcLaunch L) {
     extern __shared__ __align__(128) unsigned char sbc_smem_raw[];
     float* smem_f = reinterpret_cast<float*>(sbc_smem_raw);
     const int tid = threadIdx.x;
@@ -626,6 +636,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
     } else {
         arena = L.gws + (size_t)blockIdx.x * (size_t)L.arena_floats;
     }
+    float* park = L.gpark ? L.gpark + (size_t)blockIdx.x * (size_t)L.park_floats : nullptr;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_f + off);   // off is a multiple of 4 floats
     uint16_t* halo = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(bars) + SBC_MISC_BARS);
 
@@ -768,7 +779,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     if ((dbg & 16) || ((dbg & 4) && kind != SBC_OP_CONV_MMA)) kind = -1;   // timing experiments
                 }
                 if (kind == SBC_OP_CONV_MMA) {
-                    sbc_conv_mma<X3, SMEM_ARENA>(op, GS, GD, arena, wseg, tid, sub, dbg);
+                    sbc_conv_mma<X3, SMEM_ARENA>(op, GS, GD, arena, park, wseg, tid, sub, dbg);
                 } else if (kind == SBC_OP_NORM_ELU) {
                     sbc_norm_op(op, GS, arena, wseg, tid);
                 } else if (kind == SBC_OP_MAXPOOL5) {
@@ -779,6 +790,10 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                     sbc_upacc_op(op, GS, GD, arena, tid, SBC_NTHREADS);
                 } else if (kind == SBC_OP_AFFINE) {
                     sbc_affine_op(op, GS, arena, tid, SBC_NTHREADS);
+                } else if (kind == SBC_OP_SPILL) {
+                    sbc_spill_op(op, arena, park, tid, SBC_NTHREADS);
+                } else if (kind == SBC_OP_FILL) {
+                    sbc_fill_op(op, arena, park, tid, SBC_NTHREADS);
                 }
                 // fresh outputs whose halo the planner could not prove clean (interior and halo cells are disjoint)
                 if (op.flags & (SBC_F_ZH_DST | SBC_F_ZH_EDST)) {
@@ -791,8 +806,11 @@ __global__ void __launch_bounds__(SBC_NTHREADS, 1) sbc_ald_kernel(const __grid_c
                 __syncthreads();
             }
             if (INSTR && L.debug_stop >= 0) {   // debugging aid: dump the arena of sample 0 and stop
-                if (b == 0)
+                if (b == 0) {   // arena, then the park area (debug_out holds arena_floats + park_floats)
                     for (int i = tid; i < L.arena_floats; i += SBC_NTHREADS) L.debug_out[i] = arena[i];
+                    if (park)
+                        for (int i = tid; i < L.park_floats; i += SBC_NTHREADS) L.debug_out[L.arena_floats + i] = park[i];
+                }
                 return;
             }
 

@@ -58,11 +58,14 @@ SBC_HD void sbc_mma_a_frag(const float* asrc, int off, int po0, int po1, int pl4
 }
 
 // what the epilogue needs from the op
+// (accb = base the accumulator offset is relative to: the arena, or the park area when SBC_F_ACC_G is set)
 struct SbcEpi {
     int dst, acc, edst, flags, cout, b_rel, pps4;
+    float* accb;
 };
-SBC_HD SbcEpi sbc_epi(const SbcOp& op, const SbcGeo& GD) {
-    return SbcEpi{op.dst, op.acc, op.edst, op.flags, op.cout, op.b_rel, GD.pps * 4};
+SBC_HD SbcEpi sbc_epi(const SbcOp& op, const SbcGeo& GD, float* arena, float* park) {
+    return SbcEpi{op.dst, op.acc, op.edst, op.flags, op.cout, op.b_rel, GD.pps * 4,
+                  (op.flags & SBC_F_ACC_G) ? park : arena};
 }
 
 // Epilogue of one lane for cout tile nt of one pixel tile:  v = c + bias;  dst <- v;  acc <- (v += acc);
@@ -89,7 +92,7 @@ SBC_HD void sbc_mma_epilogue(SbcEpi e, float* arena, const float* wseg, int pd0,
         const int idx = pd + cofs;
         if (e.dst >= 0) *reinterpret_cast<SbcF2*>(arena + e.dst + idx) = v;
         if (e.acc >= 0) {
-            SbcF2* ap = reinterpret_cast<SbcF2*>(arena + e.acc + idx);
+            SbcF2* ap = reinterpret_cast<SbcF2*>(e.accb + e.acc + idx);
             const SbcF2 o = *ap;
             v.x += o.x; v.y += o.y;
             *ap = v;

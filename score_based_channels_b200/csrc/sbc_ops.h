@@ -206,6 +206,25 @@ SBC_HD void sbc_elu_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, 
         });
     }
 }
+// SPILL / FILL (two-CTAs-per-SM plans): a whole tensor -- halo cells included, so the zero-halo invariant travels
+// with it -- is parked in the CTA's slice of a global-memory (L2-resident) area while shared memory is needed for
+// something else.  MT = float4 items.  FILL issues its loads in batches so that one L2 latency covers several.
+SBC_HD void sbc_spill_op(const SbcOp& op, const float* arena, float* park, int tid, int nthr) {
+    const SbcF4* s = reinterpret_cast<const SbcF4*>(arena + op.src);
+    SbcF4* d = reinterpret_cast<SbcF4*>(park + op.dst);
+    for (int i = tid; i < op.MT; i += nthr) d[i] = s[i];
+}
+SBC_HD void sbc_fill_op(const SbcOp& op, float* arena, const float* park, int tid, int nthr) {
+    const SbcF4* s = reinterpret_cast<const SbcF4*>(park + op.src);
+    SbcF4* d = reinterpret_cast<SbcF4*>(arena + op.dst);
+    const int n = op.MT;
+    int i = tid;
+    for (; i + 4 * nthr < n; i += 5 * nthr) {
+        const SbcF4 a = s[i], b = s[i + nthr], c = s[i + 2 * nthr], e = s[i + 3 * nthr], f = s[i + 4 * nthr];
+        d[i] = a; d[i + nthr] = b; d[i + 2 * nthr] = c; d[i + 3 * nthr] = e; d[i + 4 * nthr] = f;
+    }
+    for (; i < n; i += nthr) d[i] = s[i];
+}
 // dst (8 stored channels) = 2*x - 1 on channels 0,1 read from the compact state; channels 2..7 zero
 // (ncsnv2.py:270-271; begin_conv then contracts over one chunk of 8 input channels)
 SBC_HD void sbc_affine_op(const SbcOp& op, const SbcGeo& G, float* arena, int tid, int nthr) {

@@ -13,7 +13,9 @@ enum SbcOpKind : int32_t {
     SBC_OP_UPACC = 5,     // acc += bilinear(src -> oh x ow, align_corners=True)   (layers.py:182-183)
     SBC_OP_CONV_MMA = 6,  // Conv2d k in {1,3}, stride 1, pad = dil*(k/2) (layers.py:28-60) + fused epilogue,
                           // contraction on tensor cores (mma.sync m16n8k8 TF32)
-    SBC_OP_LAST = 6,
+    SBC_OP_SPILL = 7,     // park[dst .. dst + 4*MT) = arena[src ..]: a whole tensor (halo included) leaves shared memory
+    SBC_OP_FILL = 8,      // arena[dst .. dst + 4*MT) = park[src ..]: ... and comes back (two-CTAs-per-SM plans, program.py)
+    SBC_OP_LAST = 8,
 };
 
 enum SbcOpFlags : int32_t {
@@ -24,6 +26,8 @@ enum SbcOpFlags : int32_t {
     SBC_F_ZH_EDST = 16,   // program.py:_halo_analysis); same for edst
     SBC_F_UNIT = 32,      // conv with fewer (pixel tile, cout tile) units than warps: unit u is owned by the `ks`
                           // warps u*ks .. u*ks+ks-1 (ks = 1: one warp, no K split)
+    SBC_F_ACC_G = 64,     // conv: `acc` is an offset into the CTA's park area in global memory (L2), not into the arena:
+                          // a residual stream that only the epilogues read-modify-write needs no shared memory
 };
 
 // Geometry of every tensor of one resolution: channel-interleaved by 4 (one pixel of one plane = 4 channels

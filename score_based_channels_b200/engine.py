@@ -46,7 +46,7 @@ class PackedModel:
         d = _lib.ModelDesc(ngf, Nt, Nr, channels, self._tab.ctypes.data, self._tab.shape[0], self._geo.ctypes.data,
                            len(p.geos), p.blob.ctypes.data,
                            p.blob.size, p.arena_floats, p.in_off, p.out_off, p.post_off, p.max_w_len,
-                           self.sigmas.ctypes.data, self.sigmas.size, p.conv_flops, p.nthreads)
+                           self.sigmas.ctypes.data, self.sigmas.size, p.conv_flops, p.nthreads, p.park_floats)
         h = C.c_void_p()
         _lib.check(_lib.lib().sbc_model_create(C.byref(d), device, C.byref(h)), "sbc_model_create")
         self.handle = h

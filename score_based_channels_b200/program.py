@@ -45,6 +45,8 @@ OP_ELU = 3        # dst = ELU(src)
 OP_MAXPOOL5 = 4   # dst = maxpool 5x5 stride 1 pad 2
 OP_UPACC = 5      # acc += bilinear(src -> (oh,ow), align_corners=True)
 OP_CONV_MMA = 6   # Conv2d k in {1,3} (+ fused epilogue) on tensor cores (mma.sync m16n8k8 TF32)
+OP_SPILL = 7      # park[dst:dst+4*MT] = arena[src:...]   (whole tensor incl. halo leaves shared memory)
+OP_FILL = 8       # arena[dst:dst+4*MT] = park[src:...]
 
 # ---- flags ----------------------------------------------------------------
 F_POOL = 1        # conv followed by 2x2 mean-pool (ConvMeanPool)
@@ -56,6 +58,18 @@ F_COMPACT = 4     # conv epilogue writes couts (0,1) as compact (re, im) pairs: 
 F_ZH_DST = 8      # the halo of the fresh tensor `dst` must be re-zeroed (set by ProgramBuilder._halo_analysis)
 F_ZH_EDST = 16    # same for `edst`
 F_UNIT = 32       # conv: unit (pixel tile, cout tile) u is owned by warps u*ks .. u*ks+ks-1 (ks = 1: no K split)
+F_ACC_G = 64      # conv: `acc` is an offset into the CTA's park area (global memory / L2) instead of the arena
+
+# Shared memory of one B200 SM that CTAs can share (cudaDevAttrMaxSharedMemoryPerMultiprocessor), the per-CTA
+# reservation and an upper bound of the kernel's static shared memory: a plan whose arena + misc region is at most
+# smem_budget_bytes(2) runs with TWO CTAs (= two channel realisations in flight) per SM.
+SMEM_PER_SM = 233472
+SMEM_RESERVED_PER_CTA = 1024
+SMEM_STATIC_BOUND = 1024
+
+
+def smem_budget_bytes(ctas_per_sm: int) -> int:
+    return SMEM_PER_SM // ctas_per_sm - SMEM_RESERVED_PER_CTA - SMEM_STATIC_BOUND
 
 OP_FIELDS = ("kind", "flags", "src", "dst", "acc", "edst", "cin", "cout", "h", "w", "ksize", "dil",
              "w_off", "w_len", "b_rel", "sgeo", "dgeo", "ks", "scratch", "oh", "ow", "next_w", "tapmask",
@@ -153,6 +167,15 @@ class Program:
     max_w_len: int
     conv_flops: int                  # dense conv FLOPs / forward / sample (reference convention)
     precision: str
+    park_floats: int = 0             # per-CTA park area in global memory (SPILL / FILL / F_ACC_G); 0: none
+
+    def misc_bytes(self) -> int:
+        """Shared-memory misc region next to the arena (csrc/sbc_api.cu): two mbarriers + the halo-pixel lists."""
+        halo = sum(g.pps - g.h * g.w for g in self.geos)
+        return (64 + 2 * halo + 15) // 16 * 16
+
+    def smem_bytes(self) -> int:
+        return 4 * self.arena_floats + self.misc_bytes()
 
     def op_table(self) -> np.ndarray:
         t = np.zeros((len(self.ops), OP_WORDS), dtype=np.int32)
@@ -234,6 +257,7 @@ class _Planner:
         self.died: Dict[str, int] = {}
         self.size: Dict[str, int] = {}
         self.offs: Dict[str, int] = {}
+        self.pinned: Dict[str, int] = {}     # name -> fixed offset (placed before everything else)
         self.peak = 0
 
     def alloc(self, name: str, n: int, now: int, died: Optional[int] = None) -> None:
@@ -250,8 +274,12 @@ class _Planner:
     def solve(self, end: int) -> None:
         for n in self.size:
             self.died.setdefault(n, end)
-        order = sorted(self.size, key=lambda n: (-self.size[n], self.born[n]))
+        order = sorted((n for n in self.size if n not in self.pinned), key=lambda n: (-self.size[n], self.born[n]))
         placed: List[str] = []
+        for n, off in self.pinned.items():
+            self.offs[n] = off
+            placed.append(n)
+            self.peak = max(self.peak, off + self.size[n])
         for n in order:
             busy = sorted((self.offs[m], self.size[m]) for m in placed
                           if self.born[m] < self.died[n] and self.born[n] < self.died[m])
@@ -271,15 +299,31 @@ def tf32_rna(x: np.ndarray) -> np.ndarray:
     return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+class _G:
+    """Reference to a tensor in the per-CTA park area (global memory): name + float shift."""
+
+    def __init__(self, name: str, shift: int = 0):
+        self.name, self.shift = name, shift
+
+
 class ProgramBuilder:
-    """Builds the op list for one (ngf, H, W) instance of NCSNv2Deepest."""
+    """Builds the op list for one (ngf, H, W) instance of NCSNv2Deepest.
+
+    ``park=True`` plans for TWO resident CTAs per SM (two channel realisations in flight per SM):
+    the arena must stay under half of an SM's shared memory, so (a) the residual / skip streams of the largest
+    resolution live in a per-CTA *park area* in global memory (L2 resident) -- the conv epilogues read-modify-write them
+    there (``F_ACC_G``) and an ``OP_FILL`` brings a copy into the arena for the ops that gather from it; (b) the skip
+    tensors of the other resolutions are spilled between their producer and their RefineBlock; (c) parameter segments
+    are capped at half the size (more cout chunks)."""
+
+    BIG_BYTES = 24 * 1024        # park mode: tensors at least this large are "big" (their streams live in the park area)
 
     # largest parameter segment (floats) one slot of the shared-memory ring holds; convs whose fragment
     # array is bigger are split into cout chunks (each chunk is its own op)
     SLOT_FLOATS = 9300
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, H: int, W: int,
-                 channels: int = 2, nthreads: int = 512, precision: str = "tf32x3"):
+                 channels: int = 2, nthreads: int = 512, precision: str = "tf32x3", park: bool = False):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % (PRECISIONS,))
         if H <= 0 or W <= 0 or H % 8 or W % 8:
@@ -288,6 +332,11 @@ class ProgramBuilder:
         self.sd = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
         self.ngf, self.H, self.W, self.channels = ngf, H, W, channels
         self.nthreads = nthreads
+        self.park = park
+        if park:
+            self.SLOT_FLOATS = 4700
+        self.goff: Dict[str, int] = {}          # park area: tensor name -> float offset (bump allocated, never reused)
+        self.gtop = 0
         self.ar = _Planner()
         self.ops: List[Op] = []
         self.blob: List[np.ndarray] = []
@@ -337,6 +386,51 @@ class ProgramBuilder:
         for n in names:
             self.ar.free(n, len(self.ops))
 
+    # -- park area (park mode) --------------------------------------------
+    def live(self, name: str) -> bool:
+        return name in self.ar.size and name not in self.ar.died
+
+    def release(self, name: str) -> None:
+        if self.live(name):
+            self.free(name)
+
+    def is_big(self, name: str) -> bool:
+        c, h, w = self.shape[name]
+        return self.park and self.geos[self.gi(h, w)].floats(c) * 4 >= self.BIG_BYTES
+
+    def _copy_op(self, kind: int, src, dst, name: str, label: str) -> None:
+        c, h, w = self.shape[name]
+        g = self.gi(h, w)
+        self.ops.append(Op(kind, 0, src, dst, cin=c, cout=c, h=h, w=w, sgeo=g, dgeo=g, oh=h, ow=w,
+                           MT=self.geos[g].floats(c) // 4, name="%s %s" % (label, name)))
+
+    def spill(self, name: str) -> None:
+        """Copy the (live) arena tensor ``name`` into its park slot; the arena copy stays live until freed."""
+        assert self.live(name)
+        if name not in self.goff:
+            c, h, w = self.shape[name]
+            self.goff[name] = self.gtop
+            self.gtop += self.geos[self.gi(h, w)].floats(c)
+        self._copy_op(OP_SPILL, name, _G(name), name, "spill")
+
+    def park_out(self, name: str) -> None:
+        self.spill(name)
+        self.free(name)
+
+    def fill(self, gname: str) -> str:
+        """Bring the parked tensor back into a fresh arena tensor (returned); the park copy stays valid."""
+        c, h, w = self.shape[gname]
+        t = self.tmp(c, h, w, "f")
+        self._copy_op(OP_FILL, _G(gname), t, gname, "fill")
+        return t
+
+    def _copy_raw(self, kind: int, src, dst, nfloats: int, label: str) -> None:
+        assert nfloats % 4 == 0
+        self.ops.append(Op(kind, 0, src, dst, MT=nfloats // 4, name=label))
+
+    def smem_of(self, name: str) -> str:
+        return name if self.live(name) else self.fill(name)
+
     # -- parameter blob ---------------------------------------------------
     def _push(self, arrs: List[np.ndarray]) -> Tuple[int, int, List[int]]:
         off = self.blob_len
@@ -355,7 +449,7 @@ class ProgramBuilder:
     # -- ops --------------------------------------------------------------
     def conv(self, prefix: str, src: str, dst: Optional[str] = None, acc: Optional[str] = None,
              edst: Optional[str] = None, dil: int = 1, pool: bool = False, compact: bool = False,
-             siblings=()) -> None:
+             siblings=(), acc_g: bool = False) -> None:
         """One Conv2d (reference ``layers.py:28-60``) + fused epilogue, as an implicit GEMM on tensor cores:
 
             D[16 pixels, 8 couts] += A[16 pixels, 8 cins] . B[8 cins, 8 couts]   per K step (live tap, cin chunk)
@@ -455,12 +549,16 @@ class ProgramBuilder:
                     ks *= 2
             scratch = self.tmp_raw(units * ks * 32 * 4, "ksp") if ks > 1 else None
             flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0) | (F_UNIT if unit else 0)
+            if acc_g:
+                assert acc is not None and acc in self.goff and not self.live(acc), "acc_g: the stream must live in the park area only"
+                flags |= F_ACC_G
             if compact:
                 assert nt_chunk == NT and cout == 2 and acc is None and edst is None
                 shift = lambda name: -1 if name is None else name
             else:
                 shift = lambda name: -1 if name is None else (name, (co0 // 4) * dgeo.pps * 4)
-            op = Op(OP_CONV_MMA, flags, src, shift(dst), shift(acc), shift(edst), cin0, co1 - co0, h, w, k0,
+            acc_ref = _G(acc, (co0 // 4) * dgeo.pps * 4) if acc_g else shift(acc)
+            op = Op(OP_CONV_MMA, flags, src, shift(dst), acc_ref, shift(edst), cin0, co1 - co0, h, w, k0,
                     dil, w_off, w_len, rels[2] if bias is not None else -1, self.gi(h, w), self.gi(oh, ow),
                     ks, scratch if scratch is not None else -1, oh, ow, tapmask=tapmask, MT=MT, NT=ntc,
                     S=S, frag_rel=rels[1], low=ilog2(ow),
@@ -531,6 +629,23 @@ class ProgramBuilder:
         (same-shape blocks only): tensor that additionally receives ELU(output) from the last conv's epilogue."""
         cin, h, w = self.shape[x]
         d = dil or 1
+        if self.is_big(x) and cout == cin and not down:
+            # park mode: the stream x lives in the park area; only its normalised copy and conv1's output are in the arena
+            if x not in self.goff:
+                self.spill(x)
+            s_ = self.smem_of(x)
+            t = self.tmp(cin, h, w)
+            self.norm_elu(p + ".normalize1", s_, t)
+            self.free(s_)
+            t2 = self.tmp(cout, h, w)
+            self.conv(p + ".conv1", t, dst=t2, dil=d)
+            self.free(t)
+            t3 = self.tmp(cout, h, w)
+            self.norm_elu(p + ".normalize2", t2, t3)
+            self.free(t2)
+            self.conv(p + ".conv2", t3, acc=x, edst=elu_out, dil=d, acc_g=True)
+            self.free(t3)
+            return x
         t = self.tmp(cin, h, w)
         self.norm_elu(p + ".normalize1", x, t)
         t2 = self.tmp(cin if down else cout, h, w)
@@ -563,19 +678,30 @@ class ProgramBuilder:
         ``e_in`` (optional) already holds ELU(x).  Returns (x, ELU(x) or None)."""
         c, h, w = self.shape[x]
         e = e_in
+        big = self.is_big(x)       # park mode: x is only ever read-modify-written by the conv epilogues, in the park area
+        if big:
+            if x not in self.goff:
+                self.spill(x)
+            if e is not None:
+                self.release(x)
         for i in range(n_blocks):
             if e is None:
                 e = self.tmp(c, h, w)
-                self.elu(x, e)
+                if big:
+                    s_ = self.smem_of(x)
+                    self.elu(s_, e)
+                    self.free(s_)
+                else:
+                    self.elu(x, e)
             u = self.tmp(c, h, w)
             self.conv("%s.%d_1_conv" % (p, i + 1), e, edst=u)      # u = ELU(conv1(ELU(x)))
             last = (i == n_blocks - 1)
             if last and not want_elu_out:
                 self.free(e)
                 e = None
-                self.conv("%s.%d_2_conv" % (p, i + 1), u, acc=x)
+                self.conv("%s.%d_2_conv" % (p, i + 1), u, acc=x, acc_g=big)
             else:
-                self.conv("%s.%d_2_conv" % (p, i + 1), u, acc=x, edst=e)  # x += conv2(u); e = ELU(x)
+                self.conv("%s.%d_2_conv" % (p, i + 1), u, acc=x, edst=e, acc_g=big)  # x += conv2(u); e = ELU(x)
             self.free(u)
         return x, e
 
@@ -584,15 +710,18 @@ class ProgramBuilder:
 
         Returns (sum, ELU(sum)) -- the ELU feeds the output RCU that always follows."""
         c, h, w = self.shape[e]
-        self.free(x)
+        self.release(x)
+        big = self.is_big(e)
         m = self.tmp(c, h, w)
         self.maxpool5(e, m)
+        if big:                    # park mode: the running sum moves to the park area
+            self.park_out(e)
         path = self.tmp(c, h, w)
-        self.conv(p + ".convs.0", m, dst=path, acc=e)
+        self.conv(p + ".convs.0", m, dst=path, acc=e, acc_g=big)
         self.maxpool5(path, m)
         self.free(path)
         e2 = self.tmp(c, h, w)
-        self.conv(p + ".convs.1", m, acc=e, edst=e2)
+        self.conv(p + ".convs.1", m, acc=e, edst=e2, acc_g=big)
         self.free(m)
         return e, e2
 
@@ -609,19 +738,24 @@ class ProgramBuilder:
         c0, oh, ow = self.shape[hs[0]]
         if len(hs) > 1:
             s = self.tmp(features, oh, ow, "s")
-            e = self.tmp(features, oh, ow, "e")
             same = self.shape[hs[1]][1:] == (oh, ow)
+            if same:
+                e = self.tmp(features, oh, ow, "e")
             if same:   # bilinear to the same size with align_corners=True is the identity: one summed conv
-                self.conv(p + ".msf.convs.0", hs[0], dst=s, edst=e, siblings=[(p + ".msf.convs.1", hs[1], 1)])
-                self.free(hs[0])
-                self.free(hs[1])
+                a0, a1 = self.smem_of(hs[0]), self.smem_of(hs[1])
+                self.conv(p + ".msf.convs.0", a0, dst=s, edst=e, siblings=[(p + ".msf.convs.1", a1, 1)])
+                self.free(a0)
+                self.free(a1)
             else:
-                self.conv(p + ".msf.convs.0", hs[0], dst=s)
-                self.free(hs[0])
+                a0 = self.smem_of(hs[0])   # (park mode: the adapted stream comes back from the park area)
+                self.conv(p + ".msf.convs.0", a0, dst=s)
+                self.free(a0)
                 _, lh, lw = self.shape[hs[1]]
                 lo = self.tmp(features, lh, lw, "lo")
-                self.conv(p + ".msf.convs.1", hs[1], dst=lo)
-                self.free(hs[1])
+                a1 = self.smem_of(hs[1])
+                self.conv(p + ".msf.convs.1", a1, dst=lo)
+                self.free(a1)
+                e = self.tmp(features, oh, ow, "e")
                 self.upacc(lo, s, edst=e)
                 self.free(lo)
         else:
@@ -633,33 +767,53 @@ class ProgramBuilder:
     def build(self) -> Program:
         ngf, H, W = self.ngf, self.H, self.W
         assert ngf % 8 == 0, "ngf must be a multiple of 8 (one MMA K chunk = 8 input channels = two planes)"
-        xin = self.new_raw("x_in", self.channels * H * W)       # compact (re, im) pairs
+        nx = self.channels * H * W
+        xin = self.new_raw("x_in", nx)                          # compact (re, im) pairs
+        self.ar.pinned[xin] = 0
         a = self.tmp(8, H, W)                                   # begin_conv reads one chunk of 8 input channels
         self.affine(xin, a)
+        if self.park:   # the sampler state waits in the park area while the network runs; it returns to the SAME offset
+            self.goff["x_in"] = self.gtop
+            self.gtop += nx
+            self._copy_raw(OP_SPILL, xin, _G("x_in"), nx, "spill x_in")
+            self.free(xin)
         o = self.tmp(ngf, H, W, "o")
         self.conv("begin_conv", a, dst=o)
         self.free(a)
         l1 = self.residual("res1.1", self.residual("res1.0", o, ngf, False, None), ngf, False, None)
+        pk = self.park
+        keep = lambda name: self.park_out(name) if (pk and name is not None and self.live(name)) else None
+        back = lambda name: self.fill(name) if (pk and name is not None and not self.live(name)) else name
         # l4 and l5 also emit ELU(skip) from the epilogue of their last conv (the first thing their RefineBlock does
         # with them); for the others a stand-alone ELU op later is cheaper than arena held across the phase where
         # the two largest parameter staging buffers are live (it would push the plan past the 227 KB of one SM)
+        # park mode: every skip tensor waits for its RefineBlock in the park area (keep / back are no-ops otherwise)
         l2, _ = self._stage("res2", l1, 2 * ngf, None)
         l3, el3 = self._stage("res3", l2, 2 * ngf, None)
+        keep(l2)
         l31, el31 = self._stage("res31", l3, 2 * ngf, None)
+        keep(l3); keep(el3)
         l4, el4 = self._stage("res4", l31, 4 * ngf, 2, want_elu=True)
+        keep(l31); keep(el31)
         l5, el5 = self._stage("res5", l4, 4 * ngf, 4, want_elu=True)
+        keep(l4); keep(el4)
         r1, e1 = self.refine("refine1", [l5], [el5], 4 * ngf)
-        r2, e2 = self.refine("refine2", [l4, r1], [el4, e1], 2 * ngf)
-        r31, e31 = self.refine("refine31", [l31, r2], [el31, e2], 2 * ngf)
-        r3, e3 = self.refine("refine3", [l3, r31], [el3, e31], 2 * ngf)
-        r4, e4 = self.refine("refine4", [l2, r3], [None, e3], ngf)
+        r2, e2 = self.refine("refine2", [back(l4), r1], [back(el4), e1], 2 * ngf)
+        r31, e31 = self.refine("refine31", [back(l31), r2], [back(el31), e2], 2 * ngf)
+        r3, e3 = self.refine("refine3", [back(l3), r31], [back(el3), e31], 2 * ngf)
+        r4, e4 = self.refine("refine4", [back(l2), r3], [None, e3], ngf)
         r5, _ = self.refine("refine5", [l1, r4], [None, e4], ngf, end=True)
         t = self.tmp(ngf, H, W)
-        self.norm_elu("normalizer", r5, t)
-        self.free(r5)
+        r5s = self.smem_of(r5)
+        self.norm_elu("normalizer", r5s, t)
+        self.free(r5s)
         out = self.new_raw("net_out", self.channels * H * W)    # compact (re, im) pairs
         self.conv("end_conv", t, dst=out, compact=True)
         self.free(t)
+        if self.park:
+            xin2 = self.new_raw("x_in.back", nx)
+            self.ar.pinned[xin2] = 0
+            self._copy_raw(OP_FILL, _G("x_in"), xin2, nx, "fill x_in")
         # scratch for the sampler phases that follow the network (residual P*x-y, reductions)
         post = self.new_raw("post", 2 * H * W)
         blob = np.concatenate(self.blob) if self.blob else np.zeros(0, np.float32)
@@ -691,7 +845,9 @@ class ProgramBuilder:
                     tab[m["step0"]:m["step0"] + n] += m["src_off"] - base
             for f in ("src", "dst", "acc", "edst", "scratch", "wbuf"):
                 v = getattr(op, f)
-                if isinstance(v, tuple):
+                if isinstance(v, _G):
+                    setattr(op, f, self.goff[v.name] + v.shift)
+                elif isinstance(v, tuple):
                     setattr(op, f, self.ar.offs[v[0]] + v[1])
                 elif isinstance(v, str):
                     setattr(op, f, self.ar.offs[v])
@@ -701,7 +857,7 @@ class ProgramBuilder:
                                            (self.ar.offs[post], 2 * H * W)])
         return Program(self.ops, self.geos, self.ar.peak, blob, self.ar.offs[xin], self.ar.offs[out],
                        self.ar.offs[post], H, W, ngf, self.channels, self.nthreads, max_w_len, self.flops,
-                       self.precision)
+                       self.precision, self.gtop)
 
     def _halo_analysis(self, arena_floats: int, raw_regions) -> None:
         """Decide which ops must re-zero the halo of the tensors they create (flags F_ZH_DST / F_ZH_EDST).
@@ -754,6 +910,13 @@ class ProgramBuilder:
             elif op.kind == OP_UPACC:
                 if op.edst >= 0 and fresh(op.edst, op.dgeo, op.cin):
                     op.flags |= F_ZH_EDST
+            elif op.kind == OP_SPILL:
+                pass
+            elif op.kind == OP_FILL:
+                if op.cin == 0:
+                    raw(op.dst, 4 * op.MT)         # raw buffer (the sampler state)
+                else:
+                    fresh(op.dst, op.dgeo, op.cin) # the copy brings its (zero) halo along: tag the planes, no re-zeroing
             else:
                 raise ValueError(op.kind)
 
@@ -762,20 +925,29 @@ class ProgramBuilder:
         Returns (output, ELU(output) or None)."""
         cin, h, w = self.shape[skip]
         d = dil or 1
+        big = self.is_big(skip)    # park mode: the skip stream lives in the park area, arena copies come and go
+        if big and skip not in self.goff:
+            self.spill(skip)
+        s_ = self.smem_of(skip) if big else skip
         t = self.tmp(cin, h, w)
-        self.norm_elu(p + ".0.normalize1", skip, t)
+        self.norm_elu(p + ".0.normalize1", s_, t)
+        if big:
+            self.free(s_)
         t2 = self.tmp(cin, h, w)
         self.conv(p + ".0.conv1", t, dst=t2, dil=d)
         self.free(t)
         t3 = self.tmp(cin, h, w)
         self.norm_elu(p + ".0.normalize2", t2, t3)
         self.free(t2)
+        s_ = self.smem_of(skip) if big else skip
         if dil is None:
             out = self.tmp(cout, h // 2, w // 2, "o")
-            self.conv(p + ".0.conv2.conv", t3, dst=out, pool=True, siblings=[(p + ".0.shortcut.conv", skip, 1)])
+            self.conv(p + ".0.conv2.conv", t3, dst=out, pool=True, siblings=[(p + ".0.shortcut.conv", s_, 1)])
         else:
             out = self.tmp(cout, h, w, "o")
-            self.conv(p + ".0.conv2", t3, dst=out, dil=d, siblings=[(p + ".0.shortcut", skip, d)])
+            self.conv(p + ".0.conv2", t3, dst=out, dil=d, siblings=[(p + ".0.shortcut", s_, d)])
+        if big:
+            self.free(s_)
         self.free(t3)
         e = None
         if want_elu:
@@ -785,8 +957,20 @@ class ProgramBuilder:
 
 
 def build_program(state: Dict[str, np.ndarray], ngf: int, H: int, W: int, channels: int = 2,
-                  nthreads: int = 512, precision: str = "tf32x3") -> Program:
-    return ProgramBuilder(state, ngf, H, W, channels, nthreads, precision).build()
+                  nthreads: int = 256, precision: str = "tf32x3", park: Optional[bool] = None) -> Program:
+    """``park=None``: plan for two resident CTAs per SM when that plan fits (``smem_budget_bytes(2)``), else the
+    single-CTA plan (which itself falls back to a global-memory arena in the library when it exceeds one SM)."""
+    if park is None:
+        pp = ProgramBuilder(state, ngf, H, W, channels, nthreads, precision, park=True).build()
+        if pp.smem_bytes() <= smem_budget_bytes(2):
+            return pp
+        p1 = ProgramBuilder(state, ngf, H, W, channels, nthreads, precision, park=False).build()
+        # one CTA per SM: the plain plan when it fits an SM, else the park plan when THAT fits (shared-memory resident
+        # beats the global-memory arena), else the plain plan from a global-memory arena
+        if p1.smem_bytes() > smem_budget_bytes(1) and pp.smem_bytes() <= smem_budget_bytes(1):
+            return pp
+        return p1
+    return ProgramBuilder(state, ngf, H, W, channels, nthreads, precision, park=park).build()
 
 
 # ---------------------------------------------------------------------------
@@ -819,18 +1003,24 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
     """Run the program on one sample ``x`` ([channels,H,W] float32 torch tensor) with torch CPU ops (fp32
     arithmetic; in "tf32" mode the decoded weights carry their TF32 rounding).
 
-    Returns (raw network output [channels,H,W] (before the /sigma of ncsnv2.py:295-298), arena)."""
+    Returns (raw network output [channels,H,W] (before the /sigma of ncsnv2.py:295-298), arena); the park area of a
+    two-CTAs-per-SM plan is attached to the arena tensor as ``arena.park``."""
     import torch
     import torch.nn.functional as F
 
     arena = torch.zeros(prog.arena_floats, dtype=torch.float32)
+    park = torch.zeros(max(prog.park_floats, 1), dtype=torch.float32)
     blob = torch.from_numpy(prog.blob)
     rd = lambda off, c, h, w: prog.read(arena, off, c, h, w)
     prog.write_input(arena, x.float())
     for i, op in enumerate(prog.ops):
         if upto is not None and i >= upto:
             break
-        if op.kind == OP_AFFINE:
+        if op.kind == OP_SPILL:
+            park[op.dst:op.dst + 4 * op.MT] = arena[op.src:op.src + 4 * op.MT]
+        elif op.kind == OP_FILL:
+            arena[op.dst:op.dst + 4 * op.MT] = park[op.src:op.src + 4 * op.MT]
+        elif op.kind == OP_AFFINE:
             xin = arena[op.src:op.src + op.cin * op.h * op.w].view(op.h, op.w, op.cin).permute(2, 0, 1)
             prog.write(arena, op.dst, 2 * xin - 1.0, cstore=op.cout)
         elif op.kind == OP_ELU:
@@ -872,11 +1062,13 @@ def simulate(prog: Program, x, upto: Optional[int] = None):
             elif op.dst >= 0:
                 prog.write(arena, op.dst, v)
             if op.acc >= 0:
-                v = rd(op.acc, op.cout, op.oh, op.ow) + v
-                prog.write(arena, op.acc, v)
+                accb = park if (op.flags & F_ACC_G) else arena
+                v = prog.read(accb, op.acc, op.cout, op.oh, op.ow) + v
+                prog.write(accb, op.acc, v)
             if op.edst >= 0:
                 prog.write(arena, op.edst, F.elu(v))
         else:
             raise ValueError(op.kind)
     out = prog.read_output(arena).clone()
+    arena.park = park
     return out, arena

@@ -15,7 +15,7 @@
 // with the operand rounding of the device path (3xTF32: a = trunc(a) + (a - trunc(a)), the low parts
 // truncated by the tensor core, weights split the same way; TF32: rna on activations, weights pre-rounded),
 // then the per-lane epilogue runs.
-static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena, const float* wseg, int nthr) {
+static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float* arena, float* park, const float* wseg, int nthr) {
     const bool x3 = (op.flags & SBC_F_X3) != 0;
     const int nq = (op.flags & SBC_F_POOL) ? 4 : 1;
     const int* steptab = reinterpret_cast<const int*>(wseg);
@@ -72,7 +72,7 @@ static void conv_mma(const SbcOp& op, const SbcGeo& GS, const SbcGeo& GD, float*
                 const float c[4] = {D[g][2 * t], D[g][2 * t + 1], D[g + 8][2 * t], D[g + 8][2 * t + 1]};
                 int pd[2];
                 sbc_mma_dst_off(op, GD, mt, g, pd);
-                sbc_mma_epilogue(sbc_epi(op, GD), arena, wseg, pd[0], pd[1], mt * 16 + g, nt, lane, c[0], c[1], c[2], c[3]);
+                sbc_mma_epilogue(sbc_epi(op, GD, arena, park), arena, wseg, pd[0], pd[1], mt * 16 + g, nt, lane, c[0], c[1], c[2], c[3]);
             }
         }
 }
@@ -101,7 +101,7 @@ static void norm_op(const SbcOp& op, const SbcGeo& G, float* arena, const float*
 }
 
 extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t* geo_table, const float* blob,
-                               float* arena, int nthr, int stop_op) {
+                               float* arena, float* park, int nthr, int stop_op) {
     const SbcOp* ops = reinterpret_cast<const SbcOp*>(op_table);
     const SbcGeo* geo = reinterpret_cast<const SbcGeo*>(geo_table);
     for (int i = 0; i < n_ops; i++) {
@@ -112,7 +112,7 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t
         const SbcGeo& GD = geo[op.dgeo];
         switch (op.kind) {
             case SBC_OP_CONV_MMA:
-                conv_mma(op, GS, GD, arena, wseg, nthr);
+                conv_mma(op, GS, GD, arena, park, wseg, nthr);
                 break;
             case SBC_OP_NORM_ELU:
                 norm_op(op, GS, arena, wseg, nthr);
@@ -128,6 +128,12 @@ extern "C" int emu_run_program(const int32_t* op_table, int n_ops, const int32_t
                 break;
             case SBC_OP_UPACC:
                 for (int t = 0; t < nthr; t++) sbc_upacc_op(op, GS, GD, arena, t, nthr);
+                break;
+            case SBC_OP_SPILL:
+                for (int t = 0; t < nthr; t++) sbc_spill_op(op, arena, park, t, nthr);
+                break;
+            case SBC_OP_FILL:
+                for (int t = 0; t < nthr; t++) sbc_fill_op(op, arena, park, t, nthr);
                 break;
             default:
                 return -2;

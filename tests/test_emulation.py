@@ -25,7 +25,7 @@ def emu():
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
     lib = C.CDLL(so)
-    lib.emu_run_program.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.emu_run_program.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.emu_langevin_step.restype = C.c_float
     lib.emu_langevin_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_uint64,
@@ -37,12 +37,14 @@ def emu():
 def run_emu(lib, prog, x, stop=-1):
     # garbage-filled arena: every op must (re)establish the zero halos it relies on
     arena = np.random.default_rng(5).standard_normal(prog.arena_floats).astype(np.float32) * 100
+    park = np.random.default_rng(6).standard_normal(max(prog.park_floats, 4)).astype(np.float32) * 100
     prog.write_input(arena, np.asarray(x, np.float32))
     tab = np.ascontiguousarray(prog.op_table())
     geo = np.ascontiguousarray(prog.geo_table())
     rc = lib.emu_run_program(tab.ctypes.data, tab.shape[0], geo.ctypes.data, prog.blob.ctypes.data, arena.ctypes.data,
-                             prog.nthreads, stop)
+                             park.ctypes.data, prog.nthreads, stop)
     assert rc == 0
+    run_emu.park = park
     return arena
 
 
@@ -72,7 +74,8 @@ def test_emulated_ops_match_simulator_op_by_op(emu, prec):
     sd = params.random_state(8, seed=1)
     prog = program.build_program(sd, 8, 64, 16, precision=prec)
     x = (np.random.default_rng(0).standard_normal((2, 64, 16)) * 3).astype(np.float32)
-    for k in list(range(1, 40)) + list(range(40, len(prog.ops), 7)) + [len(prog.ops)]:
+    assert prog.park_floats > 0, "the 64x16 ngf-8 plan is expected to be the two-CTAs-per-SM (park) plan"
+    for k in list(range(1, 40)) + list(range(40, len(prog.ops), 7)) + list(range(len(prog.ops) - 35, len(prog.ops) + 1)):
         _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
         ea = run_emu(emu, prog, x, stop=k)
         op = prog.ops[k - 1]
@@ -80,10 +83,20 @@ def test_emulated_ops_match_simulator_op_by_op(emu, prec):
             e, r = prog.read_output(ea), prog.read_output(ra.numpy())
             assert np.abs(e - r).max() / (np.abs(r).max() + 1e-6) < 5e-5, (k - 1, op.name)
             continue
-        for off in (op.dst, op.acc, op.edst):
+        if op.kind == program.OP_SPILL or (op.kind == program.OP_FILL and op.cin == 0):
+            n = 4 * op.MT   # whole-tensor copies into the park area / raw sampler state coming back
+            if op.kind == program.OP_SPILL:
+                e, r = run_emu.park[op.dst:op.dst + n], ra.park.numpy()[op.dst:op.dst + n]
+            else:
+                e, r = ea[op.dst:op.dst + n], ra.numpy()[op.dst:op.dst + n]
+            assert np.abs(e - r).max() / (np.abs(r).max() + 1e-6) < 5e-5, (k - 1, op.name)
+            continue
+        acc_g = bool(op.flags & program.F_ACC_G)
+        for fi, off in enumerate((op.dst, op.acc, op.edst)):
             if off >= 0:
-                e = prog.read(ea, off, op.cout, op.oh, op.ow)
-                r = prog.read(ra.numpy(), off, op.cout, op.oh, op.ow)
+                eb, rb = (run_emu.park, ra.park.numpy()) if (fi == 1 and acc_g) else (ea, ra.numpy())
+                e = prog.read(eb, off, op.cout, op.oh, op.ow)
+                r = prog.read(rb, off, op.cout, op.oh, op.ow)
                 d, sc = np.abs(e - r).max(), np.abs(r).max() + 1e-6
                 assert d / sc < 5e-5, (k - 1, op.name, op.kind, d, sc)
 

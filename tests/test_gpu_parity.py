@@ -44,7 +44,7 @@ def _rel(a, b):
 
 def test_native_library_is_the_one_running(dev):
     L = _lib.lib()
-    assert L.sbc_version() == 200
+    assert L.sbc_version() == 210
     sd, m = _model(8, 1, dev)
     info = m.packed(64, 16, dev).info()
     assert info.num_sms >= 100 and info.threads_per_cta == L.sbc_threads_per_cta() and info.threads_per_cta in (256, 512, 1024)
@@ -267,21 +267,29 @@ def test_debug_arena_matches_schedule_simulator_op_by_op(dev, prec):
     prog = pm.prog
     x = (np.random.default_rng(0).standard_normal((2, 64, 16)) * 3).astype(np.float32)
     xd = torch.from_numpy(x).to(dev)
-    arena = torch.empty(prog.arena_floats, dtype=torch.float32, device=dev)
-    for k in list(range(1, 60, 2)) + list(range(60, len(prog.ops), 5)) + [len(prog.ops)]:
+    assert prog.park_floats > 0 and pm.info().ctas_per_sm == 2, "expected the two-CTAs-per-SM (park) plan"
+    arena = torch.empty(prog.arena_floats + prog.park_floats, dtype=torch.float32, device=dev)
+    for k in list(range(1, 60, 2)) + list(range(60, len(prog.ops), 5)) + list(range(len(prog.ops) - 32, len(prog.ops) + 1)):
         _lib.check(_lib.lib().sbc_debug_arena(pm.handle, xd.data_ptr(), k, arena.data_ptr(), None), "debug")
         torch.cuda.synchronize()
         _, ra = program.simulate(prog, torch.from_numpy(x), upto=k)
         op = prog.ops[k - 1]
-        ga, ra = arena.cpu().numpy(), ra.numpy()
+        ga, gp = arena.cpu().numpy()[:prog.arena_floats], arena.cpu().numpy()[prog.arena_floats:]
+        ra, rp = ra.numpy(), ra.park.numpy()
         if op.flags & program.F_COMPACT:
             e, r = prog.read_output(ga), prog.read_output(ra)
             assert np.abs(e - r).max() / (np.abs(r).max() + 1e-6) < 5e-5, (k - 1, op.name)
             continue
-        for off in (op.dst, op.acc, op.edst):
+        if op.kind == program.OP_SPILL or (op.kind == program.OP_FILL and op.cin == 0):
+            n = 4 * op.MT
+            e, r = (gp[op.dst:op.dst + n], rp[op.dst:op.dst + n]) if op.kind == program.OP_SPILL else (ga[op.dst:op.dst + n], ra[op.dst:op.dst + n])
+            assert np.abs(e - r).max() / (np.abs(r).max() + 1e-6) < 5e-5, (k - 1, op.name)
+            continue
+        for fi, off in enumerate((op.dst, op.acc, op.edst)):
             if off >= 0:
-                e = prog.read(ga, off, op.cout, op.oh, op.ow)
-                r = prog.read(ra, off, op.cout, op.oh, op.ow)
+                eb, rb = (gp, rp) if (fi == 1 and (op.flags & program.F_ACC_G)) else (ga, ra)
+                e = prog.read(eb, off, op.cout, op.oh, op.ow)
+                r = prog.read(rb, off, op.cout, op.oh, op.ow)
                 d, s = np.abs(e - r).max(), np.abs(r).max() + 1e-6
                 assert d / s < 5e-5, (k - 1, op.name, d, s)
 

@@ -101,7 +101,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     L.sbc_version.restype = C.c_int
-    assert L.sbc_version() == 200
+    assert L.sbc_version() == 210
     L.sbc_model_create.restype = C.c_int
     h = C.c_void_p()
     assert L.sbc_model_create(None, 0, C.byref(h)) == -1        # SBC_E_ARG, never a crash
@@ -119,7 +119,10 @@ def test_program_tiling_covers_other_geometries():
             assert all(op.w_len == 0 or (op.wbuf >= 0 and op.wbuf % 4 == 0 and op.wbuf + op.w_len <= p.arena_floats)
                        for op in p.ops)
     p = program.build_program(sd, 8, 64, 16)
-    assert p.arena_floats * 4 + 256 <= 227 * 1024, "the shipped geometry must fit the B200 shared memory"
+    assert p.park_floats > 0 and p.smem_bytes() <= program.smem_budget_bytes(2), \
+        "the shipped geometry must be planned for two resident CTAs per SM (half of the B200 shared memory each)"
+    p1 = program.build_program(sd, 8, 64, 16, park=False)
+    assert p1.park_floats == 0 and p1.arena_floats * 4 + 256 <= 227 * 1024, "the single-CTA plan must fit one SM"
     with pytest.raises(ValueError, match="multiples of 8"):
         program.build_program(sd, 8, 60, 16)
 

@@ -47,7 +47,7 @@ tw = full[5 * len(prog.ops) + 2:]
 d = np.diff(st)
 tot = st[-1] - st[0]
 print("CTA0 second step (warm): %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
-kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "conv_mma"}
+kinds = {0: "affine", 1: "conv", 2: "norm_elu", 3: "elu", 4: "maxpool5", 5: "upacc", 6: "conv_mma", 7: "spill", 8: "fill"}
 by_kind = {}
 rows = []
 for i, op in enumerate(prog.ops):
