@@ -177,10 +177,11 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
         SbcOp& o = ops[i];
         const int j = o.next_w >= 0 ? o.next_w : next;
         o.nw_off = j >= 0 ? ops[j].w_off : 0;
-        o.nw_len = j >= 0 ? ops[j].w_len : 0;
+        o.nw_len = (j >= 0 && !(ops[j].flags & SBC_F_LATEW)) ? ops[j].w_len : 0;   // late segments load themselves
         o.nw_buf = j >= 0 ? ops[j].wbuf : 0;
     }
     m->first_w = next;
+    if (next >= 0 && (ops[next].flags & SBC_F_LATEW)) { return sbc_fail(SBC_E_ARG, "the first parameterised op must not be a late-loading one"); }
 
     // where do activations live, and are parameters staged through shared memory?
     cudaFuncAttributes fa{};

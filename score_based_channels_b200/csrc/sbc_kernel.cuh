@@ -174,80 +174,104 @@ struct SbcALane {
 // the fragment array.  A dependent mma.sync chain advances one link per ~HMMA latency, far slower than the pipe
 // rate, so when a warp owns fewer than 4 (tile, cout tile) accumulators the three 3xTF32 terms (resp. even / odd
 // K steps in TF32 mode) go to separate accumulator copies that are summed at the end.
+// Operands of one K step as they come out of memory: the raw A fragments of the NS tiles and the raw B fragments of
+// the NN cout tiles (split into hi / lo right before the MMAs that consume them).
+template <int NS, int NN>
+struct SbcKStep {
+    float a[NS][4];
+    float2 b[NN];
+};
+template <bool SMEM, int NS, int NN>
+__device__ __forceinline__ void sbc_kstep_load(const SbcALane<SMEM>& A, const int (&po)[NS][2], const int* tp,
+                                               const float* bp, SbcKStep<NS, NN>& k) {
+    const int off = *tp;
+#pragma unroll
+    for (int n = 0; n < NN; n++) k.b[n] = *reinterpret_cast<const float2*>(bp + n * 64);
+#pragma unroll
+    for (int j = 0; j < NS; j++) A.frag(off, po[j], k.a[j]);
+}
+// the MMAs of one K step.  ODD selects the accumulator copy in the SPLIT TF32 mode (see sbc_mma_pass).
+template <bool X3, bool SPLIT, bool ODD, int NS, int NN, int NCX>
+__device__ __forceinline__ void sbc_kstep_mma(SbcKStep<NS, NN>& k, float (&acc)[NS][NN][4], float (&accx)[NCX][NS][NN][4]) {
+    float bh[NN][2], bl[NN][2];
+#pragma unroll
+    for (int n = 0; n < NN; n++) {
+        bh[n][0] = k.b[n].x; bh[n][1] = k.b[n].y;   // X3: plain fp32 (hi part = what the tensor core reads of it)
+        if (X3) {                                    // w = hi + lo exactly; the tensor core truncates lo to 11 bits
+            bl[n][0] = k.b[n].x - __uint_as_float(__float_as_uint(k.b[n].x) & 0xFFFFE000u);
+            bl[n][1] = k.b[n].y - __uint_as_float(__float_as_uint(k.b[n].y) & 0xFFFFE000u);
+        } else {
+            bl[n][0] = bl[n][1] = 0.f;
+        }
+    }
+    float al[NS][4];
+#pragma unroll
+    for (int j = 0; j < NS; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (X3) al[j][i] = k.a[j][i] - __uint_as_float(__float_as_uint(k.a[j][i]) & 0xFFFFE000u);
+            else k.a[j][i] = sbc_cvt_tf32(k.a[j][i]);
+        }
+    if (X3) {   // small terms first; term-major order keeps dependent MMAs NS*NN apart
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[0][j][n] : acc[j][n], al[j], bh[n][0], bh[n][1]);
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[NCX - 1][j][n] : acc[j][n], k.a[j], bl[n][0], bl[n][1]);
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], k.a[j], bh[n][0], bh[n][1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+#pragma unroll
+            for (int n = 0; n < NN; n++) sbc_mma_tf32((SPLIT && ODD) ? accx[0][j][n] : acc[j][n], k.a[j], bh[n][0], bh[n][1]);
+    }
+}
+
+// Accumulate K steps [s0, s1) for NS pixel-tile slots (row offsets po[j]) and NN cout tiles that share each
+// gathered A fragment.  bfrag = first B fragment of this lane for cout tile nt0; bstride = floats per K step in
+// the fragment array.  A dependent mma.sync chain advances one link per ~HMMA latency, far slower than the pipe
+// rate, so when a warp owns fewer than 4 (tile, cout tile) accumulators the three 3xTF32 terms (resp. even / odd
+// K steps in TF32 mode) go to separate accumulator copies that are summed at the end.
+// The loop is software-pipelined by hand, two K steps per trip with ping-pong operand registers: the loads (step
+// offset, B fragments, ldmatrix) of step s+1 are issued BEFORE the MMAs of step s, so that their latency is covered by
+// tensor-pipe time instead of by the few other warps of a 25 %-occupancy kernel.
 template <bool X3, bool SMEM, int NS, int NN>
 __device__ __forceinline__ void sbc_mma_pass(const SbcALane<SMEM>& A, const int (&po)[NS][2],
                                              const int* __restrict__ steptab, const float* __restrict__ bfrag,
                                              int bstride, int s0, int s1, float (&acc)[NS][NN][4]) {
     constexpr bool SPLIT = NS * NN < 4;
     constexpr int NC = SPLIT ? (X3 ? 3 : 2) : 1;
-    float accx[NC > 1 ? NC - 1 : 1][NS][NN][4];
+    constexpr int NCX = NC > 1 ? NC - 1 : 1;
+    float accx[NCX][NS][NN][4];
     if (SPLIT) {
 #pragma unroll
-        for (int c = 0; c < NC - 1; c++)
+        for (int c = 0; c < NCX; c++)
 #pragma unroll
             for (int j = 0; j < NS; j++)
 #pragma unroll
                 for (int n = 0; n < NN; n++) accx[c][j][n][0] = accx[c][j][n][1] = accx[c][j][n][2] = accx[c][j][n][3] = 0.f;
     }
+    if (s0 >= s1) return;
     const int* tp = steptab + s0;                 // running pointers: no per-step 64-bit address arithmetic
     const float* bp = bfrag + (size_t)s0 * bstride;
+    SbcKStep<NS, NN> k0, k1;
+    sbc_kstep_load<SMEM, NS, NN>(A, po, tp, bp, k0);
+    int left = s1 - s0;                           // steps not yet multiplied; k0 holds the first of them
 #pragma unroll 1
-    for (int s = s0; s < s1; s++, tp++, bp += bstride) {
-        const int off = *tp;
-        float bh[NN][2], bl[NN][2];
-#pragma unroll
-        for (int n = 0; n < NN; n++) {
-            const float2 b = *reinterpret_cast<const float2*>(bp + n * 64);
-            bh[n][0] = b.x; bh[n][1] = b.y;       // X3: plain fp32 (hi part = what the tensor core reads of it)
-            if (X3) {                              // w = hi + lo exactly; the tensor core truncates lo to 11 bits
-                bl[n][0] = b.x - __uint_as_float(__float_as_uint(b.x) & 0xFFFFE000u);
-                bl[n][1] = b.y - __uint_as_float(__float_as_uint(b.y) & 0xFFFFE000u);
-            } else {
-                bl[n][0] = bl[n][1] = 0.f;
-            }
-        }
-        float ah[NS][4], al[NS][4];
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-            A.frag(off, po[j], ah[j]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (X3) al[j][i] = ah[j][i] - __uint_as_float(__float_as_uint(ah[j][i]) & 0xFFFFE000u);
-                else ah[j][i] = sbc_cvt_tf32(ah[j][i]);
-            }
-        }
-        if (X3) {   // small terms first; term-major order keeps dependent MMAs NS*NN apart
-#pragma unroll
-            for (int j = 0; j < NS; j++)
-#pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[0][j][n] : acc[j][n], al[j], bh[n][0], bh[n][1]);
-#pragma unroll
-            for (int j = 0; j < NS; j++)
-#pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(SPLIT ? accx[1][j][n] : acc[j][n], ah[j], bl[n][0], bl[n][1]);
-#pragma unroll
-            for (int j = 0; j < NS; j++)
-#pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
-        } else if (SPLIT) {
-            if ((s - s0) & 1) {
-#pragma unroll
-                for (int j = 0; j < NS; j++)
-#pragma unroll
-                    for (int n = 0; n < NN; n++) sbc_mma_tf32(accx[0][j][n], ah[j], bh[n][0], bh[n][1]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < NS; j++)
-#pragma unroll
-                    for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NS; j++)
-#pragma unroll
-                for (int n = 0; n < NN; n++) sbc_mma_tf32(acc[j][n], ah[j], bh[n][0], bh[n][1]);
-        }
+    while (left >= 2) {
+        sbc_kstep_load<SMEM, NS, NN>(A, po, tp + 1, bp + bstride, k1);
+        sbc_kstep_mma<X3, SPLIT, false, NS, NN, NCX>(k0, acc, accx);
+        tp += 2; bp += 2 * bstride; left -= 2;
+        if (left > 0) sbc_kstep_load<SMEM, NS, NN>(A, po, tp, bp, k0);
+        sbc_kstep_mma<X3, SPLIT, true, NS, NN, NCX>(k1, acc, accx);
     }
+    if (left > 0) sbc_kstep_mma<X3, SPLIT, false, NS, NN, NCX>(k0, acc, accx);
     if (SPLIT) {
 #pragma unroll
         for (int j = 0; j < NS; j++)
@@ -688,6 +712,7 @@ __global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(cons
     }
 
     const int nsteps = (L.mode == 1) ? (L.level_end - L.level_begin) * L.steps_each : 1;
+    const long long t_cta0 = INSTR ? clock64() : 0;
 
     for (int b = blockIdx.x; b < L.B; b += gridDim.x) {
         const bool last_sample = (b + (int)gridDim.x >= L.B);
@@ -757,8 +782,14 @@ __global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(cons
                 if (op.w_len > 0 && stage) {
                     const uint32_t slot = wcount & 1u;
                     if (tid == 0) {   // prefetch the next parameter segment into its staging buffer
+                        // the staging buffers recycle arena space that generic-proxy stores wrote before
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (op.flags & SBC_F_LATEW) {   // own segment first: nobody prefetched it
+                            sbc_mbar_expect_tx(&bars[slot], (uint32_t)op.w_len * 4u);
+                            sbc_bulk_g2s(arena + op.wbuf, L.blob + op.w_off, (uint32_t)op.w_len * 4u, &bars[slot]);
+                        }
                         // next op with parameters; the last one wraps into the next forward
-                        if (op.next_w >= 0 || !(last_step && last_sample)) {
+                        if (op.nw_len > 0 && (op.next_w >= 0 || !(last_step && last_sample))) {
                             sbc_mbar_expect_tx(&bars[slot ^ 1u], (uint32_t)op.nw_len * 4u);
                             sbc_bulk_g2s(arena + op.nw_buf, L.blob + op.nw_off, (uint32_t)op.nw_len * 4u, &bars[slot ^ 1u]);
                         }
@@ -855,5 +886,11 @@ __global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(cons
             for (int e = tid; e < ne; e += SBC_NTHREADS) X[e] = reinterpret_cast<const float2*>(ax)[e];
         }
         __syncthreads();
+    }
+    if (INSTR && L.prof != nullptr && tid == 0) {   // per-CTA totals after the per-op stamps: (cycles, SM id) per CTA
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        L.prof[6 * L.n_ops + 2 + 2 * blockIdx.x] = clock64() - t_cta0;
+        L.prof[6 * L.n_ops + 3 + 2 * blockIdx.x] = (long long)smid;
     }
 }

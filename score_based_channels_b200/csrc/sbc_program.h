@@ -26,6 +26,8 @@ enum SbcOpFlags : int32_t {
     SBC_F_ZH_EDST = 16,   // program.py:_halo_analysis); same for edst
     SBC_F_UNIT = 32,      // conv with fewer (pixel tile, cout tile) units than warps: unit u is owned by the `ks`
                           // warps u*ks .. u*ks+ks-1 (ks = 1: one warp, no K split)
+    SBC_F_LATEW = 128,    // the parameter segment is NOT prefetched during the previous parameterised op (its staging buffer
+                          // would not fit next to that op's): the op issues its own bulk copy and waits for it
     SBC_F_ACC_G = 64,     // conv: `acc` is an offset into the CTA's park area in global memory (L2), not into the arena:
                           // a residual stream that only the epilogues read-modify-write needs no shared memory
 };

@@ -58,6 +58,7 @@ F_COMPACT = 4     # conv epilogue writes couts (0,1) as compact (re, im) pairs: 
 F_ZH_DST = 8      # the halo of the fresh tensor `dst` must be re-zeroed (set by ProgramBuilder._halo_analysis)
 F_ZH_EDST = 16    # same for `edst`
 F_UNIT = 32       # conv: unit (pixel tile, cout tile) u is owned by warps u*ks .. u*ks+ks-1 (ks = 1: no K split)
+F_LATEW = 128     # the op loads its own parameter segment (single staging buffer) instead of being prefetched
 F_ACC_G = 64      # conv: `acc` is an offset into the CTA's park area (global memory / L2) instead of the arena
 
 # Shared memory of one B200 SM that CTAs can share (cudaDevAttrMaxSharedMemoryPerMultiprocessor), the per-CTA
@@ -333,8 +334,9 @@ class ProgramBuilder:
         self.ngf, self.H, self.W, self.channels = ngf, H, W, channels
         self.nthreads = nthreads
         self.park = park
-        if park:
-            self.SLOT_FLOATS = 4700
+        # park mode: a segment above this size gets a single staging buffer, filled at the start of its own op
+        # (F_LATEW): two of them side by side (double buffering) would not fit half an SM
+        self.LATE_FLOATS = 4700 if park else 1 << 30
         self.goff: Dict[str, int] = {}          # park area: tensor name -> float offset (bump allocated, never reused)
         self.gtop = 0
         self.ar = _Planner()
@@ -545,7 +547,7 @@ class ProgramBuilder:
             # 36.3 est/s without, 40.5 with)
             ks, unit = 1, units * 2 <= nwarps
             if unit:
-                while units * ks * 2 <= min(nwarps, 16) and ks * 2 <= S:
+                while units * ks * 2 <= min(nwarps, int(os.environ.get("SBC_KS_CAP", 16))) and ks * 2 <= S:
                     ks *= 2
             scratch = self.tmp_raw(units * ks * 32 * 4, "ksp") if ks > 1 else None
             flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0) | (F_UNIT if unit else 0)
@@ -829,6 +831,9 @@ class ProgramBuilder:
                 name = "wbuf%d" % i
                 if prev is None:
                     self.ar.alloc(name, op.w_len, 0, end)
+                elif op.w_len > self.LATE_FLOATS:
+                    op.flags |= F_LATEW
+                    self.ar.alloc(name, op.w_len, i, i + 1)
                 else:
                     self.ar.alloc(name, op.w_len, prev, i + 1)
                 op.wbuf = name

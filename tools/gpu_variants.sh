@@ -1,8 +1,5 @@
 #!/bin/bash
-# chain-length experiment: forward time at B=148 (one sample per SM) for experiment builds of engine 1
 mkdir -p gpurun_out
-for lib in "" build/lib_512_64.so build/lib_256.so; do
-  echo "== lib=${lib:-default}"
-  SBC_LIB=${lib:+$PWD/$lib} timeout 300 python tools/profile_ops.py 148 tf32x3 2>&1 | head -2
-done
-echo "== engine 2 check"; timeout 300 python tools/e2_check.py 2>&1 | tail -4
+timeout 300 python tools/e2_check.py 2>&1 | grep "tf32x3:"
+echo "instrumented build (SBC_DBG=32):"; SBC_DBG=32 timeout 300 python tools/e2_check.py 2>&1 | grep "tf32x3:"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sbc_ald_kernel -s 1 -c 1 -o gpurun_out/prof_e1x2 -f python tools/e2_short.py 296 2 tf32x3 > gpurun_out/ncu_e1x2.log 2>&1; echo "ncu rc=$?"

@@ -31,7 +31,7 @@ e1.record()
 torch.cuda.synchronize()
 print("precision %s forward B=%d: %.3f ms per launch" % (PREC, B, e0.elapsed_time(e1) / 10))
 
-stamps = torch.zeros(6 * len(prog.ops) + 2, dtype=torch.int64, device=dev)
+stamps = torch.zeros(6 * len(prog.ops) + 2 + 2 * max(B, 1024), dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, stamps.data_ptr()), "prof")
 P = torch.from_numpy(synth.qpsk_pilots(B, 64, 38)).to(dev)
 H = torch.from_numpy(synth.cdl_like_channels(B)).to(dev)
@@ -43,7 +43,8 @@ _lib.check(_lib.lib().sbc_set_profile_buffer(pm.handle, None), "prof")
 full = stamps.cpu().numpy()
 st = full[:len(prog.ops) + 2]
 sub = full[len(prog.ops) + 2:5 * len(prog.ops) + 2].reshape(len(prog.ops), 4)
-tw = full[5 * len(prog.ops) + 2:]
+tw = full[5 * len(prog.ops) + 2:6 * len(prog.ops) + 2]
+cta = full[6 * len(prog.ops) + 2:6 * len(prog.ops) + 2 + 2 * min(B, 2 * 148)].reshape(-1, 2)
 d = np.diff(st)
 tot = st[-1] - st[0]
 print("CTA0 second step (warm): %d cycles total; network %d, langevin %d" % (tot, st[-2] - st[0], st[-1] - st[-2]))
@@ -70,6 +71,11 @@ for i, op in enumerate(prog.ops):
     if tw[i] > 0:
         phases += " | fetch+wait %d" % (tw[i] - st[i])
     rows.append((i, op.name, key + phases, c))
+cyc, sm = cta[:, 0], cta[:, 1]
+occ = np.bincount(sm.astype(np.int64), minlength=148)
+two = cyc[occ[sm] == 2]; one = cyc[occ[sm] == 1]
+print("per-CTA total cycles (whole launch: 2 steps): all CTAs min %d median %d max %d; on SMs with 2 CTAs: n=%d median %d max %d; alone on an SM: n=%d median %d"
+      % (cyc.min(), np.median(cyc), cyc.max(), two.size, np.median(two) if two.size else 0, two.max() if two.size else 0, one.size, np.median(one) if one.size else 0))
 print("\n== by op class (cycles, count, cycles/op, share of network)")
 net = st[-2] - st[0]
 for k, (c, n) in sorted(by_kind.items(), key=lambda kv: -kv[1][0]):
