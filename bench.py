@@ -46,8 +46,9 @@ METRIC = "channel-estimates/sec (full ALD, 16x64 CDL-C)"
 ENGINE_PRECISION = {1: "tf32x3", 2: "fp16x2"}
 # HBM traffic of one launch, from the ncu captures committed under profiles/ (dram__bytes_read + write):
 # bytes = fixed + per_level * levels at the captured batch; scaled linearly with the batch.
-TRAFFIC = {1: {"batch": 256, "fixed": 11.9e6, "per_level": 3.1e3, "src": "profiles/r02_ncu_engine1_raw.txt (16-level launch: 11.9 MB read, "
-                                                                       "0 written; the NMSE log, 3 KB per level, stays in L2)"},
+TRAFFIC = {1: {"batch": 256, "fixed": 15.0e6, "per_level": 0.378e6, "src": "profiles/r02b_ncu_engine1_2cta_raw.txt (16-level launch: 11.9 MB read = the "
+                                                                         "inputs, 9.2 MB written) and a 2-level capture (4.5 MB written at B=296): "
+                                                                         "the per-CTA park areas (41 MB in all) live in L2, a trickle of dirty lines is written back"},
            2: {"batch": 256, "fixed": 0.21e9, "per_level": 0.833e9, "src": "profiles/r02_ncu_engine2_raw.txt and r02_ncu_engine2_2levels_raw.txt "
                                                                          "(16 / 2 levels: 13.5 / 1.88 GB: the 115 MB working set of 256 per-CTA arenas "
                                                                          "does not stay in the 126 MB L2, dirty lines are written back)"}}
@@ -376,6 +377,7 @@ def main():
         extra.append(short(2, 2 if engine == 1 else 1, min(levels, 96)))
         extra.append(short(3, 2, min(levels, 12)))
         extra.append(short(3, 1, min(levels, 12)))
+        extra.append(short(4, 1, min(levels, 6)))
         extra.append(short(4, 2, min(levels, 6)))
         extra.append(short(5, 2, min(levels, 3), batch=2368))
         extra.append(short(5, 1, min(levels, 3), batch=2368))

@@ -200,7 +200,6 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     SBC_CUDA(cudaMemcpy(m->d_blob, desc->blob, sizeof(float) * (size_t)desc->blob_floats, cudaMemcpyHostToDevice));
     SBC_CUDA(cudaMalloc(&m->d_sigmas, sizeof(float) * (size_t)desc->n_sigmas));
     SBC_CUDA(cudaMemcpy(m->d_sigmas, desc->sigmas, sizeof(float) * (size_t)desc->n_sigmas, cudaMemcpyHostToDevice));
-    if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms));
     m->d.op_table = nullptr; m->d.blob = nullptr; m->d.sigmas = nullptr; m->d.geo_table = nullptr;   // host pointers are not retained
 
     SBC_CUDA(cudaFuncSetAttribute(sbc_ald_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
@@ -214,15 +213,21 @@ extern "C" int sbc_model_create(const sbc_model_desc* desc, int device, void** h
     // resident CTAs per SM: plans made for two CTAs per SM (program.py, park mode) keep their arena under half of the
     // shared memory of an SM; the grid is sized to fill every slot (any grid is correct: CTAs stride over the batch)
     m->ctas_per_sm = 1;
-    if (m->arena_in_smem) {
+    {   // (a global-memory arena needs no shared memory beyond the misc region: registers bound the residency)
         int nb = 0;
-        if (m->x3) SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, true, false>, SBC_NTHREADS, m->smem_bytes));
-        else SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, false, false>, SBC_NTHREADS, m->smem_bytes));
+        if (m->arena_in_smem) {
+            if (m->x3) SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, true, false>, SBC_NTHREADS, m->smem_bytes));
+            else SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<true, false, false>, SBC_NTHREADS, m->smem_bytes));
+        } else {
+            if (m->x3) SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<false, true, false>, SBC_NTHREADS, m->smem_bytes));
+            else SBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sbc_ald_kernel<false, false, false>, SBC_NTHREADS, m->smem_bytes));
+        }
         const int cap = env_int("SBC_CTAS", 0);
         if (cap > 0 && nb > cap) nb = cap;
         m->ctas_per_sm = nb < 1 ? 1 : nb;
     }
     if (desc->park_floats < 0 || desc->park_floats % 4) { return sbc_fail(SBC_E_ARG, "sbc_model_create: bad park_floats"); }
+    if (!m->arena_in_smem) SBC_CUDA(cudaMalloc(&m->d_gws, arena_bytes * (size_t)m->num_sms * (size_t)m->ctas_per_sm));
     if (desc->park_floats > 0)
         SBC_CUDA(cudaMalloc(&m->d_park, sizeof(float) * (size_t)desc->park_floats * (size_t)m->num_sms * (size_t)m->ctas_per_sm));
     *handle_out = mh.release();

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/e2_check.py 2>&1 | grep "tf32x3:"
-echo "instrumented build (SBC_DBG=32):"; SBC_DBG=32 timeout 300 python tools/e2_check.py 2>&1 | grep "tf32x3:"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sbc_ald_kernel -s 1 -c 1 -o gpurun_out/prof_e1x2 -f python tools/e2_short.py 296 2 tf32x3 > gpurun_out/ncu_e1x2.log 2>&1; echo "ncu rc=$?"
+for d in 0 150000 300000 550000; do
+  echo "== SBC_DESYNC=$d"; SBC_DESYNC=$d timeout 300 python bench.py --levels 48 --steps 2 --warmup 1 --no-cpu-baseline --no-extra 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.2f est/s ms/step %.2f'%(d['value'], d['ms_per_step']))"
+done
+echo "== config 5, engine 1 (global arena, 2 CTAs/SM)"; timeout 300 python bench.py --config 5 --engine 1 --batch 2368 --levels 3 --steps 2 --warmup 1 --no-cpu-baseline --no-extra 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.2f est/s ms/step %.2f ctas %s'%(d['value'], d['ms_per_step'], d['roofline']['ctas_per_sm']))"
