@@ -137,8 +137,32 @@ int sbc_model_create(const sbc_model_desc* desc, int device, void** handle_out);
  * ("fp16x2", 22 significant bits, fp32 accumulate in TMEM): fp32-equivalent. */
 int sbc_model_create_from_state(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt, int32_t Nr,
                                 int32_t channels, int device, void** handle_out);
+/* The same with the engine chosen by `precision`: SBC_PREC_FP16X2 = the tcgen05 engine (as above); SBC_PREC_TF32X3 /
+ * SBC_PREC_TF32 = engine 1 (fused shared-memory arena on mma.sync; two channel realisations per SM at 64x16), planned
+ * and packed inside the library by the C++ twin of program.py (csrc/sbc1_plan.h) -- no Python needed for either. */
+enum { SBC_PREC_FP16X2 = 0, SBC_PREC_TF32X3 = 1, SBC_PREC_TF32 = 2 };
+int sbc_model_create_from_state_ex(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt,
+                                   int32_t Nr, int32_t channels, int device, int32_t precision, void** handle_out);
 int sbc_model_free(void* handle);
 int sbc_query(void* handle, sbc_info* out);
+
+/* Host-only view of an engine-1 plan built by the in-library planner (no CUDA call: usable without a GPU; the CPU
+ * tests compare it word for word with program.py).  park: -1 = automatic choice, 0 / 1 = force.  The view points into
+ * the plan object: valid until sbc_plan1_free(plan). */
+typedef struct sbc_plan1_view {
+    const int32_t* op_table;    /* [n_ops][32] */
+    int32_t n_ops;
+    const int32_t* geo_table;   /* [n_geo][8] */
+    int32_t n_geo;
+    const float* blob;
+    int64_t blob_floats;
+    int32_t arena_floats, in_off, out_off, post_off, max_w_len, park_floats, nthreads;
+    int64_t conv_flops;
+} sbc_plan1_view;
+int sbc_plan1_build(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt, int32_t Nr,
+                    int32_t channels, int32_t nthreads, int32_t precision, int32_t park, void** plan_out,
+                    sbc_plan1_view* view);
+int sbc_plan1_free(void* plan);
 
 /* NCSNv2Deepest.forward(x, y) (reference ncsnv2/models/ncsnv2.py:269-300).  Device pointers.
  * x: fp32 [B,channels,Nt,Nr] with element strides x_strides (any layout, e.g. the permuted

@@ -11,7 +11,9 @@ LIB_PATH = os.environ.get("SBC_LIB") or os.path.join(_HERE, "libsbc_b200.so")   
 
 EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_create_from_state",
            "sbc_model_free", "sbc_query", "sbc_forward", "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host",
-           "sbc_debug_arena", "sbc_set_profile_buffer", "sbc_debug_plan", "sbc_debug_run", "sbc_op_name", "sbc_op_kind")
+           "sbc_debug_arena", "sbc_set_profile_buffer", "sbc_debug_plan", "sbc_debug_run", "sbc_op_name", "sbc_op_kind",
+           "sbc_model_create_from_state_ex", "sbc_plan1_build", "sbc_plan1_free")
+PREC_CODE = {"fp16x2": 0, "tf32x3": 1, "tf32": 2}
 
 
 class ModelDesc(C.Structure):
@@ -32,6 +34,13 @@ class Info(C.Structure):
 
 class StateEntry(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("shape", C.c_void_p), ("ndim", C.c_int32)]
+
+
+class Plan1View(C.Structure):
+    _fields_ = [("op_table", C.c_void_p), ("n_ops", C.c_int32), ("geo_table", C.c_void_p), ("n_geo", C.c_int32),
+                ("blob", C.c_void_p), ("blob_floats", C.c_int64), ("arena_floats", C.c_int32), ("in_off", C.c_int32),
+                ("out_off", C.c_int32), ("post_off", C.c_int32), ("max_w_len", C.c_int32), ("park_floats", C.c_int32),
+                ("nthreads", C.c_int32), ("conv_flops", C.c_int64)]
 
 
 class TensorInfo(C.Structure):
@@ -75,6 +84,11 @@ def lib():
         L.sbc_set_profile_buffer.argtypes = [C.c_void_p, C.c_void_p]
         L.sbc_model_create_from_state.argtypes = [C.POINTER(StateEntry), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, C.c_int, C.POINTER(C.c_void_p)]
+        L.sbc_model_create_from_state_ex.argtypes = [C.POINTER(StateEntry), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                     C.c_int32, C.c_int, C.c_int32, C.POINTER(C.c_void_p)]
+        L.sbc_plan1_build.argtypes = [C.POINTER(StateEntry), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(Plan1View)]
+        L.sbc_plan1_free.argtypes = [C.c_void_p]
         L.sbc_debug_plan.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
         L.sbc_debug_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]

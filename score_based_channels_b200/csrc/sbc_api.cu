@@ -11,6 +11,7 @@
 #include "../../include/sbc.h"
 #include "sbc_kernel.cuh"
 #include "sbc2_host.cuh"
+#include "sbc1_plan.h"
 
 static thread_local char g_err[512] = "";
 
@@ -564,6 +565,82 @@ extern "C" int sbc_debug_run(void* handle, const float* x, int32_t S, int32_t re
     cudaFree(scratch);
     if (ce != cudaSuccess) return sbc_fail(SBC_E_CUDA, "sbc_debug_run: %s", cudaGetErrorString(ce));
     return SBC_OK;
+}
+
+// ---- engine 1 planned inside the library (csrc/sbc1_plan.h) -----------------------------------------------------
+static int state_from_entries(const sbc_state_entry* entries, int32_t n_entries, sbc2::StateDict& sd, const char* who) {
+    if (!entries || n_entries <= 0) return sbc_fail(SBC_E_ARG, "%s: null / empty state", who);
+    for (int i = 0; i < n_entries; i++) {
+        const sbc_state_entry& e = entries[i];
+        if (!e.name || !e.data || e.ndim < 0 || e.ndim > 8 || (e.ndim > 0 && !e.shape)) return sbc_fail(SBC_E_ARG, "%s: bad entry %d", who, i);
+        sbc2::TensorArg t;
+        t.data = e.data;
+        for (int k = 0; k < e.ndim; k++) t.shape.push_back(e.shape[k]);
+        sd[e.name] = t;
+    }
+    return SBC_OK;
+}
+
+static void plan1_view(const sbc1::Plan& P, sbc_plan1_view* v) {
+    v->op_table = reinterpret_cast<const int32_t*>(P.ops.data()); v->n_ops = (int32_t)P.ops.size();
+    v->geo_table = reinterpret_cast<const int32_t*>(P.geos.data()); v->n_geo = (int32_t)P.geos.size();
+    v->blob = P.blob.data(); v->blob_floats = (int64_t)P.blob.size();
+    v->arena_floats = P.arena_floats; v->in_off = P.in_off; v->out_off = P.out_off; v->post_off = P.post_off;
+    v->max_w_len = P.max_w_len; v->park_floats = P.park_floats; v->nthreads = P.nthreads; v->conv_flops = P.conv_flops;
+}
+
+extern "C" int sbc_plan1_build(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt, int32_t Nr,
+                               int32_t channels, int32_t nthreads, int32_t precision, int32_t park, void** plan_out,
+                               sbc_plan1_view* view) {
+    if (!plan_out || !view) return sbc_fail(SBC_E_ARG, "sbc_plan1_build: null argument");
+    if (precision != SBC_PREC_TF32X3 && precision != SBC_PREC_TF32) return sbc_fail(SBC_E_ARG, "sbc_plan1_build: engine-1 precisions are SBC_PREC_TF32X3 / SBC_PREC_TF32");
+    if (nthreads < 32 || nthreads > 1024 || (nthreads & (nthreads - 1))) return sbc_fail(SBC_E_ARG, "sbc_plan1_build: nthreads must be a power of two in [32, 1024]");
+    sbc2::StateDict sd;
+    int rc = state_from_entries(entries, n_entries, sd, "sbc_plan1_build");
+    if (rc) return rc;
+    try {
+        std::unique_ptr<sbc1::Plan> P(new sbc1::Plan(sbc1::build_auto(sd, ngf, Nt, Nr, channels, nthreads, precision == SBC_PREC_TF32X3, park)));
+        plan1_view(*P, view);
+        *plan_out = P.release();
+    } catch (const std::exception& ex) {
+        return sbc_fail(SBC_E_ARG, "sbc_plan1_build: %s", ex.what());
+    }
+    return SBC_OK;
+}
+
+extern "C" int sbc_plan1_free(void* plan) {
+    delete (sbc1::Plan*)plan;
+    return SBC_OK;
+}
+
+extern "C" int sbc_model_create_from_state_ex(const sbc_state_entry* entries, int32_t n_entries, int32_t ngf, int32_t Nt,
+                                              int32_t Nr, int32_t channels, int device, int32_t precision, void** handle_out) {
+    if (precision == SBC_PREC_FP16X2) return sbc_model_create_from_state(entries, n_entries, ngf, Nt, Nr, channels, device, handle_out);
+    if (!handle_out) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state_ex: null argument");
+    void* plan = nullptr;
+    sbc_plan1_view v;
+    int rc = sbc_plan1_build(entries, n_entries, ngf, Nt, Nr, channels, SBC_NTHREADS, precision, -1, &plan, &v);
+    if (rc) return rc;
+    std::unique_ptr<sbc1::Plan> P((sbc1::Plan*)plan);
+    const float* sigmas = nullptr;
+    int n_sigmas = 0;
+    for (int i = 0; i < n_entries; i++)
+        if (strcmp(entries[i].name, "sigmas") == 0) {
+            sigmas = entries[i].data;
+            n_sigmas = entries[i].ndim > 0 ? (int)entries[i].shape[0] : 1;
+        }
+    if (!sigmas || n_sigmas <= 0) return sbc_fail(SBC_E_ARG, "sbc_model_create_from_state_ex: the state has no 'sigmas' (noise schedule)");
+    int32_t geo[SBC_MAX_GEO][8];
+    memset(geo, 0, sizeof geo);
+    memcpy(geo, v.geo_table, sizeof(SbcGeo) * (size_t)v.n_geo);
+    sbc_model_desc d;
+    memset(&d, 0, sizeof d);
+    d.ngf = ngf; d.Nt = Nt; d.Nr = Nr; d.channels = channels;
+    d.op_table = v.op_table; d.n_ops = v.n_ops; d.geo_table = &geo[0][0]; d.n_geo = v.n_geo;
+    d.blob = v.blob; d.blob_floats = v.blob_floats; d.arena_floats = v.arena_floats;
+    d.in_off = v.in_off; d.out_off = v.out_off; d.post_off = v.post_off; d.max_w_len = v.max_w_len;
+    d.sigmas = sigmas; d.n_sigmas = n_sigmas; d.conv_flops = v.conv_flops; d.nthreads = v.nthreads; d.park_floats = v.park_floats;
+    return sbc_model_create(&d, device, handle_out);
 }
 
 extern "C" const char* sbc_op_name(void* handle, int32_t i) {

@@ -17,13 +17,16 @@ class PackedModel:
     """Owns one ``sbc_model_create`` handle for a (state_dict, ngf, Nt, Nr) on one CUDA device."""
 
     def __init__(self, state: Dict[str, np.ndarray], ngf: int, Nt: int, Nr: int, device: int = 0,
-                 channels: int = 2, precision: str = "tf32x3"):
+                 channels: int = 2, precision: str = "tf32x3", planner: str = "python"):
+        """``planner``: engine 1 only -- "python" = program.py (keeps ``self.prog`` for the simulator / profiling tools),
+        "library" = the C++ twin inside the library (``sbc_model_create_from_state_ex``; identical op table)."""
         self.precision = precision
         self.ngf, self.Nt, self.Nr, self.channels, self.device = ngf, Nt, Nr, channels, device
         self.sigmas = np.ascontiguousarray(state["sigmas"], dtype=np.float32)
         self.prog = None
-        if precision in ENGINE2_PRECISIONS:
-            # engine 2 (tcgen05): the library plans and packs from the plain state dict (sbc_model_create_from_state)
+        if precision in ENGINE2_PRECISIONS or planner == "library":
+            # the library plans and packs from the plain state dict: engine 2 (tcgen05), or engine 1 through the C++ twin
+            # of program.py
             keep, ents = [], (_lib.StateEntry * len(state))()
             for i, (k, v) in enumerate(state.items()):
                 a = np.ascontiguousarray(v, dtype=np.float32)
@@ -31,8 +34,9 @@ class PackedModel:
                 keep += [a, shp]
                 ents[i] = _lib.StateEntry(k.encode(), a.ctypes.data, shp.ctypes.data, len(shp))
             h = C.c_void_p()
-            _lib.check(_lib.lib().sbc_model_create_from_state(ents, len(state), ngf, Nt, Nr, channels, device,
-                                                              C.byref(h)), "sbc_model_create_from_state")
+            _lib.check(_lib.lib().sbc_model_create_from_state_ex(ents, len(state), ngf, Nt, Nr, channels, device,
+                                                                 _lib.PREC_CODE[precision], C.byref(h)),
+                       "sbc_model_create_from_state_ex")
             self.handle = h
             self.conv_flops = int(self.info().conv_flops_per_forward)
             return

@@ -547,7 +547,7 @@ class ProgramBuilder:
             # 36.3 est/s without, 40.5 with)
             ks, unit = 1, units * 2 <= nwarps
             if unit:
-                while units * ks * 2 <= min(nwarps, int(os.environ.get("SBC_KS_CAP", 16))) and ks * 2 <= S:
+                while units * ks * 2 <= min(nwarps, 16) and ks * 2 <= S:
                     ks *= 2
             scratch = self.tmp_raw(units * ks * 32 * 4, "ksp") if ks > 1 else None
             flags = (F_POOL if pool else 0) | (F_X3 if x3 else 0) | (F_COMPACT if compact else 0) | (F_UNIT if unit else 0)

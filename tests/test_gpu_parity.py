@@ -189,6 +189,38 @@ def test_host_buffer_abi_matches_device_abi(dev):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+def test_engine1_model_created_inside_the_library_is_bit_identical(dev, prec):
+    """Self-contained C ABI for engine 1: sbc_model_create_from_state_ex (C++ planner, no program.py on the path) gives
+    the same forward and the same ALD trajectory, bit for bit, as the model packed by the Python planner."""
+    from score_based_channels_b200.engine import PackedModel
+    sd, m = _model(8, 1, dev, prec)
+    pm_py = m.packed(64, 16, dev)
+    pm_c = PackedModel(sd, 8, 64, 16, device=dev.index or 0, precision=prec, planner="library")
+    assert pm_c.prog is None and pm_c.info().engine == 1 and pm_c.info().ctas_per_sm == pm_py.info().ctas_per_sm == 2
+    assert pm_c.info().n_ops == pm_py.info().n_ops and pm_c.info().arena_bytes == pm_py.info().arena_bytes
+    x = np.random.default_rng(1).standard_normal((3, 2, 64, 16)).astype(np.float32)
+    y = np.array([3, 2000, 2310], np.int64)
+    outs = []
+    for pm in (pm_py, pm_c):
+        out = np.empty_like(x)
+        _lib.check(_lib.lib().sbc_forward_host(pm.handle, x.ctypes.data, y.ctypes.data, out.ctypes.data, 3), "fwd_host")
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    P, Y, X0, H, nv = _problem(3, seed=4)
+    f = lambda v: np.full(3, v, np.float32)
+    res = []
+    for pm in (pm_py, pm_c):
+        Xh, nlog = X0.copy(), np.zeros((6, 3), np.float32)
+        nvh, alh, beh = f(nv), f(3e-11), f(0.01)
+        a = _lib.AldArgs(3, 64, 16, 38, 0, 2, 3, P.ctypes.data, Y.ctypes.data, Xh.ctypes.data, H.ctypes.data,
+                         nvh.ctypes.data, alh.ctypes.data, beh.ctypes.data, SIGMA_END, nlog.ctypes.data, 9, None, None)
+        _lib.check(_lib.lib().sbc_ald_run_host(pm.handle, C.byref(a)), "sbc_ald_run_host")
+        res.append((Xh, nlog))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    pm_c.close()
+
+
 def test_edge_cases_and_error_codes(dev):
     sd, m = _model(8, 1, dev)
     P, Y, X0, H, nv = _problem(2)

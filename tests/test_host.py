@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import REPO, have_reference
-from score_based_channels_b200 import dist as sdist
+from score_based_channels_b200 import _lib, dist as sdist
 from score_based_channels_b200 import dotmap_shim, hdf5_min, params, program
 
 REF_MAT = "/root/reference/sample_data/CDL-C_Nt64_Nr16_ULA0.50_seed4321.mat"
@@ -204,3 +204,51 @@ def test_oracle_dc_boost_and_early_stop_semantics():
     assert np.array_equal(Xc[1], Xa[1])
     Xe, _ = net.ald(P, Y, X0, H, level_end=2, dc_boost=4.0, **kw)
     assert np.abs(Xe - Xa).max() > 1e-4 * np.abs(Xa).max()
+
+
+def _library_plan(sd, ngf, H, W, nthreads, prec, park):
+    """Engine-1 plan built by the C++ planner inside the library (host-only entry point: no GPU needed)."""
+    import ctypes as C
+    L = _lib.lib()
+    keep, ents = [], (_lib.StateEntry * len(sd))()
+    for i, (k, v) in enumerate(sd.items()):
+        a = np.ascontiguousarray(v, dtype=np.float32)
+        shp = np.asarray(a.shape if a.ndim else (1,), dtype=np.int64)
+        keep += [a, shp]
+        ents[i] = _lib.StateEntry(k.encode(), a.ctypes.data, shp.ctypes.data, len(shp))
+    h, v = C.c_void_p(), _lib.Plan1View()
+    _lib.check(L.sbc_plan1_build(ents, len(sd), ngf, H, W, 2, nthreads, _lib.PREC_CODE[prec], park, C.byref(h), C.byref(v)),
+               "sbc_plan1_build")
+    tab = np.ctypeslib.as_array(C.cast(v.op_table, C.POINTER(C.c_int32)), (v.n_ops, 32)).copy()
+    geo = np.ctypeslib.as_array(C.cast(v.geo_table, C.POINTER(C.c_int32)), (v.n_geo, 8)).copy()
+    blob = np.ctypeslib.as_array(C.cast(v.blob, C.POINTER(C.c_float)), (v.blob_floats,)).copy()
+    meta = {f: getattr(v, f) for f in ("arena_floats", "in_off", "out_off", "post_off", "max_w_len", "park_floats",
+                                       "nthreads", "conv_flops")}
+    L.sbc_plan1_free(h)
+    return tab, geo, blob, meta
+
+
+@pytest.mark.parametrize("ngf,H,W,prec,park", [(8, 64, 16, "tf32x3", -1), (8, 64, 16, "tf32", -1), (8, 64, 16, "tf32x3", 0),
+                                               (8, 32, 8, "tf32x3", -1), (8, 24, 40, "tf32x3", -1), (16, 64, 16, "tf32x3", -1),
+                                               (8, 128, 32, "tf32x3", -1)])
+def test_library_planner_matches_python_planner_word_for_word(ngf, H, W, prec, park):
+    """The self-contained C ABI of engine 1: csrc/sbc1_plan.h must reproduce program.py exactly -- op table, geometry
+    table, parameter blob (bit patterns) and every plan scalar -- so that everything the CPU suite proves about the
+    Python plan (simulator vs the reference modules, thread emulation) holds for models created without Python."""
+    sd = params.random_state(ngf, seed=3)
+    p = program.build_program(sd, ngf, H, W, nthreads=256, precision=prec, park=None if park < 0 else bool(park))
+    tab, geo, blob, meta = _library_plan(sd, ngf, H, W, 256, prec, park)
+    assert np.array_equal(p.op_table(), tab)
+    assert np.array_equal(p.geo_table()[:len(p.geos)], geo)
+    assert blob.size == p.blob.size and np.array_equal(blob.view(np.uint32), p.blob.view(np.uint32))
+    assert meta == dict(arena_floats=p.arena_floats, in_off=p.in_off, out_off=p.out_off, post_off=p.post_off,
+                        max_w_len=p.max_w_len, park_floats=p.park_floats, nthreads=p.nthreads, conv_flops=p.conv_flops)
+
+
+def test_library_planner_rejects_bad_input():
+    sd = params.random_state(8, seed=3)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        _library_plan(sd, 8, 60, 16, 256, "tf32x3", -1)
+    bad = {k: v for k, v in sd.items() if k != "res1.0.conv1.weight"}
+    with pytest.raises(RuntimeError, match="res1.0.conv1.weight"):
+        _library_plan(bad, 8, 64, 16, 256, "tf32x3", -1)

@@ -15,4 +15,4 @@ a=torch.load('gpurun_out/ts1/results.pt',weights_only=False); b=torch.load('gpur
 print('shard invariance: nmse_log identical =', np.array_equal(a['nmse_log'],b['nmse_log']), 'max abs diff', float(np.abs(a['nmse_log']-b['nmse_log']).max()), a['nmse_log'].shape)
 PY
 rm -rf gpurun_out/ts1/results.pt gpurun_out/ts2/results.pt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --levels 48 > gpurun_out/bench_n2.log 2>&1; echo "rc3=$?"; tail -1 gpurun_out/bench_n2.log | cut -c1-700
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --levels 48 --no-extra > gpurun_out/bench_n2.log 2>&1; echo "rc3=$?"; tail -1 gpurun_out/bench_n2.log | cut -c1-700
