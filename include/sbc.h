@@ -170,6 +170,14 @@ int sbc_plan1_free(void* plan);
 int sbc_forward(void* handle, const float* x, const int64_t x_strides[4], const int64_t* labels, float* out,
                 int32_t B, void* stream);
 
+/* Denoising-score-matching loss, forward only: anneal_dsm_score_estimation (reference ncsnv2/losses/dsm.py:6-32) as it is
+ * evaluated under torch.no_grad() for the validation loss of train_score.py:170-185.  Device pointers; samples and z
+ * (the torch.randn_like draw) are fp32 [B,channels,Nt,Nr] contiguous, labels int64 [B]; one launch perturbs, runs the
+ * score network and reduces  loss_out[b] = 1/2 * sum((score - target)^2) * sigmas[labels[b]]^anneal_power  (the caller
+ * takes the mean).  Engine-1 models.  The backward pass / optimiser step of the training loop is not part of this library. */
+int sbc_dsm_loss(void* handle, const float* samples, const int64_t* labels, const float* z, float anneal_power,
+                 float* loss_out, int32_t B, void* stream);
+
 /* Device-pointer ALD run (all arrays in sbc_ald_args are device memory). */
 int sbc_ald_run(void* handle, const sbc_ald_args* args, void* stream);
 

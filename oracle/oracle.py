@@ -85,6 +85,18 @@ class OracleNet:
         self.L.orc_forward(self.h, x.ctypes.data, sig.ctypes.data, out.ctypes.data, x.shape[0])
         return out
 
+    def dsm_losses(self, samples: np.ndarray, labels: np.ndarray, z: np.ndarray, anneal_power: float = 2.0) -> np.ndarray:
+        """Per-sample anneal_dsm_score_estimation terms (reference ncsnv2/losses/dsm.py:13-31, before the mean) for the
+        randn draw ``z``: fp32, same operation order as the reference."""
+        x, z = _f32(samples), _f32(z)
+        B = x.shape[0]
+        sig = _f32(self.sigmas[np.asarray(labels, dtype=np.int64)]).reshape(B, 1, 1, 1)
+        noise = z * sig
+        target = np.float32(-1.0) / (sig ** 2) * noise
+        scores = self.forward(x + noise, labels)
+        d = (scores.reshape(B, -1) - target.reshape(B, -1)).astype(np.float32)
+        return (np.float32(0.5) * (d ** 2).sum(axis=-1, dtype=np.float32) * sig.reshape(B) ** np.float32(anneal_power)).astype(np.float32)
+
     def ald(self, P, Y, X0, H=None, *, noise_var, alpha_step, beta, sigma_end, level_begin=0,
             level_end=None, steps_each=3, seed=0, sample_ids=None, ext_noise=None, log=True, dc_boost=None,
             stop_step=None):

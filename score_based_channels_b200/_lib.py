@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SBC_LIB") or os.path.join(_HERE, "libsbc_b200.so")   
 EXPORTS = ("sbc_version", "sbc_threads_per_cta", "sbc_last_error", "sbc_model_create", "sbc_model_create_from_state",
            "sbc_model_free", "sbc_query", "sbc_forward", "sbc_ald_run", "sbc_forward_host", "sbc_ald_run_host",
            "sbc_debug_arena", "sbc_set_profile_buffer", "sbc_debug_plan", "sbc_debug_run", "sbc_op_name", "sbc_op_kind",
-           "sbc_model_create_from_state_ex", "sbc_plan1_build", "sbc_plan1_free")
+           "sbc_model_create_from_state_ex", "sbc_plan1_build", "sbc_plan1_free", "sbc_dsm_loss")
 PREC_CODE = {"fp16x2": 0, "tf32x3": 1, "tf32": 2}
 
 
@@ -77,6 +77,8 @@ def lib():
         L.sbc_query.argtypes = [C.c_void_p, C.POINTER(Info)]
         L.sbc_forward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_void_p]
+        L.sbc_dsm_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32,
+                                   C.c_void_p]
         L.sbc_ald_run.argtypes = [C.c_void_p, C.POINTER(AldArgs), C.c_void_p]
         L.sbc_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.sbc_ald_run_host.argtypes = [C.c_void_p, C.POINTER(AldArgs)]

@@ -330,6 +330,22 @@ extern "C" int sbc_forward(void* handle, const float* x, const int64_t x_strides
     return launch(m, L, (cudaStream_t)stream);
 }
 
+extern "C" int sbc_dsm_loss(void* handle, const float* samples, const int64_t* labels, const float* z, float anneal_power,
+                            float* loss_out, int32_t B, void* stream) {
+    if (!handle || !samples || !labels || !z || !loss_out) return sbc_fail(SBC_E_ARG, "sbc_dsm_loss: null argument");
+    if (B < 0) return sbc_fail(SBC_E_ARG, "sbc_dsm_loss: negative batch");
+    if (B == 0) return SBC_OK;
+    SbcModel* m = (SbcModel*)handle;
+    if (m->engine == 2) return sbc_fail(SBC_E_UNSUPPORTED, "sbc_dsm_loss: engine-1 models only (precision tf32x3 / tf32)");
+    SbcLaunch L;
+    fill_common(m, L);
+    L.mode = 2; L.B = B; L.fx = samples; L.labels = (const long long*)labels; L.dsm_z = z; L.dsm_out = loss_out;
+    L.anneal_power = anneal_power;
+    L.fxs[0] = (long long)m->d.channels * m->d.Nt * m->d.Nr; L.fxs[1] = (long long)m->d.Nt * m->d.Nr;
+    L.fxs[2] = m->d.Nr; L.fxs[3] = 1;
+    return launch(m, L, (cudaStream_t)stream);
+}
+
 static int check_ald(const SbcModel* m, const sbc_ald_args* a) {
     if (!a) return sbc_fail(SBC_E_ARG, "sbc_ald_run: null args");
     if (a->B < 0) return sbc_fail(SBC_E_ARG, "sbc_ald_run: negative batch");

@@ -40,7 +40,7 @@ struct SbcLaunch {
     int halo_off[SBC_MAX_GEO];   // start (uint16 units) of geometry g's halo-pixel list in the shared misc region
     int arena_floats, in_off, out_off, post_off;
     int Nt, Nr, channels, max_w_len;
-    int mode;                // 0 = forward (NCSNv2Deepest.forward), 1 = annealed Langevin
+    int mode;                // 0 = forward (NCSNv2Deepest.forward), 1 = annealed Langevin, 2 = denoising-score-matching loss
     int B;
     // forward mode
     const float* fx;         // [B,2,Nt,Nr] with element strides fxs
@@ -49,6 +49,11 @@ struct SbcLaunch {
     float* fout;             // [B,2,Nt,Nr] contiguous
     const float* sigmas;     // [n_sigmas]
     int n_sigmas;
+    // DSM-loss mode (ncsnv2/losses/dsm.py:6-32): fx = clean samples, dsm_z = the randn draw [B,2,Nt,Nr] contiguous,
+    // labels as in forward mode; dsm_out[b] = 1/2 * sum((score - target)^2) * sigma^anneal_power
+    const float* dsm_z;
+    float* dsm_out;
+    float anneal_power;
     // ALD mode
     int Np, level_begin, level_end, steps_each;
     const float* P;          // [B,Np,Nt] complex64
@@ -732,10 +737,20 @@ __global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(cons
             }
         } else {
             const float* fx = L.fx + (size_t)b * L.fxs[0];
+            float sg = 0.f;
+            const float* z = nullptr;
+            if (L.mode == 2) {   // perturbed_samples = samples + randn * sigma   (dsm.py:15-17)
+                long long lab = L.labels[b];
+                lab = lab < 0 ? 0 : (lab >= L.n_sigmas ? L.n_sigmas - 1 : lab);
+                sg = L.sigmas[lab];
+                z = L.dsm_z + (size_t)b * L.channels * ne;
+            }
             for (int e = tid; e < ne; e += SBC_NTHREADS) {
                 const int t = e / Nr, r = e - t * Nr;
                 const float* q = fx + t * L.fxs[2] + r * L.fxs[3];
-                reinterpret_cast<float2*>(ax)[e] = make_float2(q[0], q[L.fxs[1]]);
+                float2 v = make_float2(q[0], q[L.fxs[1]]);
+                if (z) { v.x += z[e] * sg; v.y += z[ne + e] * sg; }
+                reinterpret_cast<float2*>(ax)[e] = v;
             }
         }
         __syncthreads();
@@ -847,7 +862,21 @@ __global__ void __launch_bounds__(SBC_NTHREADS, SBC_MINCTAS) sbc_ald_kernel(cons
 
             if (INSTR && do_prof) L.prof[L.n_ops] = clock64();
             const float* net = arena + L.out_off;   // compact (re, im) pairs
-            if (L.mode == 0) {
+            if (L.mode == 2) {
+                // target = -1/sigma^2 * noise;  loss = 1/2 * sum((score - target)^2) * sigma^anneal_power   (dsm.py:19-31)
+                long long lab = L.labels[b];
+                lab = lab < 0 ? 0 : (lab >= L.n_sigmas ? L.n_sigmas - 1 : lab);
+                const float sg = L.sigmas[lab], isg2 = 1.f / (sg * sg);
+                const float* z = L.dsm_z + (size_t)b * L.channels * ne;
+                float part = 0.f;
+                for (int e = tid; e < ne; e += SBC_NTHREADS) {
+                    const float2 v = reinterpret_cast<const float2*>(net)[e];
+                    const float dx = v.x / sg + isg2 * (z[e] * sg), dy = v.y / sg + isg2 * (z[ne + e] * sg);
+                    part += dx * dx + dy * dy;
+                }
+                const float tot = sbc_block_sum(part, s_red, tid);
+                if (tid == 0) L.dsm_out[b] = 0.5f * tot * powf(sg, L.anneal_power);
+            } else if (L.mode == 0) {
                 // score = net / sigmas[y]   (ncsnv2.py:295-298)
                 long long lab = L.labels[b];
                 if (lab < 0) lab = 0;

@@ -130,6 +130,30 @@ class NCSNv2Deepest(nn.Module):
         return out
 
 
+    def dsm_losses(self, samples: torch.Tensor, labels: torch.Tensor, z: torch.Tensor, anneal_power: float = 2.) -> torch.Tensor:
+        """Per-sample denoising-score-matching losses [B] for the clean ``samples`` perturbed by ``z * sigmas[labels]``
+        (reference ``ncsnv2/losses/dsm.py:13-31`` without the final mean), one fused launch, no autograd."""
+        if not samples.is_cuda:
+            raise RuntimeError("NCSNv2Deepest (B200) runs on CUDA tensors only; there is no CPU path")
+        if samples.dim() != 4 or samples.shape[1] != self.channels or z.shape != samples.shape:
+            raise ValueError("expected samples and z of shape [B,%d,Nt,Nr]" % self.channels)
+        B, _, Nt, Nr = samples.shape
+        x = samples.float().contiguous()
+        zz = z.to(device=x.device, dtype=torch.float32).contiguous()
+        y = labels.to(device=x.device, dtype=torch.int64).contiguous()
+        if y.numel() != B:
+            raise ValueError("labels must have one entry per sample")
+        pm = self.packed(Nt, Nr, x.device)
+        out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sbc_dsm_loss(pm.handle, x.data_ptr(), y.data_ptr(), zz.data_ptr(), float(anneal_power),
+                                               out.data_ptr(), B, C.c_void_p(stream)), "sbc_dsm_loss")
+        return out
+
+
 class NCSNv2Deeper(NCSNv2Deepest):
     """Drop-in ``NCSNv2Deeper`` (reference ``ncsnv2/models/ncsnv2.py:94-195``): five encoder stages, two mean-pools, dilated
     stages at a quarter of the input resolution.  Same forward contract; runs on engine 2 (tcgen05), whose C++ planner reads

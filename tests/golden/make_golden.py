@@ -148,7 +148,36 @@ def golden_real_checkpoint(name="real_ckpt_forward.npz"):
     print(name, "reference fp32 vs fp64 relative error per sample", rel)
 
 
+def golden_dsm(name="dsm_val.npz", ngf=8, wseed=1, B=4, H=64, W=16, anneal_power=2.0, seed=77):
+    """anneal_dsm_score_estimation (ncsnv2/losses/dsm.py:6-32) evaluated under no_grad as train_score.py:170-185 does for the
+    validation loss: labels given, the randn_like draw recovered by re-seeding."""
+    from ncsnv2.losses.dsm import anneal_dsm_score_estimation
+    m, _ = ref_model(ngf, wseed, H, W)
+    rng = np.random.default_rng(seed)
+    Hc = synth.cdl_like_channels(B, H, W, seed=seed)
+    samples = torch.from_numpy(np.stack([Hc.real, Hc.imag], 1).astype(np.float32))      # 'H_herm' layout [B,2,Nt,Nr]
+    labels = torch.from_numpy(rng.integers(0, L, B))
+    labels[0], labels[1] = 0, L - 1
+    with torch.no_grad():
+        torch.manual_seed(seed)
+        loss = anneal_dsm_score_estimation(m, samples, m.sigmas, labels, anneal_power)
+        torch.manual_seed(seed)
+        z = torch.randn_like(samples)
+        # per-sample terms, restated from the reference lines to store more than one number
+        us = m.sigmas[labels].view(B, 1, 1, 1)
+        noise = z * us
+        scores = m(samples + noise, labels)
+        per = 0.5 * ((scores.view(B, -1) - (-1 / us ** 2 * noise).view(B, -1)) ** 2).sum(-1) * us.squeeze() ** anneal_power
+        assert torch.allclose(per.mean(), loss, rtol=1e-6), (per.mean(), loss)
+    np.savez_compressed(os.path.join(OUT, name), ngf=ngf, wseed=wseed, samples=samples.numpy(), labels=labels.numpy(),
+                        z=z.numpy(), anneal_power=anneal_power, per_sample=per.numpy(), loss=float(loss))
+    print(name, "loss", float(loss), "per sample", per.numpy())
+
+
 if __name__ == "__main__":
+    golden_dsm()
+    if "--dsm-only" in sys.argv:
+        sys.exit(0)
     golden_real_checkpoint()
     golden_forward("forward_ngf8.npz", 8, 1, 64, 16, [0, 1000, 2310, 17, 2000], [27.0, 0.5, 1.0, 10.0, 0.05])
     golden_forward("forward_ngf8_32x8.npz", 8, 2, 32, 8, [5, 1500], [20.0, 1.0])

@@ -406,3 +406,36 @@ def test_ngf32_train_default_width_matches_oracle(dev, prec):
     Xo, nlo = net.ald(P, Y, X0, H, **kw)
     assert np.abs(X.cpu().numpy() - Xo).max() < 2e-5 * np.abs(Xo).max()
     assert np.allclose(nlog.cpu().numpy(), nlo, rtol=1e-4)
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", 2e-5), ("tf32", 5e-3)])
+def test_dsm_validation_loss_matches_reference_golden_and_oracle(dev, prec, tol):
+    """Fused DSM-loss launch (sbc_dsm_loss: perturb + score network + weighted L2 reduction) against the golden produced
+    by the reference's own anneal_dsm_score_estimation (ncsnv2/losses/dsm.py:6-32) and against the CPU oracle."""
+    from oracle import oracle as orc
+    from score_based_channels_b200 import dsm
+    g = np.load(os.path.join(GOLDEN, "dsm_val.npz"))
+    sd, m = _model(int(g["ngf"]), int(g["wseed"]), dev, prec)
+    tt = lambda a: torch.from_numpy(a).to(dev)
+    per = m.dsm_losses(tt(g["samples"]), tt(g["labels"]), tt(g["z"]), float(g["anneal_power"])).cpu().numpy()
+    assert np.allclose(per, g["per_sample"], rtol=tol), (per, g["per_sample"])
+    ref = orc.OracleNet(sd, int(g["ngf"]), 64, 16).dsm_losses(g["samples"], g["labels"], g["z"], float(g["anneal_power"]))
+    assert np.allclose(per, ref, rtol=tol)
+    # the drop-in function: labels given -> the only draw is randn_like(samples), exactly as in the reference
+    torch.manual_seed(5)
+    loss = dsm.anneal_dsm_score_estimation(m, tt(g["samples"]), m.sigmas, tt(g["labels"]), float(g["anneal_power"]))
+    torch.manual_seed(5)
+    z = torch.randn_like(tt(g["samples"]))
+    assert loss.dim() == 0
+    assert torch.allclose(loss, m.dsm_losses(tt(g["samples"]), tt(g["labels"]), z, float(g["anneal_power"])).mean(), rtol=1e-6)
+    # labels drawn inside (training-style call): finite, and the generator is consumed labels-first like the reference
+    torch.manual_seed(6)
+    l2 = dsm.anneal_dsm_score_estimation(m, tt(g["samples"]), m.sigmas, None, 2.)
+    torch.manual_seed(6)
+    lab = torch.randint(0, m.sigmas.numel(), (4,), device=dev)
+    z2 = torch.randn_like(tt(g["samples"]))
+    assert torch.allclose(l2, m.dsm_losses(tt(g["samples"]), lab, z2, 2.).mean(), rtol=1e-6)
+    # engine 2 declines loudly instead of falling back
+    m2 = make_model(sd, ngf=8, precision="fp16x2").to(dev)
+    with pytest.raises(RuntimeError, match="engine-1"):
+        m2.dsm_losses(tt(g["samples"]), tt(g["labels"]), tt(g["z"]), 2.)

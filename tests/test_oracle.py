@@ -77,3 +77,14 @@ def test_oracle_matches_reference_on_shipped_checkpoint():
     for b in range(out.shape[0]):
         e32, e = _rel(g["out32"][b].astype(np.float64), g["out64"][b]), _rel(out[b], g["out64"][b])
         assert e <= 3 * e32 + 2e-6, (b, e, e32)
+
+
+def test_oracle_dsm_loss_matches_reference_function():
+    """anneal_dsm_score_estimation (reference ncsnv2/losses/dsm.py:6-32, evaluated by the reference itself under no_grad
+    as train_score.py:170-185 does) vs its CPU restatement: per-sample terms and the mean."""
+    g = np.load(os.path.join(GOLDEN, "dsm_val.npz"))
+    sd = params.random_state(int(g["ngf"]), seed=int(g["wseed"]))
+    net = orc.OracleNet(sd, int(g["ngf"]), 64, 16)
+    per = net.dsm_losses(g["samples"], g["labels"], g["z"], float(g["anneal_power"]))
+    assert np.allclose(per, g["per_sample"], rtol=5e-6)
+    assert abs(float(per.mean()) - float(g["loss"])) < 5e-6 * float(g["loss"])
