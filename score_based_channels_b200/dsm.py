@@ -11,7 +11,7 @@ import torch
 
 
 def anneal_dsm_score_estimation(scorenet, samples, sigmas, labels=None, anneal_power=2.):
-    if getattr(scorenet, "training", False) and torch.is_grad_enabled() and any(p.requires_grad for p in scorenet.parameters()):
+    if getattr(scorenet, "training", False) and torch.is_grad_enabled():   # the training call site (train_score.py:145-153)
         raise NotImplementedError("the B200 library evaluates the DSM loss forward only (validation loss); "
                                   "the training backward pass is not implemented")
     if len(sigmas) != scorenet.sigmas.numel():

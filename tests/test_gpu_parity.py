@@ -435,6 +435,13 @@ def test_dsm_validation_loss_matches_reference_golden_and_oracle(dev, prec, tol)
     lab = torch.randint(0, m.sigmas.numel(), (4,), device=dev)
     z2 = torch.randn_like(tt(g["samples"]))
     assert torch.allclose(l2, m.dsm_losses(tt(g["samples"]), lab, z2, 2.).mean(), rtol=1e-6)
+    # the training call site (train mode, autograd on) is refused: there is no backward pass to hand a graph to
+    m.train()
+    with pytest.raises(NotImplementedError, match="forward only"):
+        dsm.anneal_dsm_score_estimation(m, tt(g["samples"]), m.sigmas, None, 2.)
+    with torch.no_grad():   # ... while the validation call site of train_score.py:170-185 (no_grad, any mode) works
+        assert torch.isfinite(dsm.anneal_dsm_score_estimation(m, tt(g["samples"]), m.sigmas, None, 2.))
+    m.eval()
     # engine 2 declines loudly instead of falling back
     m2 = make_model(sd, ngf=8, precision="fp16x2").to(dev)
     with pytest.raises(RuntimeError, match="engine-1"):
