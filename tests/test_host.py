@@ -252,3 +252,25 @@ def test_library_planner_rejects_bad_input():
     bad = {k: v for k, v in sd.items() if k != "res1.0.conv1.weight"}
     with pytest.raises(RuntimeError, match="res1.0.conv1.weight"):
         _library_plan(bad, 8, 64, 16, 256, "tf32x3", -1)
+
+
+REF_H5 = "/root/reference/sample_data/CDL-A_Nt64_Nr16_ULA0.50.h5"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_H5), reason="reference sample data not mounted")
+def test_minimal_hdf5_reader_on_the_shipped_cdl_a_file():
+    """The second on-disk format the reference ships (sample_data/CDL-A_Nt64_Nr16_ULA0.50.h5: chunked, compound complex):
+    read with the bundled minimal HDF5 reader (no h5py / hdf5storage in the image).  QPSK pilots must come out EXACT
+    (+-1/sqrt(2) in both parts) -- any mis-decoded chunk, stride or compound member breaks that -- and the channels finite
+    with the expected power; two element probes pin byte order and axis order."""
+    d = hdf5_min.loadmat_v73(REF_H5)
+    assert set(d.keys()) == {"H", "P"}
+    H, P = np.ascontiguousarray(d["H"]), np.ascontiguousarray(d["P"])
+    assert H.shape == (64, 16, 200) and P.shape == (64, 64, 200) and H.dtype == np.complex128 and P.dtype == np.complex128
+    r = np.float64(1.0) / np.sqrt(np.float64(2.0))
+    assert np.array_equal(np.abs(P.real), np.full(P.shape, r)) and np.array_equal(np.abs(P.imag), np.full(P.shape, r))
+    assert np.isfinite(H.real).all() and np.isfinite(H.imag).all()
+    assert abs(float(np.mean(np.abs(H) ** 2)) - 0.12251568411307497) < 1e-12
+    assert H[0, 0, 0] == complex(-0.26163689087463343, -0.11179212128717307)
+    assert H[63, 15, 199] == complex(0.24750735074003632, -0.0525550311589591)
+    assert P[0, 0, 0] == complex(r, r) and P[63, 63, 199] == complex(-r, -r)
