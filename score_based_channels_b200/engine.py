@@ -13,6 +13,28 @@ ENGINE2_PRECISIONS = ("fp16x2",)      # tcgen05 engine: fp16 hi/lo split operand
 ALL_PRECISIONS = ENGINE2_PRECISIONS + tuple(program.PRECISIONS)
 
 
+def engine1_runs_two_ctas_per_sm(state: Dict[str, np.ndarray], ngf: int, Nt: int, Nr: int, channels: int = 2) -> bool:
+    """True when engine 1's planner (the C++ twin inside the library, host only) picks the two-CTAs-per-SM park plan for
+    this shape -- the regime where engine 1 is the faster engine (the automatic engine choice of NCSNv2Deepest)."""
+    L = _lib.lib()
+    keep, ents = [], (_lib.StateEntry * len(state))()
+    for i, (k, v) in enumerate(state.items()):
+        a = np.ascontiguousarray(v, dtype=np.float32)
+        shp = np.asarray(a.shape if a.ndim else (1,), dtype=np.int64)
+        keep += [a, shp]
+        ents[i] = _lib.StateEntry(k.encode(), a.ctypes.data, shp.ctypes.data, len(shp))
+    h, v = C.c_void_p(), _lib.Plan1View()
+    rc = L.sbc_plan1_build(ents, len(state), ngf, Nt, Nr, channels, int(L.sbc_threads_per_cta()), _lib.PREC_CODE["tf32x3"], -1,
+                           C.byref(h), C.byref(v))
+    if rc != 0:          # shapes engine 1 cannot plan at all (its planner says why): engine 2 decides
+        return False
+    geo = np.ctypeslib.as_array(C.cast(v.geo_table, C.POINTER(C.c_int32)), (v.n_geo, 8))
+    misc = (64 + 2 * int(sum(g[5] - g[0] * g[1] for g in geo)) + 15) // 16 * 16
+    two = v.park_floats > 0 and 4 * v.arena_floats + misc <= program.smem_budget_bytes(2)
+    L.sbc_plan1_free(h)
+    return bool(two)
+
+
 class PackedModel:
     """Owns one ``sbc_model_create`` handle for a (state_dict, ngf, Nt, Nr) on one CUDA device."""
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, params
-from .engine import ENGINE2_PRECISIONS, PackedModel
+from .engine import ALL_PRECISIONS, ENGINE2_PRECISIONS, PackedModel, engine1_runs_two_ctas_per_sm
 
 
 class _Node(nn.Module):
@@ -42,7 +42,11 @@ class NCSNv2Deepest(nn.Module):
       (22 significant bits), fp32 accumulate: fp32-equivalent results;
     * ``"tf32x3"``: engine 1 -- mma.sync tensor cores, 3xTF32 error-compensated products -- fp32-equivalent
       results (the reference disables TF32, ``test_score.py:24-26``);
-    * ``"tf32"``: tensor cores, plain TF32 operands (round to nearest), fp32 accumulate (fastest).
+    * ``"tf32"``: tensor cores, plain TF32 operands (round to nearest), fp32 accumulate (fastest);
+    * ``None`` / ``"auto"`` (default): the faster fp32-equivalent engine for the shape at hand, decided when the model is
+      packed for an (Nt, Nr): engine 1 (``"tf32x3"``) where its two-CTAs-per-SM plan fits (ngf 8 at 64x16 and below:
+      61 vs 31 est/s), engine 2 (``"fp16x2"``) elsewhere (measured on B200: 128x32 14.4 vs 13.6, ngf 16 22.5 vs 18.3,
+      ngf 32 8.6 vs 3.6 est/s).
     The environment variable ``SBC_PRECISION`` overrides the default."""
 
     ARCH = "deepest"
@@ -50,8 +54,10 @@ class NCSNv2Deepest(nn.Module):
     def __init__(self, config, precision: Optional[str] = None):
         super().__init__()
         self.config = config
-        default = "tf32x3" if self.ARCH == "deepest" else "fp16x2"
+        default = "auto" if self.ARCH == "deepest" else "fp16x2"
         self.precision = precision or os.environ.get("SBC_PRECISION", default)
+        if self.precision not in ALL_PRECISIONS + ("auto",):
+            raise ValueError("precision must be one of %s or 'auto'" % (ALL_PRECISIONS,))
         if self.ARCH != "deepest" and self.precision not in ENGINE2_PRECISIONS:
             raise NotImplementedError("%s runs on engine 2 only (precision 'fp16x2'); the engine-1 planner knows "
                                       "NCSNv2Deepest" % type(self).__name__)
@@ -102,7 +108,10 @@ class NCSNv2Deepest(nn.Module):
                 self._packed.close()
                 self._packed, self._packed_key = None, None
             state = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
-            self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels, self.precision)
+            prec = self.precision
+            if prec == "auto":
+                prec = "tf32x3" if engine1_runs_two_ctas_per_sm(state, self.ngf, Nt, Nr, self.channels) else "fp16x2"
+            self._packed = PackedModel(state, self.ngf, Nt, Nr, key[2], self.channels, prec)
             self._packed_key = key
         return self._packed
 

@@ -53,7 +53,7 @@ def main(argv=None):
     parser.add_argument('--mmse_avg', type=int, default=50)
     parser.add_argument('--snr_range', nargs='+', type=float, default=None)
     parser.add_argument('--levels', type=int, default=None, help='run only the first N sigma levels (debug)')
-    parser.add_argument('--precision', type=str, default=None, choices=[None, 'tf32x3', 'tf32'])
+    parser.add_argument('--precision', type=str, default=None, choices=[None, 'auto', 'tf32x3', 'tf32', 'fp16x2'])
     parser.add_argument('--seed', type=int, default=None)
     args = parser.parse_args(argv)
 

@@ -32,7 +32,7 @@ def main(argv=None):
     parser.add_argument('--out_dir', type=str, default=None)
     parser.add_argument('--levels', type=int, default=None)
     parser.add_argument('--num_channels', type=int, default=100)
-    parser.add_argument('--precision', type=str, default=None, choices=[None, 'tf32x3', 'tf32'])
+    parser.add_argument('--precision', type=str, default=None, choices=[None, 'auto', 'tf32x3', 'tf32', 'fp16x2'])
     parser.add_argument('--seed', type=int, default=None)
     parser.add_argument('--no_plot', action='store_true')
     args = parser.parse_args(argv)

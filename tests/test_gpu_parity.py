@@ -446,3 +446,13 @@ def test_dsm_validation_loss_matches_reference_golden_and_oracle(dev, prec, tol)
     m2 = make_model(sd, ngf=8, precision="fp16x2").to(dev)
     with pytest.raises(RuntimeError, match="engine-1"):
         m2.dsm_losses(tt(g["samples"]), tt(g["labels"]), tt(g["z"]), 2.)
+
+
+def test_default_precision_picks_the_faster_engine_per_shape(dev):
+    for ngf, want in ((8, 1), (16, 2)):
+        sd = params.random_state(ngf, seed=2)
+        m = make_model(sd, ngf=ngf).to(dev)          # precision=None -> "auto"
+        assert m.precision == "auto"
+        x = torch.randn(2, 2, 64, 16, device=dev)
+        out = m(x, torch.tensor([0, 2000], device=dev))
+        assert torch.isfinite(out).all() and m.packed(64, 16, dev).info().engine == want

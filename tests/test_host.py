@@ -274,3 +274,11 @@ def test_minimal_hdf5_reader_on_the_shipped_cdl_a_file():
     assert H[0, 0, 0] == complex(-0.26163689087463343, -0.11179212128717307)
     assert H[63, 15, 199] == complex(0.24750735074003632, -0.0525550311589591)
     assert P[0, 0, 0] == complex(r, r) and P[63, 63, 199] == complex(-r, -r)
+
+
+def test_automatic_engine_choice_follows_the_two_cta_plan():
+    """NCSNv2Deepest(precision=None) picks engine 1 exactly where its planner produces the two-CTAs-per-SM plan (host-only
+    query through the library's C++ planner) and the tcgen05 engine elsewhere (measured crossover)."""
+    from score_based_channels_b200 import engine
+    for ngf, Nt, Nr, want in ((8, 64, 16, True), (8, 32, 8, True), (8, 24, 40, True), (8, 128, 32, False), (16, 64, 16, False)):
+        assert engine.engine1_runs_two_ctas_per_sm(params.random_state(ngf, seed=1), ngf, Nt, Nr) is want, (ngf, Nt, Nr)
